@@ -1,0 +1,51 @@
+// Library-internal declarations shared by the translation units of librlt_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/rlt_b200.h"
+
+namespace rlt {
+
+struct EpiParams;
+
+// ---- error plumbing (thread-local message behind rlt_last_error) ----
+int set_error(int code, const char* fmt, ...);
+#define RLT_CHECK_CUDA(expr)                                                                    \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return ::rlt::set_error(RLT_CUDA_ERROR, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                              __FILE__, __LINE__);                                              \
+  } while (0)
+#define RLT_CHECK_LAUNCH() RLT_CHECK_CUDA(cudaGetLastError())
+#define RLT_REQUIRE(cond, code, ...)                          \
+  do {                                                        \
+    if (!(cond)) return ::rlt::set_error((code), __VA_ARGS__); \
+  } while (0)
+#define RLT_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != RLT_OK) return _rc; \
+  } while (0)
+
+int num_sms();
+
+// ---- GEMM front-ends (gemm.cu).  Operands are fp32 containers; on the tensor-core path they
+//      must hold tf32-rounded values unless tma_rounds() is true. ----
+// C[M,N] = A[M,K] * B[N,K]^T with the fused epilogue described by EpiParams.
+int gemm_tn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
+            cudaStream_t stream);
+// C[M,N] += alpha * sum_t A[t,m] * B[t,n]   (A: [T,lda], B: [T,ldb]; C pre-initialised by the caller)
+int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
+            cudaStream_t stream);
+
+// 0 = tcgen05 tensor-core kernels (default), 1 = plain SIMT kernels (validation backend only)
+int gemm_backend();
+// true when the TMA tensor maps are encoded as TFLOAT32 (TMA rounds fp32->tf32 while loading), so
+// producers need not materialise rounded operand copies.
+bool tma_rounds();
+
+}  // namespace rlt

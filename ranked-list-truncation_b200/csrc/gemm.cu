@@ -1,0 +1,350 @@
+// Library plumbing (errors, options, TMA tensor maps) and the GEMM front-ends.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.h"
+#include "gemm_tc.cuh"
+
+namespace rlt {
+
+// ------------------------------------------------------------------------------------------
+// errors / options
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+static int g_gemm_backend = env_int("RLT_GEMM_BACKEND", 0);
+static int g_tma_round = env_int("RLT_TMA_ROUND", 0);
+
+int gemm_backend() { return g_gemm_backend; }
+bool tma_rounds() { return g_tma_round != 0 && g_gemm_backend == 0; }
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA tensor maps.  cuTensorMapEncodeTiled is fetched through the runtime so the library has no
+// link-time dependency on libcuda.so.
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major fp32 matrix [rows, cols] with leading dimension ld (elements); box = box_rows x 32
+// columns (128 B), SWIZZLE_128B, zero fill outside the matrix.
+static int make_tmap(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_rows, bool round_tf32) {
+  EncodeTiledFn fn = encode_fn();
+  RLT_REQUIRE(fn != nullptr, RLT_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from the driver");
+  RLT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld % 4) == 0, RLT_INVALID_ARG,
+              "TMA operand must be 16-byte aligned with a leading dimension that is a multiple of 4 floats "
+              "(ptr=%p ld=%llu)", (const void*)base, (unsigned long long)ld);
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {ld * sizeof(float)};
+  const cuuint32_t box[2] = {32u, box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = fn(out, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RLT_REQUIRE(r == CUDA_SUCCESS, RLT_CUDA_ERROR, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+  return RLT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// SIMT validation backend (same contracts, no tensor cores, exact fp32 FMA)
+// ------------------------------------------------------------------------------------------
+__global__ void gemm_tn_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                    int M, int N, int K, EpiParams ep) {
+  __shared__ float sA[16][65];
+  __shared__ float sB[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, c = i & 15;
+      sA[c][r] = (m0 + r < M && k0 + c < K) ? A[size_t(m0 + r) * lda + k0 + c] : 0.f;
+      sB[c][r] = (n0 + r < N && k0 + c < K) ? B[size_t(n0 + r) * ldb + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty * 4 + i]; b[i] = sB[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const int r = m0 + ty * 4 + i, c = n0 + tx * 4 + j;
+      if (r >= M || c >= N) continue;
+      float v = acc[i][j] * ep.alpha;
+      if (ep.bias) v += ep.bias[c];
+      if (ep.relu) v = fmaxf(v, 0.f);
+      const size_t off = size_t(r) * ep.ldo + c;
+      if (ep.gate_src) v = ep.gate_src[off] > 0.f ? v : 0.f;
+      if (ep.out) {
+        if (ep.accumulate) v += ep.out[off];
+        ep.out[off] = v;
+      }
+      if (ep.out_tf32) ep.out_tf32[off] = to_tf32(v);
+      if (ep.colsum) atomicAdd(ep.colsum + c, v);
+    }
+}
+
+__global__ void gemm_dw_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                    int T, int M, int N, float* __restrict__ C, int ldc, float alpha, int tchunk) {
+  // one thread per (m, n) output, looping over a chunk of tokens; blockIdx.z selects the chunk
+  const int n = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int m = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (m >= M || n >= N) return;
+  const int t0 = blockIdx.z * tchunk, t1 = min(T, t0 + tchunk);
+  float acc = 0.f;
+  for (int t = t0; t < t1; ++t) acc = fmaf(A[size_t(t) * lda + m], B[size_t(t) * ldb + n], acc);
+  atomicAdd(C + size_t(m) * ldc + n, alpha * acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// front-ends
+// ------------------------------------------------------------------------------------------
+template <int BN>
+static int launch_tn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
+                     cudaStream_t stream) {
+  using Cfg = GemmTnCfg<BN>;
+  CUtensorMap tmA, tmB;
+  RLT_TRY(make_tmap(&tmA, A, M, K, lda, Cfg::BM, tma_rounds()));
+  RLT_TRY(make_tmap(&tmB, B, N, K, ldb, BN, tma_rounds()));
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(Cfg::SMEM_BYTES)));
+    attr_set = true;
+  }
+  const int tiles = ((M + Cfg::BM - 1) / Cfg::BM) * (N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tn_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+
+int gemm_tn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
+            cudaStream_t stream) {
+  RLT_REQUIRE(M > 0 && N > 0 && K > 0, RLT_INVALID_ARG, "gemm_tn: empty problem M=%d N=%d K=%d", M, N, K);
+  if (gemm_backend() == 1) {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    gemm_tn_simt_kernel<<<grid, 256, 0, stream>>>(A, lda, B, ldb, M, N, K, ep);
+    RLT_CHECK_LAUNCH();
+    return RLT_OK;
+  }
+  RLT_REQUIRE(N % 32 == 0, RLT_UNSUPPORTED_SHAPE, "gemm_tn: N=%d must be a multiple of 32", N);
+  RLT_REQUIRE(ep.ldo % 4 == 0, RLT_UNSUPPORTED_SHAPE, "gemm_tn: output leading dimension %d must be a multiple of 4",
+              ep.ldo);
+  if (N % 256 == 0) return launch_tn<256>(A, lda, B, ldb, M, N, K, ep, stream);
+  if (N % 128 == 0) return launch_tn<128>(A, lda, B, ldb, M, N, K, ep, stream);
+  if (N % 64 == 0) return launch_tn<64>(A, lda, B, ldb, M, N, K, ep, stream);
+  return launch_tn<32>(A, lda, B, ldb, M, N, K, ep, stream);
+}
+
+template <int BN>
+static int launch_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int N, float* C, int ldc,
+                     float alpha, cudaStream_t stream) {
+  using Cfg = GemmDwCfg<BN>;
+  CUtensorMap tmA, tmB;
+  RLT_TRY(make_tmap(&tmA, A, T, M, lda, Cfg::BT, tma_rounds()));
+  RLT_TRY(make_tmap(&tmB, B, T, N, ldb, Cfg::BT, tma_rounds()));
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_dw_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(Cfg::SMEM_BYTES)));
+    attr_set = true;
+  }
+  const int tiles = ((M + Cfg::BM - 1) / Cfg::BM) * (N / BN);
+  const int num_tb = (T + Cfg::BT - 1) / Cfg::BT;
+  // one wave of CTAs: split the token axis so that tiles * splits ~ #SMs, at least 8 token blocks per split
+  int splits = num_sms() / tiles;
+  if (splits < 1) splits = 1;
+  const int max_splits = (num_tb + 7) / 8;
+  if (splits > max_splits) splits = max_splits;
+  gemm_dw_kernel<BN><<<dim3(tiles, splits), 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, T, M, N, C, ldc, alpha);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+
+int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
+            cudaStream_t stream) {
+  RLT_REQUIRE(T > 0 && M > 0 && N > 0, RLT_INVALID_ARG, "gemm_dw: empty problem T=%d M=%d N=%d", T, M, N);
+  if (gemm_backend() == 1) {
+    const int tchunk = 2048;
+    dim3 grid((N + 15) / 16, (M + 15) / 16, (T + tchunk - 1) / tchunk);
+    gemm_dw_simt_kernel<<<grid, 256, 0, stream>>>(A, lda, B, ldb, T, M, N, C, ldc, alpha, tchunk);
+    RLT_CHECK_LAUNCH();
+    return RLT_OK;
+  }
+  RLT_REQUIRE(N % 32 == 0, RLT_UNSUPPORTED_SHAPE, "gemm_dw: N=%d must be a multiple of 32", N);
+  if (N % 256 == 0) return launch_dw<256>(A, lda, B, ldb, T, M, N, C, ldc, alpha, stream);
+  if (N % 128 == 0) return launch_dw<128>(A, lda, B, ldb, T, M, N, C, ldc, alpha, stream);
+  if (N % 64 == 0) return launch_dw<64>(A, lda, B, ldb, T, M, N, C, ldc, alpha, stream);
+  return launch_dw<32>(A, lda, B, ldb, T, M, N, C, ldc, alpha, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// operand preparation
+// ------------------------------------------------------------------------------------------
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  const size_t n4 = n / 4;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<float4*>(dst)[i] = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+  }
+  for (size_t i = n4 * 4 + size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = to_tf32(src[i]);
+}
+
+__global__ void transpose_round_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[size_t(r) * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[size_t(c) * rows + r] = to_tf32(tile[threadIdx.x][i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// probe: what does a TFLOAT32 tensor map do to fp32 data?
+// ------------------------------------------------------------------------------------------
+__global__ void probe_tma_kernel(const __grid_constant__ CUtensorMap tm, float* __restrict__ dst, int rows) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, 128 * 32 * 4);
+    tma_load_2d(smem, &tm, &bar, 0, 0);
+  }
+  mbar_wait(&bar, 0);
+  for (int i = threadIdx.x; i < rows * 32; i += blockDim.x) {
+    const int r = i >> 5, c = i & 31;
+    dst[i] = *reinterpret_cast<const float*>(smem + sw128_offset(r, c >> 2) + (c & 3) * 4);
+  }
+}
+
+}  // namespace rlt
+
+using namespace rlt;
+
+extern "C" {
+
+const char* rlt_version(void) { return "rlt_b200 0.1.0 (sm_100a)"; }
+const char* rlt_last_error(void) { return g_err; }
+
+int rlt_set_option(const char* key, int value) {
+  if (key == nullptr) return set_error(RLT_INVALID_ARG, "rlt_set_option: null key");
+  if (strcmp(key, "gemm_backend") == 0) { g_gemm_backend = value; return RLT_OK; }
+  if (strcmp(key, "tma_round") == 0) { g_tma_round = value; return RLT_OK; }
+  return set_error(RLT_INVALID_ARG, "rlt_set_option: unknown option '%s'", key);
+}
+int rlt_get_option(const char* key) {
+  if (key == nullptr) return set_error(RLT_INVALID_ARG, "rlt_get_option: null key");
+  if (strcmp(key, "gemm_backend") == 0) return g_gemm_backend;
+  if (strcmp(key, "tma_round") == 0) return g_tma_round;
+  return set_error(RLT_INVALID_ARG, "rlt_get_option: unknown option '%s'", key);
+}
+
+int rlt_round_tf32(const float* src, float* dst, size_t n, rlt_stream_t stream) {
+  RLT_REQUIRE(src && dst, RLT_INVALID_ARG, "rlt_round_tf32: null pointer");
+  if (n == 0) return RLT_OK;
+  RLT_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, RLT_INVALID_ARG,
+              "rlt_round_tf32: pointers must be 16-byte aligned");
+  size_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > size_t(num_sms()) * 8) blocks = size_t(num_sms()) * 8;
+  round_tf32_kernel<<<unsigned(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+
+int rlt_transpose_round_tf32(const float* src, float* dst, int rows, int cols, rlt_stream_t stream) {
+  RLT_REQUIRE(src && dst && rows > 0 && cols > 0, RLT_INVALID_ARG, "rlt_transpose_round_tf32: bad arguments");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_round_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(src, dst, rows, cols);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+
+int rlt_linear(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, float alpha,
+               int relu, rlt_stream_t stream) {
+  RLT_REQUIRE(A && B && C, RLT_INVALID_ARG, "rlt_linear: null pointer");
+  EpiParams ep{};
+  ep.out = C;
+  ep.ldo = N;
+  ep.bias = bias;
+  ep.relu = relu;
+  ep.alpha = alpha;
+  return gemm_tn(A, K, B, K, M, N, K, ep, static_cast<cudaStream_t>(stream));
+}
+
+int rlt_grad_weight(const float* A, const float* B, float* C, int T, int M, int N, float alpha,
+                    rlt_stream_t stream) {
+  RLT_REQUIRE(A && B && C, RLT_INVALID_ARG, "rlt_grad_weight: null pointer");
+  return gemm_dw(A, M, B, N, T, M, N, C, N, alpha, static_cast<cudaStream_t>(stream));
+}
+
+int rlt_probe_tma_tf32(const float* src, float* dst, int rows, rlt_stream_t stream) {
+  RLT_REQUIRE(src && dst && rows > 0 && rows <= 128, RLT_INVALID_ARG, "rlt_probe_tma_tf32: rows must be in [1,128]");
+  CUtensorMap tm;
+  RLT_TRY(make_tmap(&tm, src, rows, 32, 32, 128, true));
+  probe_tma_kernel<<<1, 128, 128 * 32 * 4 + 1024, static_cast<cudaStream_t>(stream)>>>(tm, dst, rows);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+"""tcgen05/TMA GEMM building blocks vs float64 matmul of the tf32-rounded operands (GPU)."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _tf32(x):
+    from rlt_b200 import _lib
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().rlt_round_tf32(_lib.ptr(x), _lib.ptr(out), ctypes.c_size_t(x.numel()), _lib.stream_ptr()),
+               "rlt_round_tf32")
+    return out
+
+
+def test_round_tf32_matches_bit_definition():
+    x = torch.randn(100003, device="cuda") * 3
+    r = _tf32(x)
+    bits = x.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    expect = ((bits + 0x1000) & 0xFFFFE000).to(torch.int64)
+    expect = torch.where(expect >= 2**31, expect - 2**32, expect).to(torch.int32).view(torch.float32)
+    assert torch.equal(r, expect)
+
+
+def test_probe_tma_tfloat32_rounding(capsys):
+    """Records what a TFLOAT32 tensor map does to fp32 data (rna / rn / truncate / nothing)."""
+    from rlt_b200 import _lib
+    x = (torch.randn(128, 32, device="cuda") * 2).contiguous()
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().rlt_probe_tma_tf32(_lib.ptr(x), _lib.ptr(out), 128, _lib.stream_ptr()), "probe")
+    torch.cuda.synchronize()
+    rna = _tf32(x)
+    trunc = (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    kinds = {"identity": torch.equal(out, x), "rna": torch.equal(out, rna), "truncate": torch.equal(out, trunc)}
+    print("TMA TFLOAT32 behaviour:", kinds, "max|out-x|/|x|", ((out - x).abs() / x.abs().clamp_min(1e-30)).max().item())
+    with capsys.disabled():
+        print("\n[probe] TMA TFLOAT32 behaviour:", kinds)
+    assert any(kinds.values()) or ((out - x).abs() <= x.abs() * 2**-10).all()
+
+
+@pytest.mark.parametrize("backend", [1, 0])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (300, 384, 128), (1500, 2048, 128), (777, 128, 2048),
+                                   (19200, 256, 256), (64, 32, 64), (4096, 512, 256)])
+def test_linear(backend, M, N, K):
+    from rlt_b200 import _lib
+    lib = _lib.load()
+    _lib.set_option("gemm_backend", backend)
+    try:
+        g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+        A = _tf32(torch.randn(M, K, device="cuda", generator=g))
+        B = _tf32(torch.randn(N, K, device="cuda", generator=g) / K ** 0.5)
+        bias = torch.randn(N, device="cuda", generator=g)
+        C = torch.full((M, N), float("nan"), device="cuda")
+        _lib.check(lib.rlt_linear(_lib.ptr(A), _lib.ptr(B), _lib.ptr(bias), _lib.ptr(C), M, N, K,
+                                  ctypes.c_float(1.0), 1, _lib.stream_ptr()), "rlt_linear")
+        torch.cuda.synchronize()
+        ref = torch.relu(A.double() @ B.double().t() + bias.double())
+        err = (C.double() - ref).abs().max().item()
+        assert err < 2e-5 * max(1.0, ref.abs().max().item()), (backend, M, N, K, err)
+    finally:
+        _lib.set_option("gemm_backend", 0)
+
+
+@pytest.mark.parametrize("backend", [1, 0])
+@pytest.mark.parametrize("T,M,N", [(256, 128, 128), (1500, 384, 128), (19200, 2048, 128), (5000, 128, 2048),
+                                   (333, 256, 256), (40, 128, 32)])
+def test_grad_weight(backend, T, M, N):
+    from rlt_b200 import _lib
+    lib = _lib.load()
+    _lib.set_option("gemm_backend", backend)
+    try:
+        g = torch.Generator(device="cuda").manual_seed(T + M + N)
+        A = _tf32(torch.randn(T, M, device="cuda", generator=g))
+        B = _tf32(torch.randn(T, N, device="cuda", generator=g))
+        C0 = torch.randn(M, N, device="cuda", generator=g)
+        C = C0.clone()
+        _lib.check(lib.rlt_grad_weight(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), T, M, N, ctypes.c_float(0.5),
+                                       _lib.stream_ptr()), "rlt_grad_weight")
+        torch.cuda.synchronize()
+        ref = C0.double() + 0.5 * (A.double().t() @ B.double())
+        err = (C.double() - ref).abs().max().item()
+        assert err < 3e-5 * max(1.0, ref.abs().max().item()) * max(1.0, (T / 256) ** 0.5), (backend, T, M, N, err)
+    finally:
+        _lib.set_option("gemm_backend", 0)
