@@ -67,6 +67,172 @@ int rlt_grad_weight(const float* A, const float* B, float* C, int T, int M, int 
  * shared-memory image (de-swizzled) to dst.  Used once to learn whether TMA rounds or truncates. */
 int rlt_probe_tma_tf32(const float* src, float* dst, int rows, rlt_stream_t stream);
 
+/* C[M,N] = A[M,K] B[K,N] (B row-major [K,N]; the dX = dY W contraction of a Linear backward). */
+int rlt_linear_nn(const float* A, const float* B, float* C, int M, int N, int K, rlt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Transformer encoder layer (replaces torch.nn.TransformerEncoderLayer.forward/backward as built
+ * at models/Choopy.py:11-12, AttnCut.py:9-10, MtChoopy.py:11-12, MtAttnCut.py:9-10,
+ * MMOECut.py:9-10: post-norm, ReLU, no batch_first => attention ACROSS the lists of a group).    */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct rlt_encoder_desc {
+  int32_t n_groups;    /* G independent attention groups (one reference forward call each)          */
+  int32_t group_size;  /* S lists per group (the reference's batch size B of one call)              */
+  int32_t seq_len;     /* L positions per list                                                       */
+  int32_t d_model;     /* 128 (Choopy family) or 256 (AttnCut family / experts)                      */
+  int32_t n_head;
+  int32_t d_ff;        /* 2048 (torch default dim_feedforward)                                       */
+  int32_t attend_axis; /* 0 = across lists (reference); 1 = within a list (not implemented)          */
+  int32_t training;    /* reserved                                                                   */
+  float ln_eps;        /* 1e-5                                                                       */
+  float dropout_p;     /* must be 0 for now                                                          */
+  uint64_t dropout_seed;
+} rlt_encoder_desc;
+
+/* nn.TransformerEncoderLayer parameters in state_dict order (all fp32 device pointers). */
+typedef struct rlt_encoder_weights {
+  const float* in_proj_w;  /* self_attn.in_proj_weight [3d, d]  */
+  const float* in_proj_b;  /* self_attn.in_proj_bias   [3d]     */
+  const float* out_proj_w; /* self_attn.out_proj.weight [d, d]  */
+  const float* out_proj_b; /* self_attn.out_proj.bias   [d]     */
+  const float* lin1_w;     /* linear1.weight [d_ff, d]          */
+  const float* lin1_b;     /* linear1.bias   [d_ff]             */
+  const float* lin2_w;     /* linear2.weight [d, d_ff]          */
+  const float* lin2_b;     /* linear2.bias   [d]                */
+  const float* norm1_w;    /* norm1.weight [d]                  */
+  const float* norm1_b;
+  const float* norm2_w;
+  const float* norm2_b;
+} rlt_encoder_weights;
+
+/* gradient accumulators, same shapes; the backward ADDS into them (zero them or pass .grad). */
+typedef struct rlt_encoder_grads {
+  float* in_proj_w;
+  float* in_proj_b;
+  float* out_proj_w;
+  float* out_proj_b;
+  float* lin1_w;
+  float* lin1_b;
+  float* lin2_w;
+  float* lin2_b;
+  float* norm1_w;
+  float* norm1_b;
+  float* norm2_w;
+  float* norm2_b;
+} rlt_encoder_grads;
+
+size_t rlt_encoder_layer_saved_bytes(const rlt_encoder_desc* desc);
+size_t rlt_encoder_layer_workspace_bytes(const rlt_encoder_desc* desc);
+/* x, out: [G*S*L, d].  `saved` receives the activations the backward needs. */
+int rlt_encoder_layer_fwd(const rlt_encoder_desc* desc, const rlt_encoder_weights* w, const float* x, float* out,
+                          void* saved, size_t saved_bytes, rlt_stream_t stream);
+/* d_x may alias d_out.  workspace: rlt_encoder_layer_workspace_bytes(). */
+int rlt_encoder_layer_bwd(const rlt_encoder_desc* desc, const rlt_encoder_weights* w, const rlt_encoder_grads* gw,
+                          const float* x, const void* saved, const float* d_out, float* d_x, void* workspace,
+                          size_t workspace_bytes, rlt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Choopy input assembly (models/Choopy.py:18-20, MtChoopy.py:24-25) and its table gradient.     */
+/* ------------------------------------------------------------------------------------------ */
+int rlt_choopy_embed_fwd(const float* score /*[B,L]*/, const float* pe /*[L,127]*/, float* x /*[B,L,128]*/,
+                         int n_lists, int seq_len, rlt_stream_t stream);
+int rlt_choopy_embed_bwd(const float* dx /*[B,L,128]*/, float* dpe /*[L,127], +=*/, int n_lists, int seq_len,
+                         rlt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Linear(d, 1) heads (decison_layer.0 / classi.0 / rerank / tower layers): z[h, t] = x[t] . w[h] + b[h] */
+/* ------------------------------------------------------------------------------------------ */
+int rlt_head_dots_fwd(const float* x /*[T,d]*/, const float* w /*[H,d]*/, const float* bias /*[H]*/,
+                      float* z /*[H,T]*/, int n_tokens, int d, int n_heads, rlt_stream_t stream);
+/* dx (+)= sum_h dz[h] w[h]; dw += dz^T x; db += sum dz. */
+int rlt_head_dots_bwd(const float* x, const float* w, const float* dz /*[H,T]*/, float* dx, float* dw, float* db,
+                      int n_tokens, int d, int n_heads, int accumulate_dx, rlt_stream_t stream);
+
+/* softmax over the L positions of every list (nn.Softmax(dim=1) of the cut heads) and its backward */
+int rlt_softmax_lists(const float* z, float* p, int n_lists, int seq_len, rlt_stream_t stream);
+int rlt_softmax_lists_bwd(const float* p, const float* dp, float* dz, int n_lists, int seq_len, rlt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K3 — cut losses.  Replaces the B x L Python reward loops and the loss arithmetic of
+ * utils/losses.py:48-68 (ChoopyLoss), :71-96 (AttnCutLoss / RAML), :194-233 (DivLoss kl / js), with
+ * rewards Metric_for_Loss.f1 / .dcg (utils/metrics.py:85-101).                                   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct rlt_cut_loss_desc {
+  int32_t n_lists;
+  int32_t seq_len;         /* <= 1024 */
+  int32_t input_kind;      /* 0: `in` = logits (softmax fused, grad = dL/dlogits); 1: `in` = probabilities (grad = dL/dp) */
+  int32_t loss_kind;       /* 0 ChoopyLoss, 1 AttnCutLoss (RAML), 2 DivLoss 'kl', 3 DivLoss 'js' */
+  int32_t metric_dcg;      /* 0: F1 reward, 1: DCG reward */
+  int32_t accumulate_loss; /* loss_out += instead of = */
+  float tau;               /* reward temperature (0.95 RAML, 0.85 DivLoss augmented, 1.0 otherwise) */
+  float grad_scale;        /* multiplies the gradient (1/B for the reference's batch mean) */
+  float loss_scale;        /* multiplies the summed per-list losses (1/B) */
+} rlt_cut_loss_desc;
+/* probs_out [B,L] (optional), grad [B,L] (optional), loss_per_list [B] (optional scratch/outputs),
+ * loss_out: device scalar (optional; deterministic single-CTA reduction of loss_per_list). */
+int rlt_cut_loss(const rlt_cut_loss_desc* desc, const float* in, const float* labels, float* probs_out, float* grad,
+                 float* loss_per_list, float* loss_out, rlt_stream_t stream);
+/* Upload the DCG coefficient tables built on the host with math.log(j+2, 2) (utils/metrics.py:7). */
+int rlt_set_dcg_tables(const float* coef32_host, const double* term64_host, int n);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K4 — cut selection + metrics.  Replaces run.py:131-142 (argmax / BiCut rule) and Metric.f1 / Metric.dcg
+ * (utils/metrics.py:15-38) per list; the Python wrapper takes np.mean on the host.              */
+/* ------------------------------------------------------------------------------------------ */
+/* mode 0: probs [B,L]; mode 1 (BiCut): probs [B,L,2].  Outputs optional: k, count of relevant in the cut,
+ * number of relevant in the list, F1 and DCG as float64 with numpy's arithmetic. */
+int rlt_eval_cut(const float* probs, const float* labels, int n_lists, int seq_len, int mode, int32_t* k_out,
+                 int32_t* count_out, int32_t* nrel_out, double* f1_out, double* dcg_out, rlt_stream_t stream);
+
+/* Same metrics for caller-supplied cut positions (the Metric.f1 / Metric.dcg signature, utils/metrics.py:15,26).
+ * pyint_in[b] = 1 marks a k that was a Python int in the reference (float32 precision, run.py:135). */
+int rlt_eval_given_k(const float* labels, const int32_t* k_in, const int32_t* pyint_in, int n_lists, int seq_len,
+                     int32_t* count_out, int32_t* nrel_out, double* f1_out, double* dcg_out, rlt_stream_t stream);
+/* Reward matrix r[b, j] = Metric_for_Loss.f1 / .dcg (label_b, k = j+1)  (utils/metrics.py:85-101). */
+int rlt_reward_matrix(const float* labels, float* rewards, int n_lists, int seq_len, int metric_dcg,
+                      rlt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Auxiliary heads of MtCutLoss (utils/losses.py:164-191): BCELoss on the class head and RerankLoss
+ * (utils/losses.py:99-141) on the rerank head, per group (both are batch-global in the reference). */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct rlt_aux_loss_desc {
+  int32_t n_groups;
+  int32_t group_size;
+  int32_t seq_len;
+  int32_t rerank_softmax;  /* 1: rerank head output is softmax over positions (MMOECut TowerRerank) */
+  int32_t class_probs;     /* 1: zc already holds sigmoid outputs and dzc is the gradient w.r.t. them (API boundary) */
+  int32_t accumulate_loss;
+  float margin;            /* 5e-4 */
+  float class_weight;
+  float rerank_weight;
+  float grad_scale;        /* 1 / n_groups when averaging group losses */
+  float loss_scale;
+} rlt_aux_loss_desc;
+/* zc / zr: class / rerank head LOGITS [G*S, L] (either may be NULL).  probs_c: sigmoid(zc) (optional);
+ * out_r: softmax(zr) when rerank_softmax (required then).  status[g] = 1 when a group has no relevant or
+ * no irrelevant document (the reference raises RuntimeError there; the wrapper does too). */
+int rlt_aux_heads_loss(const rlt_aux_loss_desc* desc, const float* zc, const float* zr, const float* labels,
+                       float* probs_c, float* out_r, float* dzc, float* dzr, float* loss_group, int32_t* status,
+                       float* loss_out, rlt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* BiCut head loss (utils/losses.py:11-45).                                                       */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct rlt_bicut_loss_desc {
+  int32_t n_lists;
+  int32_t seq_len;
+  int32_t input_kind;      /* 0: u = 2-class logits, 1: u = probabilities (reference API boundary) */
+  int32_t metric_nci;      /* 1: the 'nci' weights (losses.py:39), 0: the alpha / r weights (:41) */
+  int32_t accumulate_loss;
+  float alpha;             /* 0.65 */
+  float r;                 /* 0.0971134020 */
+  float grad_scale;
+  float loss_scale;
+} rlt_bicut_loss_desc;
+int rlt_bicut_loss(const rlt_bicut_loss_desc* desc, const float* u /*[B,L,2]*/, const float* labels,
+                   float* probs_out, float* grad, float* loss_per_list, float* loss_out, rlt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,203 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (oracle/refshim.py) in this container.
+
+Run once here (the reference tree does not exist on the GPU box):  python -m oracle.make_golden
+Fixtures are small: inputs, labels, outputs, loss and gradient DIGESTS.  The weights themselves are
+not stored: they are re-created on any machine by seeding torch's CPU generator (torch.manual_seed)
+and constructing the same torch submodules in the same order as the reference constructors; a
+checksum of every state_dict entry is stored so a test can prove the weights were reproduced.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "ranked-list-truncation_b200"))
+
+from oracle import refshim  # noqa: E402
+from rlt_b200.data import synthetic_lists  # noqa: E402
+
+GOLDEN = ROOT / "tests" / "golden"
+WEIGHT_SEED = 1234
+DATA_SEED = 20240229
+
+# model name -> (reference class name, ctor kwargs, feature count, criterion builder name)
+MODELS = {
+    "bicut": ("BiCut", dict(input_size=3, dropout=0.0), 3),
+    "choopy": ("Choopy", dict(seq_len=300, dropout=0.0), 1),
+    "attncut": ("AttnCut", dict(input_size=3, dropout=0.0), 3),
+    "mtchoopy": ("MtChoopy", dict(seq_len=300, num_tasks=3, dropout=0.0), 1),
+    "mtattncut": ("MtAttnCut", dict(input_size=3, num_tasks=3, dropout=0.0), 3),
+    "mmoecut": ("MMOECut", dict(seq_len=300, num_tasks=3, input_size=3, dropout=0.0, num_experts=3), 3),
+}
+
+
+def digest(t: torch.Tensor, rng: np.random.Generator, n: int = 512) -> dict:
+    """Compact description of a tensor: norms + a fixed random subsample (full copy if it is small)."""
+    a = t.detach().double().numpy().ravel()
+    idx = np.arange(a.size) if a.size <= n else np.sort(rng.choice(a.size, size=n, replace=False))
+    return {"l2": np.float64(np.sqrt((a * a).sum())), "sum": np.float64(a.sum()), "absmax": np.float64(np.abs(a).max()),
+            "idx": idx.astype(np.int64), "val": a[idx].astype(np.float64), "size": np.int64(a.size)}
+
+
+def build_criterion(ref_losses, name: str, metric: str):
+    # the dispatch of reference run.py:59-102 with its CLI defaults (div_type='js', augmented reward)
+    if name == "bicut":
+        return ref_losses.BiCutLoss(metric=metric)
+    if name == "choopy":
+        return ref_losses.ChoopyLoss(metric=metric)
+    if name == "attncut":
+        return ref_losses.DivLoss(metric=metric, div_type="js", augmented=True)
+    if name in ("mtchoopy", "mtattncut"):
+        return ref_losses.MtCutLoss(metric=metric, rerank_weight=0.5, classi_weight=0.5, num_tasks=3)
+    return ref_losses.MtCutLoss(metric=metric, num_tasks=3)
+
+
+def model_goldens(ref_models, ref_losses):
+    for name, (cls_name, kwargs, feats) in MODELS.items():
+        for B in (5, 16):
+            torch.manual_seed(WEIGHT_SEED)
+            model = getattr(ref_models, cls_name)(**kwargs)
+            model.train()  # dropout = 0: train mode is deterministic and matches what run.py trains with
+            x, y = synthetic_lists(B, 300, feats, seed=DATA_SEED + B, device="cpu")
+            out = model(x)
+            torch.manual_seed(0)  # MtCutLoss draws an (unused) random Parameter
+            crit = build_criterion(ref_losses, name, "f1")
+            loss = crit(out, y)
+            loss.backward()
+            rng = np.random.default_rng(7)
+            rec = {"x": x.numpy(), "y": y.numpy(), "loss": np.float64(loss.item())}
+            outs = out if isinstance(out, (list, tuple)) else [out]
+            for i, o in enumerate(outs):
+                rec[f"out{i}"] = o.detach().numpy()
+            rec["n_out"] = np.int64(len(outs))
+            names = []
+            for pname, p in model.named_parameters():
+                names.append(pname)
+                d = digest(p.grad if p.grad is not None else torch.zeros_like(p), rng)
+                for k, v in d.items():
+                    rec[f"grad/{pname}/{k}"] = v
+                rec[f"wsum/{pname}"] = np.float64(p.detach().double().sum().item())
+                rec[f"wabs/{pname}"] = np.float64(p.detach().double().abs().sum().item())
+            rec["param_names"] = np.array(names)
+            # float64 truth from the same reference module (tighter target for tolerance accounting)
+            m64 = getattr(ref_models, cls_name)(**kwargs).double()
+            m64.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+            m64.train()
+            out64 = m64(x.double())
+            outs64 = out64 if isinstance(out64, (list, tuple)) else [out64]
+            for i, o in enumerate(outs64):
+                rec[f"out{i}_f64"] = o.detach().numpy()
+            np.savez_compressed(GOLDEN / f"model_{name}_B{B}.npz", **rec)
+            print(f"model_{name}_B{B}: loss={loss.item():.8f}")
+
+
+def loss_goldens(ref_losses):
+    """Every loss class on random probabilities / labels: value and gradient w.r.t. the model output."""
+    rec = {}
+    for (B, L) in ((4, 300), (3, 40)):
+        x, y = synthetic_lists(B, L, 1, seed=DATA_SEED + 100 + L, device="cpu")
+        if L == 300:
+            y[1] = 0.0  # a list without any relevant document (N_D = 0 branch of Metric_for_Loss.f1)
+        g = torch.Generator().manual_seed(99 + L)
+        z = torch.randn(B, L, 1, generator=g) * 2
+        rec[f"y_{L}"] = y.numpy()
+        rec[f"z_{L}"] = z.numpy()
+        for metric in ("f1", "dcg"):
+            cases = {
+                "choopy": lambda: ref_losses.ChoopyLoss(metric=metric),
+                "raml": lambda: ref_losses.AttnCutLoss(metric=metric),
+                "kl": lambda: ref_losses.DivLoss(metric=metric, div_type="kl", augmented=True),
+                "js": lambda: ref_losses.DivLoss(metric=metric, div_type="js", augmented=True),
+                "js_noaug": lambda: ref_losses.DivLoss(metric=metric, div_type="js", augmented=False),
+            }
+            for cname, make in cases.items():
+                zz = z.clone().requires_grad_(True)
+                p = torch.softmax(zz, dim=1)
+                p.retain_grad()
+                loss = make()(p, y)
+                loss.backward()
+                key = f"{cname}_{metric}_{L}"
+                rec[key + "/loss"] = np.float64(loss.item())
+                rec[key + "/dp"] = p.grad.numpy()
+                rec[key + "/dz"] = zz.grad.numpy()
+        # reward matrices straight from Metric_for_Loss
+        from oracle import refshim as _r
+        _, _, ref_metrics = _r.load()
+        for metric in ("f1", "dcg"):
+            r = torch.zeros(B, L)
+            fn = getattr(ref_metrics.Metric_for_Loss, metric)
+            for i in range(B):
+                for j in range(L):
+                    r[i, j] = fn(y[i], j + 1)
+            rec[f"reward_{metric}_{L}"] = r.numpy()
+        # auxiliary heads
+        base = torch.randn(B, L, 1, generator=g)
+        for tag, shift in (("active", -0.5), ("inactive", 0.5)):   # hinge on / hinge off (zero leaf, no grad)
+            s = (base + shift * y.unsqueeze(2)).requires_grad_(True)
+            rl = ref_losses.RerankLoss()(s, y)
+            rl.backward()
+            rec[f"rerank_{tag}_{L}/s"] = s.detach().numpy()
+            rec[f"rerank_{tag}_{L}/loss"] = np.float64(rl.item())
+            rec[f"rerank_{tag}_{L}/ds"] = (s.grad if s.grad is not None else torch.zeros_like(s)).numpy()
+        # BiCut loss on random 2-class outputs
+        u = torch.randn(B, L, 2, generator=g, requires_grad=True)
+        o = torch.softmax(u, dim=2)
+        o.retain_grad()
+        for metric in ("f1", "nci"):
+            if o.grad is not None:
+                o.grad = None
+                u.grad = None
+            bl = ref_losses.BiCutLoss(metric=metric)(o, y)
+            bl.backward(retain_graph=True)
+            rec[f"bicut_{metric}_{L}/loss"] = np.float64(bl.item())
+            rec[f"bicut_{metric}_{L}/do"] = o.grad.numpy().copy()
+        rec[f"bicut_{L}/u"] = u.detach().numpy()
+    np.savez_compressed(GOLDEN / "losses.npz", **rec)
+    print("losses.npz written")
+
+
+def metric_goldens(ref_metrics):
+    rec = {}
+    # the reference's only known-answer vector (utils/metrics.py:104-109)
+    x = np.array([[1, 0, 1], [0, 0, 1], [1, 0, 0]])
+    k = np.array([1, 2, 1])
+    rec["known/f1"] = np.float64(ref_metrics.Metric.f1(x, k))
+    rec["known/dcg"] = np.float64(ref_metrics.Metric.dcg(x, k))
+    for (B, L) in ((64, 300), (7, 40)):
+        _, y = synthetic_lists(B, L, 1, seed=DATA_SEED + 7 + L, device="cpu")
+        y = y.numpy()
+        y[3] = 0.0
+        rng = np.random.default_rng(5 + L)
+        p = rng.random((B, L), dtype=np.float32)
+        p[5, 10] = p[5, L - 3] = 2.0  # a tie: first maximum wins
+        ks = np.argmax(p, axis=1) + 1
+        ks[0], ks[1] = 1, L
+        rec[f"y_{L}"], rec[f"p_{L}"], rec[f"k_{L}"] = y, p, ks
+        rec[f"f1_{L}"] = np.array([ref_metrics.Metric.f1(y[i:i + 1], ks[i:i + 1]) for i in range(B)], dtype=np.float64)
+        rec[f"dcg_{L}"] = np.array([ref_metrics.Metric.dcg(y[i:i + 1], ks[i:i + 1]) for i in range(B)], dtype=np.float64)
+        rec[f"f1_mean_{L}"] = np.float64(ref_metrics.Metric.f1(y, ks))
+        rec[f"dcg_mean_{L}"] = np.float64(ref_metrics.Metric.dcg(y, ks))
+        # every cut position of one list (exercises all pairwise-summation lengths)
+        all_k = np.arange(1, L + 1)
+        rec[f"dcg_allk_{L}"] = np.array([ref_metrics.Metric.dcg(y[2:3], all_k[j:j + 1]) for j in range(L)], dtype=np.float64)
+        rec[f"f1_allk_{L}"] = np.array([ref_metrics.Metric.f1(y[2:3], all_k[j:j + 1]) for j in range(L)], dtype=np.float64)
+    np.savez_compressed(GOLDEN / "metrics.npz", **rec)
+    print("metrics.npz written", rec["known/f1"], rec["known/dcg"])
+
+
+def main():
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    ref_models, ref_losses, ref_metrics = refshim.load()
+    torch.set_num_threads(8)
+    metric_goldens(ref_metrics)
+    loss_goldens(ref_losses)
+    model_goldens(ref_models, ref_losses)
+
+
+if __name__ == "__main__":
+    main()

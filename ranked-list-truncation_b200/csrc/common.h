@@ -38,6 +38,9 @@ int num_sms();
 // C[M,N] = A[M,K] * B[N,K]^T with the fused epilogue described by EpiParams.
 int gemm_tn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
             cudaStream_t stream);
+// C[M,N] = A[M,K] * B[K,N]   (B row-major [K,N]: dX = dY W with the nn.Linear weight used as stored)
+int gemm_nn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
+            cudaStream_t stream);
 // C[M,N] += alpha * sum_t A[t,m] * B[t,n]   (A: [T,lda], B: [T,ldb]; C pre-initialised by the caller)
 int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
             cudaStream_t stream);

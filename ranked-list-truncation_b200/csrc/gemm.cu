@@ -27,7 +27,10 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 static int g_gemm_backend = env_int("RLT_GEMM_BACKEND", 0);
-static int g_tma_round = env_int("RLT_TMA_ROUND", 0);
+// Measured on B200 (tests/test_gemm_gpu.py::test_probe_tma_tfloat32_rounding): a TFLOAT32 tensor map makes
+// TMA round fp32 -> tf32 with round-to-nearest-ties-away (bit-identical to cvt.rna.tf32.f32) while it
+// fills shared memory, so operands stay exact fp32 in HBM and no rounded copies are materialised.
+static int g_tma_round = env_int("RLT_TMA_ROUND", 1);
 
 int gemm_backend() { return g_gemm_backend; }
 bool tma_rounds() { return g_tma_round != 0 && g_gemm_backend == 0; }
@@ -67,7 +70,7 @@ static EncodeTiledFn encode_fn() {
 // 2-D row-major fp32 matrix [rows, cols] with leading dimension ld (elements); box = box_rows x 32
 // columns (128 B), SWIZZLE_128B, zero fill outside the matrix.
 static int make_tmap(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                     uint32_t box_rows, bool round_tf32) {
+                     uint32_t box_rows, bool round_tf32, bool atom32 = false) {
   EncodeTiledFn fn = encode_fn();
   RLT_REQUIRE(fn != nullptr, RLT_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from the driver");
   RLT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld % 4) == 0, RLT_INVALID_ARG,
@@ -79,7 +82,8 @@ static int make_tmap(CUtensorMap* out, const float* base, uint64_t rows, uint64_
   const cuuint32_t estr[2] = {1u, 1u};
   const CUresult r = fn(out, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                         const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RLT_REQUIRE(r == CUDA_SUCCESS, RLT_CUDA_ERROR, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
   return RLT_OK;
@@ -89,7 +93,7 @@ static int make_tmap(CUtensorMap* out, const float* base, uint64_t rows, uint64_
 // SIMT validation backend (same contracts, no tensor cores, exact fp32 FMA)
 // ------------------------------------------------------------------------------------------
 __global__ void gemm_tn_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                    int M, int N, int K, EpiParams ep) {
+                                    int M, int N, int K, EpiParams ep, int b_major_n) {
   __shared__ float sA[16][65];
   __shared__ float sB[16][65];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -99,7 +103,9 @@ __global__ void gemm_tn_simt_kernel(const float* __restrict__ A, int lda, const 
     for (int i = threadIdx.x; i < 64 * 16; i += 256) {
       const int r = i >> 4, c = i & 15;
       sA[c][r] = (m0 + r < M && k0 + c < K) ? A[size_t(m0 + r) * lda + k0 + c] : 0.f;
-      sB[c][r] = (n0 + r < N && k0 + c < K) ? B[size_t(n0 + r) * ldb + k0 + c] : 0.f;
+      sB[c][r] = (n0 + r < N && k0 + c < K)
+                     ? (b_major_n ? B[size_t(k0 + c) * ldb + n0 + r] : B[size_t(n0 + r) * ldb + k0 + c])
+                     : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -123,6 +129,7 @@ __global__ void gemm_tn_simt_kernel(const float* __restrict__ A, int lda, const 
       if (ep.relu) v = fmaxf(v, 0.f);
       const size_t off = size_t(r) * ep.ldo + c;
       if (ep.gate_src) v = ep.gate_src[off] > 0.f ? v : 0.f;
+      if (ep.residual) v += ep.residual[off];
       if (ep.out) {
         if (ep.accumulate) v += ep.out[off];
         ep.out[off] = v;
@@ -147,42 +154,53 @@ __global__ void gemm_dw_simt_kernel(const float* __restrict__ A, int lda, const 
 // ------------------------------------------------------------------------------------------
 // front-ends
 // ------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool kBMajorN>
 static int launch_tn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
                      cudaStream_t stream) {
   using Cfg = GemmTnCfg<BN>;
   CUtensorMap tmA, tmB;
   RLT_TRY(make_tmap(&tmA, A, M, K, lda, Cfg::BM, tma_rounds()));
-  RLT_TRY(make_tmap(&tmB, B, N, K, ldb, BN, tma_rounds()));
+  if (kBMajorN) RLT_TRY(make_tmap(&tmB, B, K, N, ldb, Cfg::BK, tma_rounds(), true));
+  else RLT_TRY(make_tmap(&tmB, B, N, K, ldb, BN, tma_rounds()));
   static bool attr_set = false;
   if (!attr_set) {
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, kBMajorN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         int(Cfg::SMEM_BYTES)));
     attr_set = true;
   }
   const int tiles = ((M + Cfg::BM - 1) / Cfg::BM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tn_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+  gemm_tn_kernel<BN, kBMajorN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }
 
-int gemm_tn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
-            cudaStream_t stream) {
-  RLT_REQUIRE(M > 0 && N > 0 && K > 0, RLT_INVALID_ARG, "gemm_tn: empty problem M=%d N=%d K=%d", M, N, K);
+template <bool kBMajorN>
+static int gemm_any(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
+                    cudaStream_t stream) {
+  RLT_REQUIRE(M > 0 && N > 0 && K > 0, RLT_INVALID_ARG, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   if (gemm_backend() == 1) {
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    gemm_tn_simt_kernel<<<grid, 256, 0, stream>>>(A, lda, B, ldb, M, N, K, ep);
+    gemm_tn_simt_kernel<<<grid, 256, 0, stream>>>(A, lda, B, ldb, M, N, K, ep, kBMajorN ? 1 : 0);
     RLT_CHECK_LAUNCH();
     return RLT_OK;
   }
-  RLT_REQUIRE(N % 32 == 0, RLT_UNSUPPORTED_SHAPE, "gemm_tn: N=%d must be a multiple of 32", N);
-  RLT_REQUIRE(ep.ldo % 4 == 0, RLT_UNSUPPORTED_SHAPE, "gemm_tn: output leading dimension %d must be a multiple of 4",
+  RLT_REQUIRE(N % 32 == 0, RLT_UNSUPPORTED_SHAPE, "gemm: N=%d must be a multiple of 32", N);
+  RLT_REQUIRE(ep.ldo % 4 == 0, RLT_UNSUPPORTED_SHAPE, "gemm: output leading dimension %d must be a multiple of 4",
               ep.ldo);
-  if (N % 256 == 0) return launch_tn<256>(A, lda, B, ldb, M, N, K, ep, stream);
-  if (N % 128 == 0) return launch_tn<128>(A, lda, B, ldb, M, N, K, ep, stream);
-  if (N % 64 == 0) return launch_tn<64>(A, lda, B, ldb, M, N, K, ep, stream);
-  return launch_tn<32>(A, lda, B, ldb, M, N, K, ep, stream);
+  if (N % 256 == 0) return launch_tn<256, kBMajorN>(A, lda, B, ldb, M, N, K, ep, stream);
+  if (N % 128 == 0) return launch_tn<128, kBMajorN>(A, lda, B, ldb, M, N, K, ep, stream);
+  if (N % 64 == 0) return launch_tn<64, kBMajorN>(A, lda, B, ldb, M, N, K, ep, stream);
+  return launch_tn<32, kBMajorN>(A, lda, B, ldb, M, N, K, ep, stream);
+}
+
+int gemm_tn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
+            cudaStream_t stream) {
+  return gemm_any<false>(A, lda, B, ldb, M, N, K, ep, stream);
+}
+int gemm_nn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
+            cudaStream_t stream) {
+  return gemm_any<true>(A, lda, B, ldb, M, N, K, ep, stream);
 }
 
 template <int BN>
@@ -190,8 +208,8 @@ static int launch_dw(const float* A, int lda, const float* B, int ldb, int T, in
                      float alpha, cudaStream_t stream) {
   using Cfg = GemmDwCfg<BN>;
   CUtensorMap tmA, tmB;
-  RLT_TRY(make_tmap(&tmA, A, T, M, lda, Cfg::BT, tma_rounds()));
-  RLT_TRY(make_tmap(&tmB, B, T, N, ldb, Cfg::BT, tma_rounds()));
+  RLT_TRY(make_tmap(&tmA, A, T, M, lda, Cfg::BT, tma_rounds(), true));
+  RLT_TRY(make_tmap(&tmB, B, T, N, ldb, Cfg::BT, tma_rounds(), true));
   static bool attr_set = false;
   if (!attr_set) {
     RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_dw_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -330,6 +348,15 @@ int rlt_linear(const float* A, const float* B, const float* bias, float* C, int 
   ep.relu = relu;
   ep.alpha = alpha;
   return gemm_tn(A, K, B, K, M, N, K, ep, static_cast<cudaStream_t>(stream));
+}
+
+int rlt_linear_nn(const float* A, const float* B, float* C, int M, int N, int K, rlt_stream_t stream) {
+  RLT_REQUIRE(A && B && C, RLT_INVALID_ARG, "rlt_linear_nn: null pointer");
+  EpiParams ep{};
+  ep.out = C;
+  ep.ldo = N;
+  ep.alpha = 1.f;
+  return gemm_nn(A, K, B, N, M, N, K, ep, static_cast<cudaStream_t>(stream));
 }
 
 int rlt_grad_weight(const float* A, const float* B, float* C, int T, int M, int N, float alpha,

@@ -20,6 +20,7 @@ struct EpiParams {
   int ldo;
   const float* bias;      // [N] added to every row (may be null)
   const float* gate_src;  // [M, ldo]: result *= (gate_src > 0)   (ReLU backward; may be null)
+  const float* residual;  // [M, ldo]: result += residual          (skip connections; may be null)
   float* colsum;          // [N]: atomicAdd of the column sums of the final values (bias grads; may be null)
   int relu;               // max(x, 0)
   int accumulate;         // out += result instead of out = result
@@ -81,6 +82,13 @@ __device__ __forceinline__ void epilogue_store_chunk(const EpiParams& ep, float 
       v[4 * j4 + 3] = g.w > 0.f ? v[4 * j4 + 3] : 0.f;
     }
   }
+  if (ep.residual != nullptr && row_ok) {
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(ep.residual + off) + j4);
+      v[4 * j4 + 0] += r.x; v[4 * j4 + 1] += r.y; v[4 * j4 + 2] += r.z; v[4 * j4 + 3] += r.w;
+    }
+  }
   if (row_ok) {
     if (ep.out != nullptr) {
       float4* o = reinterpret_cast<float4*>(ep.out + off);
@@ -113,7 +121,10 @@ __device__ __forceinline__ void epilogue_store_chunk(const EpiParams& ep, float 
   }
 }
 
-template <int BN>
+// kBMajorN = false: B is [N, K] row-major (K-major operand, nn.Linear weight used as-is: x W^T).
+// kBMajorN = true : B is [K, N] row-major (MN-major operand: x W with W stored [K, N]); its stage is
+//                   BN/32 boxes of 32 k-rows x 32 columns in the SWIZZLE_128B_BASE32B layout.
+template <int BN, bool kBMajorN>
 __global__ void __launch_bounds__(192, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                int K, EpiParams ep) {
@@ -163,14 +174,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + size_t(s) * Cfg::STAGE_BYTES;
           tma_load_2d(sa, &tmA, &full[s], kb * Cfg::BK, m0);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], kb * Cfg::BK, n0);
+          if constexpr (!kBMajorN) {
+            tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], kb * Cfg::BK, n0);
+          } else {
+#pragma unroll
+            for (int b = 0; b < BN / 32; ++b)
+              tma_load_2d(sa + Cfg::A_BYTES + b * 4096, &tmB, &full[s], n0 + b * 32, kb * Cfg::BK);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kFmtTF32, Cfg::BM, BN, false, false);
+      constexpr uint32_t idesc = make_idesc(kFmtTF32, Cfg::BM, BN, false, kBMajorN);
       uint32_t it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
@@ -183,10 +200,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + size_t(s) * Cfg::STAGE_BYTES);
           const uint64_t da = make_smem_desc_sw128(a_addr, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(a_addr + Cfg::A_BYTES, 16, 1024);
+          const uint64_t db = kBMajorN ? make_smem_desc_sw128(a_addr + Cfg::A_BYTES, 4096, 512, kLayoutSw128Base32)
+                                       : make_smem_desc_sw128(a_addr + Cfg::A_BYTES, 16, 1024);
+          // per MMA (K = 8): A advances 32 B inside its 128 B row (+2); a K-major B likewise, an
+          // MN-major B advances 8 k-rows = 1024 B (+64)
+          constexpr uint64_t kBStep = kBMajorN ? 64 : 2;
 #pragma unroll
-          for (int k = 0; k < Cfg::BK / 8; ++k)  // 8 tf32 = 32 B per MMA along K: +2 in the address field
-            umma_tf32(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < Cfg::BK / 8; ++k)
+            umma_tf32(d_tmem, da + uint64_t(2 * k), db + kBStep * uint64_t(k), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty[s]);
         }
         umma_commit(&tfull[buf]);
@@ -222,8 +243,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // -----------------------------------------------------------------------------------------------
 // Weight-gradient GEMM:  C[M,N] += sum over tokens t of A[t, m] * B[t, n].
 // A is [T, lda] row-major (M contiguous), B is [T, ldb] row-major (N contiguous): both MN-major.
-// One smem "box" = 32 tokens x 32 columns (128 B rows, SWIZZLE_128B): the UMMA atom is 8 tokens x
-// 128 B, SBO = 1024 B (next 8 tokens), LBO = 4096 B (next 32-column block).
+// One smem "box" = 32 tokens x 32 columns (128 B rows, TMA SWIZZLE_128B_ATOM_32B): the UMMA atom
+// (layout SWIZZLE_128B_BASE32B, the only MN-major layout for 32-bit operands) is 4 tokens x 128 B,
+// SBO = 512 B (next 4 tokens), LBO = 4096 B (next 32-column block); one K=8 MMA spans two atoms.
 // grid = (tiles_m * tiles_n, splits); every CTA reduces a contiguous token range and red.adds its
 // partial tile into C (C must be initialised by the caller: zeros or the running gradient).
 // -----------------------------------------------------------------------------------------------
@@ -305,10 +327,10 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + size_t(s) * Cfg::STAGE_BYTES);
-          const uint64_t da = make_smem_desc_sw128(a_addr, Cfg::BOX_BYTES, 1024);
-          const uint64_t db = make_smem_desc_sw128(a_addr + Cfg::A_BYTES, Cfg::BOX_BYTES, 1024);
+          const uint64_t da = make_smem_desc_sw128(a_addr, Cfg::BOX_BYTES, 512, kLayoutSw128Base32);
+          const uint64_t db = make_smem_desc_sw128(a_addr + Cfg::A_BYTES, Cfg::BOX_BYTES, 512, kLayoutSw128Base32);
 #pragma unroll
-          for (int k = 0; k < Cfg::BT / 8; ++k)  // next 8 tokens = next 1024 B atom: +64 in the address field
+          for (int k = 0; k < Cfg::BT / 8; ++k)  // next 8 tokens = +1024 B: +64 in the address field
             umma_tf32(tmem_base, da + uint64_t(64 * k), db + uint64_t(64 * k), idesc, (i | k) != 0 ? 1u : 0u);
           umma_commit(&empty[s]);
         }

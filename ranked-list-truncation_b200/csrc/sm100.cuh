@@ -126,14 +126,20 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
 // MN-major operand (rows of 128 B = 32 tf32 along M/N, one row per k): an atom is 8 k-rows x 128 B;
 //   SBO = stride between consecutive 8-k groups, LBO = stride between consecutive 32-element MN blocks.
 // ------------------------------------------------------------------------------------------
+//
+// 32-bit MN-major operands may only use layout type 1 (SWIZZLE_128B_BASE32B): rows of 128 B along
+// M/N, the swizzle permutes 32-byte chunks (address bits [5,7) ^= bits [7,9)), an atom is 4 k-rows
+// x 128 B = 512 B; SBO = stride between consecutive 4-k groups, LBO = stride between 32-element MN
+// blocks.  The matching TMA mode is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+enum : uint32_t { kLayoutSw128 = 2, kLayoutSw128Base32 = 1 };
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                         uint32_t sbo_bytes) {
+                                                         uint32_t sbo_bytes, uint32_t layout = kLayoutSw128) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout) << 61;
   return d;
 }
 

@@ -1,0 +1,238 @@
+"""The six truncation model families of the reference behind their original nn.Module API.
+
+Each class builds the SAME torch submodules, in the same order, as the reference constructor it
+mirrors (cited per class).  Those submodules are only parameter holders: this guarantees identical
+parameter names (checkpoints interchange both ways, run.py:208-220), identical shapes and — under
+the same torch seed — identical initial values.  `forward` never calls them; it hands their
+parameters to the CUDA kernels through rlt_b200.autograd.
+
+Train-mode dropout (p > 0) is not implemented yet: modules raise in train() mode unless dropout == 0
+(parity tests and benchmarks use dropout = 0; eval() always works).
+"""
+from __future__ import annotations
+
+import warnings
+
+import torch
+import torch.nn as nn
+
+from rlt_b200 import autograd as F
+from rlt_b200.ops import ENCODER_PARAM_ORDER
+
+
+def _encoder(d_model: int, n_head: int, num_layers: int, dropout: float) -> nn.TransformerEncoder:
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # torch warns that nested tensors need batch_first; irrelevant here
+        layer = nn.TransformerEncoderLayer(d_model=d_model, nhead=n_head, dropout=dropout)
+        return nn.TransformerEncoder(layer, num_layers=num_layers)
+
+
+def _bilstm(input_size: int, hidden: int = 128, layers: int = 2) -> nn.LSTM:
+    return nn.LSTM(input_size=input_size, hidden_size=hidden, num_layers=layers, batch_first=True, bidirectional=True)
+
+
+def _lin_softmax(d_model: int) -> nn.Sequential:
+    return nn.Sequential(nn.Linear(in_features=d_model, out_features=1), nn.Softmax(dim=1))
+
+
+def _lin_sigmoid(d_model: int) -> nn.Sequential:
+    return nn.Sequential(nn.Linear(in_features=d_model, out_features=1), nn.Sigmoid())
+
+
+def _encoder_params(enc: nn.TransformerEncoder):
+    flat = []
+    for layer in enc.layers:
+        named = dict(layer.named_parameters())
+        flat.extend(named[n] for n in ENCODER_PARAM_ORDER)
+    return flat
+
+
+class _Base(nn.Module):
+    _dropout_p = 0.0
+
+    def _check_mode(self):
+        if self.training and self._dropout_p > 0:
+            raise NotImplementedError(
+                f"{type(self).__name__}: train-mode dropout (p={self._dropout_p}) is not implemented on the rlt_b200 "
+                "path yet; construct the model with dropout=0 or call .eval()")
+
+    def _encode(self, x, enc: nn.TransformerEncoder):
+        layer0 = enc.layers[0]
+        return F.EncoderStack.apply(x, layer0.self_attn.num_heads, 1, layer0.norm1.eps, *_encoder_params(enc))
+
+    @staticmethod
+    def _heads(h, linears):
+        """logits [H, B, L] of H Linear(d, 1) heads evaluated in one pass over h."""
+        w = torch.cat([m.weight for m in linears], dim=0)
+        b = torch.cat([m.bias for m in linears], dim=0)
+        return F.HeadDots.apply(h, w, b)
+
+
+class Choopy(_Base):
+    """Reference models/Choopy.py:6-23."""
+
+    def __init__(self, seq_len: int = 300, d_model: int = 128, n_head: int = 8, num_layers: int = 3, dropout=0.2):
+        super().__init__()
+        self.seq_len = seq_len
+        self._dropout_p = float(dropout)
+        self.position_encoding = nn.Parameter(torch.randn(self.seq_len, 127), requires_grad=True)
+        self.attention_layer = _encoder(d_model, n_head, num_layers, dropout)
+        self.decison_layer = _lin_softmax(d_model)
+
+    def forward(self, x):
+        self._check_mode()
+        h = self._encode(F.ChoopyEmbed.apply(x, self.position_encoding), self.attention_layer)
+        z = self._heads(h, [self.decison_layer[0]])
+        return F.SoftmaxLists.apply(z[0]).unsqueeze(2)
+
+
+class MtChoopy(_Base):
+    """Reference models/MtChoopy.py:5-32."""
+
+    def __init__(self, seq_len: int = 300, d_model: int = 128, n_head: int = 8, num_layers: int = 3,
+                 num_tasks: float = 3, dropout: float = 0.4):
+        super().__init__()
+        self.seq_len = seq_len
+        self.num_tasks = num_tasks
+        self._dropout_p = float(dropout)
+        self.position_encoding = nn.Parameter(torch.randn(self.seq_len, 127), requires_grad=True)
+        self.encoding_layer = _encoder(d_model, n_head, num_layers, dropout)
+        self.classi = _lin_sigmoid(d_model)
+        self.rerank = nn.Linear(in_features=d_model, out_features=1)
+        self.decison_layer = _lin_softmax(d_model)
+
+    def forward(self, x):
+        self._check_mode()
+        h = self._encode(F.ChoopyEmbed.apply(x, self.position_encoding), self.encoding_layer)
+        return _mt_outputs(self, h)
+
+
+def _mt_outputs(self, h):
+    """The three heads of MtChoopy / MtAttnCut (MtChoopy.py:27-32, MtAttnCut.py:24-29)."""
+    z = self._heads(h, [self.classi[0], self.rerank, self.decison_layer[0]])
+    y0 = torch.sigmoid(z[0]).unsqueeze(2)
+    y1 = z[1].unsqueeze(2)
+    y2 = F.SoftmaxLists.apply(z[2]).unsqueeze(2)
+    if self.num_tasks == 3:
+        return [y0, y1, y2]
+    if self.num_tasks == 2.1:
+        return [y0, y2]
+    return [y1, y2]
+
+
+class BiCut(_Base):
+    """Reference models/Bicut.py:5-21."""
+
+    def __init__(self, input_size=231449, lstm_hiden_size=128, lstm_layers=2, fc_dimensions=256, dropout=0.4):
+        super().__init__()
+        self._dropout_p = float(dropout)
+        self.bilstm = _bilstm(input_size, lstm_hiden_size, lstm_layers)
+        self.fc = nn.Linear(in_features=lstm_hiden_size * 2, out_features=fc_dimensions)
+        self.softmax = nn.Sequential(nn.ReLU(), nn.Linear(in_features=fc_dimensions, out_features=2),
+                                     nn.Dropout(dropout), nn.Softmax(dim=2))
+
+    def forward(self, x):
+        self._check_mode()
+        h = F.BiLstm.apply(x, self.bilstm.hidden_size, self.bilstm.num_layers, *self.bilstm._flat_weights)
+        return F.BicutHead.apply(h, self.fc.weight, self.fc.bias, self.softmax[1].weight, self.softmax[1].bias)
+
+
+class AttnCut(_Base):
+    """Reference models/AttnCut.py:5-20."""
+
+    def __init__(self, input_size: int = 3, d_model: int = 256, n_head: int = 4, num_layers: int = 1,
+                 dropout: float = 0.4):
+        super().__init__()
+        self._dropout_p = float(dropout)
+        self.encoding_layer = _bilstm(input_size)
+        self.attention_layer = _encoder(d_model, n_head, num_layers, dropout)
+        self.decison_layer = _lin_softmax(d_model)
+
+    def forward(self, x):
+        self._check_mode()
+        e = self.encoding_layer
+        h = F.BiLstm.apply(x, e.hidden_size, e.num_layers, *e._flat_weights)
+        h = self._encode(h, self.attention_layer)
+        z = self._heads(h, [self.decison_layer[0]])
+        return F.SoftmaxLists.apply(z[0]).unsqueeze(2)
+
+
+class MtAttnCut(_Base):
+    """Reference models/MtAttnCut.py:4-29."""
+
+    def __init__(self, input_size: int = 3, d_model: int = 256, n_head: int = 4, num_layers: int = 1,
+                 num_tasks: float = 3, dropout: float = 0.4):
+        super().__init__()
+        self.num_tasks = num_tasks
+        self._dropout_p = float(dropout)
+        self.pre_encoding = _bilstm(input_size)
+        self.encoding_layer = _encoder(d_model, n_head, num_layers, dropout)
+        self.classi = _lin_sigmoid(d_model)
+        self.rerank = nn.Linear(in_features=d_model, out_features=1)
+        self.decison_layer = _lin_softmax(d_model)
+
+    def forward(self, x):
+        self._check_mode()
+        e = self.pre_encoding
+        h = F.BiLstm.apply(x, e.hidden_size, e.num_layers, *e._flat_weights)
+        return _mt_outputs(self, self._encode(h, self.encoding_layer))
+
+
+class _Expert(nn.Module):
+    """Parameter holder with the reference's attribute name (MMOECut.py:6-14)."""
+
+    def __init__(self, d_model, n_head, num_layers, dropout):
+        super().__init__()
+        self.attention_layer = _encoder(d_model, n_head, num_layers, dropout)
+
+
+class _Tower(nn.Module):
+    """Parameter holder for TowerCut / TowerClass / TowerRerank (MMOECut.py:17-53)."""
+
+    def __init__(self, d_model, attr: str, act: str):
+        super().__init__()
+        setattr(self, attr, _lin_sigmoid(d_model) if act == "sigmoid" else _lin_softmax(d_model))
+        self.attr, self.act = attr, act
+
+    @property
+    def linear(self) -> nn.Linear:
+        return getattr(self, self.attr)[0]
+
+
+class MMOECut(_Base):
+    """Reference models/MMOECut.py:56-110."""
+
+    def __init__(self, seq_len: int = 300, num_experts=3, num_tasks=3, input_size=3, encoding_size=128, d_model=256,
+                 n_head=4, num_layers=1, dropout=0.2):
+        super().__init__()
+        self.seq_len = seq_len
+        self.expert_hidden = d_model
+        self._dropout_p = float(dropout)
+        self.pre_encoding = _bilstm(input_size, encoding_size)
+        self.softmax = nn.Softmax(dim=1)
+        self.experts = nn.ModuleList([_Expert(self.expert_hidden, n_head, num_layers, dropout)
+                                      for _ in range(num_experts)])
+        self.w_gates = nn.ParameterList([nn.Parameter(torch.randn(encoding_size * self.seq_len * 2, num_experts),
+                                                      requires_grad=True) for _ in range(int(num_tasks))])
+        cls = lambda: _Tower(self.expert_hidden, "classification_layer", "sigmoid")  # noqa: E731
+        rer = lambda: _Tower(self.expert_hidden, "rerank_layer", "softmax")          # noqa: E731
+        cut = lambda: _Tower(self.expert_hidden, "cut_layer", "softmax")             # noqa: E731
+        if num_tasks == 3:
+            self.towers = nn.ModuleList([cls(), rer(), cut()])
+        elif num_tasks == 2.1:
+            self.towers = nn.ModuleList([cls(), cut()])
+        elif num_tasks == 2.2:
+            self.towers = nn.ModuleList([rer(), cut()])
+
+    def forward(self, x):
+        self._check_mode()
+        e = self.pre_encoding
+        h = F.BiLstm.apply(x, e.hidden_size, e.num_layers, *e._flat_weights)
+        experts = [self._encode(h, ex.attention_layer) for ex in self.experts]
+        w = torch.cat([t.linear.weight for t in self.towers], dim=0)
+        b = torch.cat([t.linear.bias for t in self.towers], dim=0)
+        z = F.MoeGateMix.apply(h, torch.stack(list(self.w_gates)), w, b, *experts)   # [T, B, L] tower logits
+        outs = []
+        for t, tower in enumerate(self.towers):
+            outs.append((torch.sigmoid(z[t]) if tower.act == "sigmoid" else F.SoftmaxLists.apply(z[t])).unsqueeze(2))
+        return outs

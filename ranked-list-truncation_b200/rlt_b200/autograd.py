@@ -1,0 +1,231 @@
+"""torch.autograd.Function wrappers that put the C-ABI kernels behind the reference's nn.Module API.
+
+Each Function's forward/backward is a handful of ctypes calls into librlt_b200.so; torch supplies
+device memory, the stream and the autograd graph.  Nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _buf(nbytes: int, device) -> torch.Tensor:
+    return torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError("rlt_b200 computes in float32 only (the reference's parameters and inputs are float32); "
+                           f"got {t.dtype}")
+    if not t.is_cuda:
+        raise RuntimeError("rlt_b200 has no CPU path: move the model and its inputs to a CUDA device "
+                           "(the reference run.py does this when torch.cuda.is_available())")
+    return t.contiguous()
+
+
+class EncoderStack(torch.autograd.Function):
+    """nn.TransformerEncoder (a stack of post-norm layers) on [B, L, d]; the B lists of the call form ONE
+    attention group, as in the reference (no batch_first)."""
+
+    @staticmethod
+    def forward(ctx, x, n_head, n_groups, ln_eps, *params):
+        x = _c(x)
+        B, L, d = x.shape
+        n_layers = len(params) // 12
+        params = [_c(p.detach()) for p in params]
+        d_ff = params[4].shape[0]
+        if B % n_groups:
+            raise RuntimeError(f"batch of {B} lists is not divisible into {n_groups} attention groups")
+        desc = ops.encoder_desc(n_groups, B // n_groups, L, d, n_head, d_ff, ln_eps)
+        need_grad = any(ctx.needs_input_grad)
+        saved_bytes = ops.encoder_saved_bytes(desc)
+        if saved_bytes == 0:
+            raise ops._lib.RltError("encoder: " + ops._lib.load().rlt_last_error().decode())
+        cur = x
+        saved, inputs = [], []
+        scratch = None
+        for i in range(n_layers):
+            w = ops.encoder_ptrs(params[12 * i:12 * i + 12])
+            out = torch.empty_like(x)
+            if need_grad:
+                sv = _buf(saved_bytes, x.device)
+            else:  # inference: one scratch "saved" buffer reused by every layer
+                if scratch is None:
+                    scratch = _buf(saved_bytes, x.device)
+                sv = scratch
+            ops.encoder_layer_fwd(desc, w, cur, out, sv)
+            if need_grad:
+                saved.append(sv)
+                inputs.append(cur)
+            cur = out
+        ctx.desc = desc
+        ctx.n_layers = n_layers
+        ctx.params = params
+        ctx.saved_bufs = saved
+        ctx.layer_inputs = inputs
+        return cur
+
+    @staticmethod
+    def backward(ctx, d_out):
+        d_out = _c(d_out)
+        desc, params = ctx.desc, ctx.params
+        ws = _buf(ops.encoder_workspace_bytes(desc), d_out.device)
+        grads = [torch.zeros_like(p) for p in params]
+        cur = d_out
+        for i in reversed(range(ctx.n_layers)):
+            w = ops.encoder_ptrs(params[12 * i:12 * i + 12])
+            g = ops.encoder_ptrs(grads[12 * i:12 * i + 12])
+            d_x = torch.empty_like(d_out)
+            ops.encoder_layer_bwd(desc, w, g, ctx.layer_inputs[i], ctx.saved_bufs[i], cur, d_x, ws)
+            cur = d_x
+        ctx.saved_bufs = ctx.layer_inputs = None
+        return (cur, None, None, None, *grads)
+
+
+class ChoopyEmbed(torch.autograd.Function):
+    """x = cat(score, position_encoding.expand(B, L, 127)) (models/Choopy.py:19-20)."""
+
+    @staticmethod
+    def forward(ctx, score, pe):
+        score, pe = _c(score), _c(pe.detach())
+        B, L = score.shape[0], score.shape[1]
+        if score.shape[2:] != (1,) or pe.shape != (L, 127):
+            raise RuntimeError(f"Choopy expects scores [B, {pe.shape[0]}, 1]; got {tuple(score.shape)}")
+        x = torch.empty(B, L, 128, dtype=torch.float32, device=score.device)
+        ops.choopy_embed_fwd(score, pe, x)
+        ctx.shape = (B, L)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        dx = _c(dx)
+        B, L = ctx.shape
+        dpe = torch.zeros(L, 127, dtype=torch.float32, device=dx.device)
+        ops.choopy_embed_bwd(dx, dpe, B, L)
+        dscore = dx[:, :, 0:1].contiguous() if ctx.needs_input_grad[0] else None
+        return dscore, dpe
+
+
+class HeadDots(torch.autograd.Function):
+    """H parallel Linear(d, 1) heads: returns logits [H, B, L]."""
+
+    @staticmethod
+    def forward(ctx, h, w, b):
+        h, w, b = _c(h), _c(w.detach()), _c(b.detach())
+        B, L, d = h.shape
+        H = w.shape[0]
+        z = torch.empty(H, B, L, dtype=torch.float32, device=h.device)
+        ops.head_dots_fwd(h, w, b, z, B * L, d, H)
+        ctx.save_for_backward(h, w)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        h, w = ctx.saved_tensors
+        dz = _c(dz)
+        B, L, d = h.shape
+        H = w.shape[0]
+        dx = torch.empty_like(h)
+        dw = torch.zeros_like(w)
+        db = torch.zeros(H, dtype=torch.float32, device=h.device)
+        ops.head_dots_bwd(h, w, dz, dx, dw, db, B * L, d, H, False)
+        return dx, dw, db
+
+
+class SoftmaxLists(torch.autograd.Function):
+    """nn.Softmax(dim=1) over the L positions of logits [B, L]."""
+
+    @staticmethod
+    def forward(ctx, z):
+        z = _c(z)
+        p = torch.empty_like(z)
+        ops.softmax_lists(z, p, z.shape[0], z.shape[1])
+        ctx.save_for_backward(p)
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        (p,) = ctx.saved_tensors
+        dz = torch.empty_like(p)
+        ops.softmax_lists_bwd(p, _c(dp), dz, p.shape[0], p.shape[1])
+        return dz
+
+
+class CutLoss(torch.autograd.Function):
+    """ChoopyLoss / AttnCutLoss / DivLoss on probabilities p [B, L] (the reference criteria take the model
+    output, i.e. probabilities): one fused kernel produces the loss and dL/dp."""
+
+    @staticmethod
+    def forward(ctx, p, labels, loss_kind, metric, tau):
+        p, labels = _c(p), _c(labels)
+        B, L = labels.shape
+        grad = torch.empty_like(p)
+        per_list = torch.empty(B, dtype=torch.float32, device=p.device)
+        loss = torch.empty((), dtype=torch.float32, device=p.device)
+        ops.cut_loss(p, labels, loss_kind=loss_kind, metric=metric, tau=tau, input_kind=1, grad=grad,
+                     loss_per_list=per_list, loss_out=loss, grad_scale=1.0 / B, loss_scale=1.0 / B)
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None, None
+
+
+class AuxHeadsLoss(torch.autograd.Function):
+    """classi_weight * BCELoss(class_p) + rerank_weight * RerankLoss(rerank_out) of MtCutLoss on the
+    reference API boundary: class_p are probabilities, rerank_out the rerank head output."""
+
+    @staticmethod
+    def forward(ctx, class_p, rerank_out, labels, class_weight, rerank_weight, margin):
+        labels = _c(labels)
+        B, L = labels.shape
+        dev = labels.device
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        loss_group = torch.empty(1, dtype=torch.float32, device=dev)
+        pc = dpc = zr = dzr = None
+        if class_p is not None:
+            pc = _c(class_p).reshape(B, L)
+            dpc = torch.empty_like(pc)
+        if rerank_out is not None:
+            zr = _c(rerank_out).reshape(B, L)
+            dzr = torch.empty_like(zr)
+        ops.aux_heads_loss(pc, zr, labels, n_groups=1, group_size=B, seq_len=L, rerank_softmax=False, class_probs=True,
+                           margin=margin, class_weight=class_weight, rerank_weight=rerank_weight, dzc=dpc, dzr=dzr,
+                           loss_group=loss_group, status=status, loss_out=loss)
+        if rerank_out is not None and int(status.item()) != 0:
+            # reference utils/losses.py:138 returns torch.tensor(0, requires_grad=True) -> RuntimeError
+            raise RuntimeError("Only Tensors of floating point and complex dtype can require gradients")
+        grads = [dpc.reshape(class_p.shape) if class_p is not None else None,
+                 dzr.reshape(rerank_out.shape) if rerank_out is not None else None]
+        ctx.grads = grads
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        gc, gr = ctx.grads
+        return (gc * g if gc is not None else None, gr * g if gr is not None else None, None, None, None, None)
+
+
+class BicutLoss(torch.autograd.Function):
+    """BiCutLoss on the model output [B, L, 2] (probabilities)."""
+
+    @staticmethod
+    def forward(ctx, out, labels, alpha, r, metric_nci):
+        out, labels = _c(out), _c(labels)
+        B, L = labels.shape
+        grad = torch.empty_like(out)
+        per_list = torch.empty(B, dtype=torch.float32, device=out.device)
+        loss = torch.empty((), dtype=torch.float32, device=out.device)
+        ops.bicut_loss(out, labels, input_kind=1, metric_nci=metric_nci, alpha=alpha, r=r, grad=grad,
+                       loss_per_list=per_list, loss_out=loss, grad_scale=1.0 / B, loss_scale=1.0 / B)
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None, None

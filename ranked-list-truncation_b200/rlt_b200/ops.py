@@ -1,0 +1,209 @@
+"""Thin Python wrappers over the C ABI (include/rlt_b200.h): one function per entry point.
+
+All tensors must be CUDA float32 and contiguous; there is no CPU path.  Functions enqueue work on
+torch's current stream and return immediately.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+MAX_LEN = 1024
+# the reference's coefficient table (utils/metrics.py:7): math.log(j+2, 2), NOT math.log2
+DCG_COEF = [math.log(j + 2, 2) for j in range(MAX_LEN)]
+
+LOSS_KINDS = {"choopy": 0, "raml": 1, "kl": 2, "js": 3}
+
+
+class EncoderDesc(C.Structure):
+    _fields_ = [("n_groups", C.c_int32), ("group_size", C.c_int32), ("seq_len", C.c_int32), ("d_model", C.c_int32),
+                ("n_head", C.c_int32), ("d_ff", C.c_int32), ("attend_axis", C.c_int32), ("training", C.c_int32),
+                ("ln_eps", C.c_float), ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64)]
+
+
+ENCODER_PARAM_ORDER = ("self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight",
+                       "self_attn.out_proj.bias", "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias",
+                       "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias")
+
+
+class EncoderPtrs(C.Structure):
+    """rlt_encoder_weights / rlt_encoder_grads (12 device pointers in ENCODER_PARAM_ORDER)."""
+    _fields_ = [(n.replace(".", "_"), C.c_void_p) for n in ENCODER_PARAM_ORDER]
+
+
+class CutLossDesc(C.Structure):
+    _fields_ = [("n_lists", C.c_int32), ("seq_len", C.c_int32), ("input_kind", C.c_int32), ("loss_kind", C.c_int32),
+                ("metric_dcg", C.c_int32), ("accumulate_loss", C.c_int32), ("tau", C.c_float),
+                ("grad_scale", C.c_float), ("loss_scale", C.c_float)]
+
+
+class AuxLossDesc(C.Structure):
+    _fields_ = [("n_groups", C.c_int32), ("group_size", C.c_int32), ("seq_len", C.c_int32),
+                ("rerank_softmax", C.c_int32), ("class_probs", C.c_int32), ("accumulate_loss", C.c_int32),
+                ("margin", C.c_float),
+                ("class_weight", C.c_float), ("rerank_weight", C.c_float), ("grad_scale", C.c_float),
+                ("loss_scale", C.c_float)]
+
+
+class BicutLossDesc(C.Structure):
+    _fields_ = [("n_lists", C.c_int32), ("seq_len", C.c_int32), ("input_kind", C.c_int32), ("metric_nci", C.c_int32),
+                ("accumulate_loss", C.c_int32), ("alpha", C.c_float), ("r", C.c_float), ("grad_scale", C.c_float),
+                ("loss_scale", C.c_float)]
+
+
+_configured = False
+_tables_on = set()
+
+
+def lib():
+    """The loaded library with argument types declared."""
+    global _configured
+    L = _lib.load()
+    if not _configured:
+        L.rlt_encoder_layer_saved_bytes.restype = C.c_size_t
+        L.rlt_encoder_layer_workspace_bytes.restype = C.c_size_t
+        for name in ("rlt_bilstm_saved_bytes", "rlt_bilstm_workspace_bytes"):
+            if hasattr(L, name):
+                getattr(L, name).restype = C.c_size_t
+        _configured = True
+    return L
+
+
+def _require(t: torch.Tensor, name: str):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise RuntimeError(f"{name}: expected a contiguous float32 CUDA tensor (the rlt_b200 path has no CPU fallback); "
+                           f"got {type(t).__name__} {getattr(t, 'dtype', None)} on {getattr(t, 'device', None)}")
+
+
+def ensure_tables():
+    """Upload the DCG tables to the current device once."""
+    dev = torch.cuda.current_device()
+    if dev in _tables_on:
+        return
+    coef32 = np.array(DCG_COEF, dtype=np.float32)
+    term64 = np.array([1.0 / c for c in DCG_COEF], dtype=np.float64)
+    check(lib().rlt_set_dcg_tables(coef32.ctypes.data_as(C.c_void_p), term64.ctypes.data_as(C.c_void_p), MAX_LEN),
+          "rlt_set_dcg_tables")
+    _tables_on.add(dev)
+
+
+# ----------------------------------------------------------------------------------------------
+# encoder layer
+# ----------------------------------------------------------------------------------------------
+def encoder_desc(n_groups, group_size, seq_len, d_model, n_head, d_ff=2048, ln_eps=1e-5, dropout_p=0.0, seed=0):
+    return EncoderDesc(n_groups, group_size, seq_len, d_model, n_head, d_ff, 0, 1, ln_eps, dropout_p, seed)
+
+
+def encoder_ptrs(tensors) -> EncoderPtrs:
+    """tensors: 12 tensors in ENCODER_PARAM_ORDER."""
+    for t, n in zip(tensors, ENCODER_PARAM_ORDER):
+        _require(t, n)
+    return EncoderPtrs(*[t.data_ptr() for t in tensors])
+
+
+def encoder_saved_bytes(desc) -> int:
+    return int(lib().rlt_encoder_layer_saved_bytes(C.byref(desc)))
+
+
+def encoder_workspace_bytes(desc) -> int:
+    return int(lib().rlt_encoder_layer_workspace_bytes(C.byref(desc)))
+
+
+def encoder_layer_fwd(desc, weights, x, out, saved):
+    _require(x, "x"); _require(out, "out")
+    check(lib().rlt_encoder_layer_fwd(C.byref(desc), C.byref(weights), ptr(x), ptr(out), ptr(saved),
+                                      C.c_size_t(saved.numel() * saved.element_size()), stream_ptr()),
+          "rlt_encoder_layer_fwd")
+
+
+def encoder_layer_bwd(desc, weights, grads, x, saved, d_out, d_x, workspace):
+    check(lib().rlt_encoder_layer_bwd(C.byref(desc), C.byref(weights), C.byref(grads), ptr(x), ptr(saved), ptr(d_out),
+                                      ptr(d_x), ptr(workspace),
+                                      C.c_size_t(workspace.numel() * workspace.element_size()), stream_ptr()),
+          "rlt_encoder_layer_bwd")
+
+
+# ----------------------------------------------------------------------------------------------
+# heads / losses / eval
+# ----------------------------------------------------------------------------------------------
+def choopy_embed_fwd(score, pe, x):
+    n_lists, seq_len = score.shape[0], score.shape[1]
+    check(lib().rlt_choopy_embed_fwd(ptr(score), ptr(pe), ptr(x), n_lists, seq_len, stream_ptr()), "rlt_choopy_embed_fwd")
+
+
+def choopy_embed_bwd(dx, dpe, n_lists, seq_len):
+    check(lib().rlt_choopy_embed_bwd(ptr(dx), ptr(dpe), n_lists, seq_len, stream_ptr()), "rlt_choopy_embed_bwd")
+
+
+def head_dots_fwd(x, w, bias, z, n_tokens, d, n_heads):
+    check(lib().rlt_head_dots_fwd(ptr(x), ptr(w), ptr(bias), ptr(z), n_tokens, d, n_heads, stream_ptr()),
+          "rlt_head_dots_fwd")
+
+
+def head_dots_bwd(x, w, dz, dx, dw, db, n_tokens, d, n_heads, accumulate_dx=False):
+    check(lib().rlt_head_dots_bwd(ptr(x), ptr(w), ptr(dz), ptr(dx), ptr(dw), ptr(db), n_tokens, d, n_heads,
+                                  int(accumulate_dx), stream_ptr()), "rlt_head_dots_bwd")
+
+
+def softmax_lists(z, p, n_lists, seq_len):
+    check(lib().rlt_softmax_lists(ptr(z), ptr(p), n_lists, seq_len, stream_ptr()), "rlt_softmax_lists")
+
+
+def softmax_lists_bwd(p, dp, dz, n_lists, seq_len):
+    check(lib().rlt_softmax_lists_bwd(ptr(p), ptr(dp), ptr(dz), n_lists, seq_len, stream_ptr()), "rlt_softmax_lists_bwd")
+
+
+def cut_loss(inp, labels, *, loss_kind, metric="f1", tau=1.0, input_kind=0, probs_out=None, grad=None,
+             loss_per_list=None, loss_out=None, grad_scale=1.0, loss_scale=1.0, accumulate=False):
+    ensure_tables()
+    n_lists, seq_len = labels.shape
+    desc = CutLossDesc(n_lists, seq_len, input_kind, LOSS_KINDS[loss_kind] if isinstance(loss_kind, str) else loss_kind,
+                       0 if metric == "f1" else 1, int(accumulate), tau, grad_scale, loss_scale)
+    check(lib().rlt_cut_loss(C.byref(desc), ptr(inp), ptr(labels), ptr(probs_out), ptr(grad), ptr(loss_per_list),
+                             ptr(loss_out), stream_ptr()), "rlt_cut_loss")
+
+
+def reward_matrix(labels, rewards, metric="f1"):
+    ensure_tables()
+    check(lib().rlt_reward_matrix(ptr(labels), ptr(rewards), labels.shape[0], labels.shape[1],
+                                  0 if metric == "f1" else 1, stream_ptr()), "rlt_reward_matrix")
+
+
+def eval_cut(probs, labels, mode=0):
+    """Returns (k int32[B], count int32[B], n_rel int32[B], f1 float64[B], dcg float64[B]) on the device."""
+    ensure_tables()
+    n_lists, seq_len = labels.shape
+    dev = labels.device
+    k = torch.empty(n_lists, dtype=torch.int32, device=dev)
+    cnt = torch.empty_like(k)
+    nrel = torch.empty_like(k)
+    f1 = torch.empty(n_lists, dtype=torch.float64, device=dev)
+    dcg = torch.empty_like(f1)
+    check(lib().rlt_eval_cut(ptr(probs), ptr(labels), n_lists, seq_len, mode, ptr(k), ptr(cnt), ptr(nrel), ptr(f1),
+                             ptr(dcg), stream_ptr()), "rlt_eval_cut")
+    return k, cnt, nrel, f1, dcg
+
+
+def aux_heads_loss(zc, zr, labels, *, n_groups, group_size, seq_len, rerank_softmax=False, class_probs=False, margin=5e-4,
+                   class_weight=0.5, rerank_weight=0.5, grad_scale=1.0, loss_scale=1.0, probs_c=None, out_r=None,
+                   dzc=None, dzr=None, loss_group=None, status=None, loss_out=None, accumulate=False):
+    desc = AuxLossDesc(n_groups, group_size, seq_len, int(rerank_softmax), int(class_probs), int(accumulate), margin, class_weight,
+                       rerank_weight, grad_scale, loss_scale)
+    check(lib().rlt_aux_heads_loss(C.byref(desc), ptr(zc), ptr(zr), ptr(labels), ptr(probs_c), ptr(out_r), ptr(dzc),
+                                   ptr(dzr), ptr(loss_group), ptr(status), ptr(loss_out), stream_ptr()),
+          "rlt_aux_heads_loss")
+
+
+def bicut_loss(u, labels, *, input_kind=0, metric_nci=False, alpha=0.65, r=0.0971134020, probs_out=None, grad=None,
+               loss_per_list=None, loss_out=None, grad_scale=1.0, loss_scale=1.0, accumulate=False):
+    n_lists, seq_len = labels.shape
+    desc = BicutLossDesc(n_lists, seq_len, input_kind, int(metric_nci), int(accumulate), alpha, r, grad_scale,
+                         loss_scale)
+    check(lib().rlt_bicut_loss(C.byref(desc), ptr(u), ptr(labels), ptr(probs_out), ptr(grad), ptr(loss_per_list),
+                               ptr(loss_out), stream_ptr()), "rlt_bicut_loss")

@@ -1,0 +1,54 @@
+"""CPU: the C-ABI library loads and exports every symbol declared in include/rlt_b200.h; the host
+mirror refuses CPU tensors (no fallback)."""
+import ctypes
+
+import pytest
+import torch
+
+from rlt_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _lib.declared_symbols()
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/rlt_b200.h but not exported: {missing}"
+    assert b"sm_100a" in lib.rlt_version()
+
+
+def test_status_codes_and_last_error_without_gpu():
+    lib = _lib.load()
+    assert lib.rlt_set_option(b"no_such_option", 1) == -1
+    assert b"unknown option" in lib.rlt_last_error()
+    assert lib.rlt_round_tf32(None, None, ctypes.c_size_t(4), None) == -1
+    assert _lib.get_option("gemm_backend") == 0
+    assert _lib.get_option("tma_round") == 1
+
+
+def test_modules_refuse_cpu_tensors():
+    import models
+    from utils import losses
+    torch.manual_seed(0)
+    m = models.Choopy(seq_len=40, dropout=0.0)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(torch.randn(2, 40, 1))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        losses.ChoopyLoss()(torch.rand(2, 40, 1), torch.zeros(2, 40))
+
+
+def test_state_dict_keys_match_reference_layout():
+    import models
+    torch.manual_seed(0)
+    keys = set(models.MMOECut(seq_len=40, dropout=0.0).state_dict())
+    for k in ("pre_encoding.weight_ih_l0", "pre_encoding.weight_hh_l1_reverse",
+              "experts.2.attention_layer.layers.0.self_attn.in_proj_weight", "w_gates.0", "w_gates.2",
+              "towers.0.classification_layer.0.weight", "towers.1.rerank_layer.0.bias", "towers.2.cut_layer.0.weight"):
+        assert k in keys, k
+    keys = set(models.Choopy(seq_len=40).state_dict())
+    assert {"position_encoding", "attention_layer.layers.2.norm2.bias", "decison_layer.0.weight"} <= keys
+    keys = set(models.BiCut(input_size=3).state_dict())
+    assert {"bilstm.weight_ih_l0", "bilstm.bias_hh_l1_reverse", "fc.weight", "softmax.1.bias"} <= keys
+    keys = set(models.MtAttnCut().state_dict())
+    assert {"pre_encoding.weight_hh_l0", "encoding_layer.layers.0.linear1.weight", "classi.0.weight", "rerank.bias",
+            "decison_layer.0.bias"} <= keys
