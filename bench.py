@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — ranked lists/sec of the truncation-model hot path (BASELINE.json metric) on N B200s.
+
+Workload (BASELINE.json configs[1]): Choopy cut-transformer, score-only input, 65 536 synthetic
+robust04-shaped lists x 300 resident in HBM; attention groups of S = 64 lists (the reference's batch).
+A "step" = one pass of the hot path over one batch of G groups per GPU (default 64 -> 4096 lists):
+forward + ChoopyLoss + backward into the flat gradient bucket (+ NCCL all-reduce of the bucket when
+N > 1).  Inference (forward + fused argmax-cut + F1/DCG) is timed as well and reported in `inference`.
+
+One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement" for every field.
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--model choopy] [--groups G]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "ranked-list-truncation_b200"))
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+DATASET_LISTS = 65536
+SEQ_LEN = 300
+GROUP = 64
+METRIC = "ranked lists/sec (train step, L=300)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="choopy")
+    ap.add_argument("--groups", type=int, default=64, help="attention groups (of 64 lists) per GPU per step")
+    ap.add_argument("--time-tag", type=int, default=3, help="kernel class timed in situ for the roofline (3 = FFN1 GEMM)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = max((int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the reference's algorithm (oracle port: same torch.nn calls + Python reward loop) on the host
+    cores, same metric / config.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import torch_port
+    from rlt_b200.data import synthetic_lists
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_batches = 2
+    x, y = synthetic_lists(GROUP * n_batches, SEQ_LEN, 1, seed=20240229, device="cpu")
+    steps, warm = max(1, min(args.steps, 4)), max(1, min(args.warmup, 1))
+    lps, times = torch_port.time_lists_per_s(args.model, x, y, GROUP, "train", steps=steps, warmup=warm)
+    ilps, _ = torch_port.time_lists_per_s(args.model, x, y, GROUP, "infer", steps=steps, warmup=warm)
+    sample = f"{steps} train steps of one batch of {GROUP} lists x {SEQ_LEN} (median), after {warm} warm-up"
+    line = {"impl": "reference", "metric": METRIC, "value": lps, "unit": "lists/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": 1e3 * GROUP / lps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.model} train step, synthetic robust04-shaped lists x {SEQ_LEN}, groups of {GROUP}",
+                       "note": "reference algorithm on host CPU cores (oracle port of the reference's torch calls + Python reward loop)"},
+            "inference": {"value": ilps, "unit": "lists/s"},
+            "cpu_baseline": {"value": lps, "unit": "lists/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": lps, "unit": "lists/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from rlt_b200 import _lib, ops
+    from rlt_b200.data import synthetic_lists
+    from rlt_b200.engine import Engine
+    import models
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the rlt_b200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = ops.lib()
+    lib.rlt_launch_count.restype = ctypes.c_ulonglong
+
+    G = args.groups
+    B = G * GROUP                                   # lists per GPU per step
+    shard = DATASET_LISTS // world                  # lists resident on this GPU
+    if shard < B:
+        shard = B
+    x_all, y_all = synthetic_lists(shard, SEQ_LEN, 1, seed=20240229 + rank, device=dev)
+    n_chunks = shard // B
+
+    torch.manual_seed(1234)
+    cls = {"choopy": models.Choopy, "mtchoopy": models.MtChoopy}[args.model]
+    model = cls(seq_len=SEQ_LEN, dropout=0.0).to(dev)
+    eng = Engine(model, n_groups=G, group_size=GROUP, seq_len=SEQ_LEN, training=True)
+
+    def step(i):
+        c = i % n_chunks
+        eng.train_step(x_all[c * B:(c + 1) * B], y_all[c * B:(c + 1) * B])
+        if world > 1:
+            dist.all_reduce(eng.grad_bucket)
+            eng.grad_bucket.mul_(1.0 / world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident train throughput
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib.set_option("time_tag", args.time_tag)
+    lib.rlt_timing_reset()
+    launches0 = lib.rlt_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    launches = int(lib.rlt_launch_count() - launches0)
+    ms = e0.elapsed_time(e1)
+    _lib.set_option("time_tag", 0)
+    tot_ms, cnt = ctypes.c_double(0), ctypes.c_int(0)
+    _lib.check(lib.rlt_timing_read(ctypes.byref(tot_ms), ctypes.byref(cnt)), "rlt_timing_read")
+    lib.rlt_timing_reset()
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    train_lps = world * B * args.steps / (ms * 1e-3)
+    loss_val = float(eng.loss.item())
+
+    # ---------------- inference (forward + fused cut/F1/DCG)
+    for i in range(2):
+        eng.infer(x_all[:B], y_all[:B])
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        c = i % n_chunks
+        k, f1, dcg = eng.infer(x_all[c * B:(c + 1) * B], y_all[c * B:(c + 1) * B])
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    infer_lps = world * B * args.steps / (float(t.item()) * 1e-3)
+
+    # ---------------- end to end: pinned host inputs -> H2D -> train step -> loss D2H, every step
+    hx = x_all[:B].cpu().pin_memory()
+    hy = y_all[:B].cpu().pin_memory()
+    dx, dy = torch.empty_like(x_all[:B]), torch.empty_like(y_all[:B])
+    def e2e_step():
+        dx.copy_(hx, non_blocking=True)
+        dy.copy_(hy, non_blocking=True)
+        eng.train_step(dx, dy)
+        if world > 1:
+            dist.all_reduce(eng.grad_bucket)
+            eng.grad_bucket.mul_(1.0 / world)
+        return eng.loss.item()        # device -> host read of the step's result
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_lps = world * B * args.steps / (float(t.item()) * 1e-3)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the kernel timed in situ
+    hbm, tf_burst, tf_sust, src = measured_peaks()
+    T = B * SEQ_LEN
+    d, dff = 128, 2048
+    roof = None
+    if cnt.value > 0:
+        avg_s = tot_ms.value / cnt.value * 1e-3
+        if args.time_tag == 3:      # FFN1 GEMM: reads y [T,d] + W1 + b1, writes relu(h) [T,dff] — HBM(write)-bound unfused
+            bytes_ = T * (d + dff) * 4 + dff * d * 4 + dff * 4
+            roof = {"kernel": "gemm_tn_kernel<256> (encoder FFN1: relu(y W1^T + b1), TF32 tcgen05)", "bound": "hbm",
+                    "achieved": bytes_ / avg_s / 1e9, "peak": hbm, "unit": "GB/s", "traffic": None,
+                    "tensor_tflops": 2.0 * T * d * dff / avg_s / 1e12}
+        else:
+            roof = {"kernel": f"tag {args.time_tag}", "bound": "hbm", "achieved": None, "peak": hbm, "unit": "GB/s",
+                    "traffic": None}
+        if roof.get("achieved"):
+            roof["frac"] = roof["achieved"] / roof["peak"]
+        roof.update({"peak_source": src, "avg_launch_ms": avg_s * 1e3, "launches_timed": cnt.value,
+                     "share_of_step": tot_ms.value / ms})
+
+    # ---------------- CPU baseline on this box's host cores (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import torch_port
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cx, cy = synthetic_lists(GROUP * 2, SEQ_LEN, 1, seed=20240229, device="cpu")
+        lps, times = torch_port.time_lists_per_s(args.model, cx, cy, GROUP, "train", steps=3, warmup=1)
+        cpu = {"value": lps, "unit": "lists/s", "cores": cores, "kind": "port",
+               "sample": f"3 reference-style train steps (fwd + Python-loop criterion + bwd + host metrics) on one batch of "
+                         f"{GROUP} lists x {SEQ_LEN}, median, 1 warm-up; step times {[round(v, 3) for v in times]} s"}
+
+    line = {"metric": METRIC, "value": train_lps, "unit": "lists/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": f"{args.model} train step (fwd + ChoopyLoss f1 + bwd{' + NCCL grad all-reduce' if world > 1 else ''}), "
+                                   f"{DATASET_LISTS} synthetic robust04-shaped lists x {SEQ_LEN} resident in HBM",
+                       "lists_per_step_per_gpu": B, "attention_group": GROUP, "seq_len": SEQ_LEN,
+                       "l2": "inputs and activations of one step (>10 GB) exceed the 126 MB L2; no explicit flush",
+                       "parallelism": f"dp{world}"},
+            "inference": {"value": infer_lps, "unit": "lists/s", "what": "forward + fused argmax-cut + per-list F1/DCG"},
+            "e2e": {"value": e2e_lps, "unit": "lists/s", "h2d_bytes_per_step": int(hx.numel() * 4 + hy.numel() * 4),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "loss": loss_val, "clocks": sampler.summary(), "roofline": roof,
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

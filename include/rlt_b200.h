@@ -49,6 +49,13 @@ const char* rlt_last_error(void);
  *          "tma_round"    (1 = encode tensor maps as TFLOAT32 so TMA rounds operands on load). */
 int rlt_set_option(const char* key, int value);
 int rlt_get_option(const char* key);
+/* Number of CUDA kernels this library has launched in this process (all entry points). */
+unsigned long long rlt_launch_count(void);
+/* In-situ timing of one kernel class: set option "time_tag" to a tag (1 qkv, 2 out-proj, 3 ffn1, 4 ffn2,
+ * 5 d_ffn2, 6 d_ffn1, 7 dW_ffn2, 8 dW_ffn1, 9 attention fwd, 10 attention bwd, 11 fused ffn, 12 lstm);
+ * matching launches are bracketed by CUDA events on their stream.  rlt_timing_read sums them. */
+int rlt_timing_reset(void);
+int rlt_timing_read(double* total_ms, int* count);
 
 /* ------------------------------------------------------------------------------------------ */
 /* building blocks exported for tests and probes                                              */

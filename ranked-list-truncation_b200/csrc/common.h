@@ -20,7 +20,13 @@ int set_error(int code, const char* fmt, ...);
       return ::rlt::set_error(RLT_CUDA_ERROR, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
                               __FILE__, __LINE__);                                              \
   } while (0)
-#define RLT_CHECK_LAUNCH() RLT_CHECK_CUDA(cudaGetLastError())
+// every kernel launch site goes through this: counts the launch (rlt_launch_count) and checks for errors
+void note_launch();
+#define RLT_CHECK_LAUNCH()             \
+  do {                                 \
+    ::rlt::note_launch();              \
+    RLT_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
 #define RLT_REQUIRE(cond, code, ...)                          \
   do {                                                        \
     if (!(cond)) return ::rlt::set_error((code), __VA_ARGS__); \
@@ -33,6 +39,15 @@ int set_error(int code, const char* fmt, ...);
 
 int num_sms();
 
+// In-situ kernel timing: when the "time_tag" option equals `tag`, the launch is bracketed by CUDA events on
+// its own stream; rlt_timing_read() sums the elapsed times.  Tags name the GEMM call sites of the encoder.
+enum KernelTag : int {
+  TAG_NONE = 0, TAG_QKV = 1, TAG_OUT_PROJ = 2, TAG_FFN1 = 3, TAG_FFN2 = 4, TAG_D_FFN2 = 5, TAG_D_FFN1 = 6,
+  TAG_DW_FFN2 = 7, TAG_DW_FFN1 = 8, TAG_ATTN_FWD = 9, TAG_ATTN_BWD = 10, TAG_FFN_FUSED = 11, TAG_LSTM = 12
+};
+void time_begin(int tag, cudaStream_t stream);
+void time_end(int tag, cudaStream_t stream);
+
 // ---- GEMM front-ends (gemm.cu).  Operands are fp32 containers; on the tensor-core path they
 //      must hold tf32-rounded values unless tma_rounds() is true. ----
 // C[M,N] = A[M,K] * B[N,K]^T with the fused epilogue described by EpiParams.
@@ -43,7 +58,7 @@ int gemm_nn(const float* A, int lda, const float* B, int ldb, int M, int N, int 
             cudaStream_t stream);
 // C[M,N] += alpha * sum_t A[t,m] * B[t,n]   (A: [T,lda], B: [T,ldb]; C pre-initialised by the caller)
 int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
-            cudaStream_t stream);
+            cudaStream_t stream, int tag = 0);
 
 // 0 = tcgen05 tensor-core kernels (default), 1 = plain SIMT kernels (validation backend only)
 int gemm_backend();

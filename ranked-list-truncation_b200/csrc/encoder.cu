@@ -381,7 +381,9 @@ static int attention_fwd(const float* qkv, float* o, float* lse, int G, int S, i
   do {                                                                                                          \
     RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         int(smem)));                                                            \
+    time_begin(TAG_ATTN_FWD, stream);                                                                           \
     attn_lists_fwd_kernel<DH><<<grid, 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale);               \
+    time_end(TAG_ATTN_FWD, stream);                                                                             \
   } while (0)
   if (dh == 16) RLT_ATTN_FWD(16);
   else if (dh == 32) RLT_ATTN_FWD(32);
@@ -404,7 +406,9 @@ static int attention_bwd(const float* qkv, const float* o, const float* lse, con
   do {                                                                                                          \
     RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         int(smem)));                                                            \
+    time_begin(TAG_ATTN_BWD, stream);                                                                           \
     attn_lists_bwd_kernel<DH><<<grid, 128, smem, stream>>>(qkv, o, lse, d_o, dqkv, S, L, d, n_head, scale);    \
+    time_end(TAG_ATTN_BWD, stream);                                                                             \
   } while (0)
   if (dh == 16) RLT_ATTN_BWD(16);
   else if (dh == 32) RLT_ATTN_BWD(32);
@@ -516,19 +520,19 @@ int rlt_encoder_layer_fwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   EpiParams ep{};
   ep.alpha = 1.f;
   // qkv = x Win^T + b_in
-  ep.out = sv + sl.qkv; ep.ldo = 3 * d; ep.bias = w->in_proj_b;
+  ep.out = sv + sl.qkv; ep.ldo = 3 * d; ep.bias = w->in_proj_b; ep.tag = TAG_QKV;
   RLT_TRY(gemm_tn(x, d, w->in_proj_w, d, T, 3 * d, d, ep, stream));
   RLT_TRY(attention_fwd(sv + sl.qkv, sv + sl.o, sv + sl.lse, e->n_groups, e->group_size, e->seq_len, d, e->n_head,
                         stream));
   // u1 = x + o Wo^T + b_o ; y = LN1(u1)
-  ep = EpiParams{}; ep.alpha = 1.f; ep.out = sv + sl.u1; ep.ldo = d; ep.bias = w->out_proj_b; ep.residual = x;
+  ep = EpiParams{}; ep.alpha = 1.f; ep.out = sv + sl.u1; ep.ldo = d; ep.bias = w->out_proj_b; ep.residual = x; ep.tag = TAG_OUT_PROJ;
   RLT_TRY(gemm_tn(sv + sl.o, d, w->out_proj_w, d, T, d, d, ep, stream));
   RLT_TRY(layer_norm_fwd(sv + sl.u1, w->norm1_w, w->norm1_b, sv + sl.y, sv + sl.st1, T, d, e->ln_eps, stream));
   // h = relu(y W1^T + b1)
-  ep = EpiParams{}; ep.alpha = 1.f; ep.out = sv + sl.h; ep.ldo = f; ep.bias = w->lin1_b; ep.relu = 1;
+  ep = EpiParams{}; ep.alpha = 1.f; ep.out = sv + sl.h; ep.ldo = f; ep.bias = w->lin1_b; ep.relu = 1; ep.tag = TAG_FFN1;
   RLT_TRY(gemm_tn(sv + sl.y, d, w->lin1_w, d, T, f, d, ep, stream));
   // u2 = y + h W2^T + b2 ; out = LN2(u2)
-  ep = EpiParams{}; ep.alpha = 1.f; ep.out = sv + sl.u2; ep.ldo = d; ep.bias = w->lin2_b; ep.residual = sv + sl.y;
+  ep = EpiParams{}; ep.alpha = 1.f; ep.out = sv + sl.u2; ep.ldo = d; ep.bias = w->lin2_b; ep.residual = sv + sl.y; ep.tag = TAG_FFN2;
   RLT_TRY(gemm_tn(sv + sl.h, f, w->lin2_w, f, T, d, f, ep, stream));
   RLT_TRY(layer_norm_fwd(sv + sl.u2, w->norm2_w, w->norm2_b, out, sv + sl.st2, T, d, e->ln_eps, stream));
   return RLT_OK;
@@ -554,15 +558,15 @@ int rlt_encoder_layer_bwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   RLT_TRY(layer_norm_bwd(d_out, sv + sl.u2, sv + sl.st2, w->norm2_w, d_u, gw->norm2_w, gw->norm2_b, gw->lin2_b, T, d,
                          stream));
   // dW2 += dU2^T h
-  RLT_TRY(gemm_dw(d_u, d, sv + sl.h, f, T, d, f, gw->lin2_w, f, 1.f, stream));
+  RLT_TRY(gemm_dw(d_u, d, sv + sl.h, f, T, d, f, gw->lin2_w, f, 1.f, stream, TAG_DW_FFN2));
   // dHpre = (dU2 W2) * (h > 0) ; db1 += colsum(dHpre)
   EpiParams ep{};
-  ep.alpha = 1.f; ep.out = wide; ep.ldo = f; ep.gate_src = sv + sl.h; ep.colsum = gw->lin1_b;
+  ep.alpha = 1.f; ep.out = wide; ep.ldo = f; ep.gate_src = sv + sl.h; ep.colsum = gw->lin1_b; ep.tag = TAG_D_FFN2;
   RLT_TRY(gemm_nn(d_u, d, w->lin2_w, f, T, f, d, ep, stream));
   // dW1 += dHpre^T y
-  RLT_TRY(gemm_dw(wide, f, sv + sl.y, d, T, f, d, gw->lin1_w, d, 1.f, stream));
+  RLT_TRY(gemm_dw(wide, f, sv + sl.y, d, T, f, d, gw->lin1_w, d, 1.f, stream, TAG_DW_FFN1));
   // dY = dU2 + dHpre W1
-  ep = EpiParams{}; ep.alpha = 1.f; ep.out = d_y; ep.ldo = d; ep.residual = d_u;
+  ep = EpiParams{}; ep.alpha = 1.f; ep.out = d_y; ep.ldo = d; ep.residual = d_u; ep.tag = TAG_D_FFN1;
   RLT_TRY(gemm_nn(wide, f, w->lin1_w, d, T, d, f, ep, stream));
   // LN1 backward: dU1 (into d_u), dgamma1, dbeta1, db_o
   RLT_TRY(layer_norm_bwd(d_y, sv + sl.u1, sv + sl.st1, w->norm1_w, d_u, gw->norm1_w, gw->norm1_b, gw->out_proj_b, T, d,

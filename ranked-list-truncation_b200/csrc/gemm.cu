@@ -4,6 +4,10 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "common.h"
 #include "gemm_tc.cuh"
 
@@ -28,9 +32,26 @@ static int env_int(const char* name, int dflt) {
 }
 static int g_gemm_backend = env_int("RLT_GEMM_BACKEND", 0);
 // Measured on B200 (tests/test_gemm_gpu.py::test_probe_tma_tfloat32_rounding): a TFLOAT32 tensor map makes
-// TMA round fp32 -> tf32 with round-to-nearest-ties-away (bit-identical to cvt.rna.tf32.f32) while it
-// fills shared memory, so operands stay exact fp32 in HBM and no rounded copies are materialised.
+// TMA round fp32 -> tf32 to NEAREST while it fills shared memory (identical to cvt.rna.tf32.f32 except on
+// exact ties), so operands stay exact fp32 in HBM and no rounded copies are materialised.  Without it the
+// tensor core would truncate the low 13 mantissa bits (a systematic -2^-11 relative bias per operand).
 static int g_tma_round = env_int("RLT_TMA_ROUND", 1);
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static int g_time_tag = 0;
+static std::mutex g_time_mu;
+static std::vector<cudaEvent_t> g_time_events;  // begin/end pairs
+void time_begin(int tag, cudaStream_t stream) {
+  if (tag == 0 || tag != g_time_tag) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, stream);
+  std::lock_guard<std::mutex> lk(g_time_mu);
+  g_time_events.push_back(e);
+}
+void time_end(int tag, cudaStream_t stream) { time_begin(tag, stream); }
 
 int gemm_backend() { return g_gemm_backend; }
 bool tma_rounds() { return g_tma_round != 0 && g_gemm_backend == 0; }
@@ -170,7 +191,9 @@ static int launch_tn(const float* A, int lda, const float* B, int ldb, int M, in
   }
   const int tiles = ((M + Cfg::BM - 1) / Cfg::BM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  time_begin(ep.tag, stream);
   gemm_tn_kernel<BN, kBMajorN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+  time_end(ep.tag, stream);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }
@@ -229,7 +252,12 @@ static int launch_dw(const float* A, int lda, const float* B, int ldb, int T, in
 }
 
 int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
-            cudaStream_t stream) {
+            cudaStream_t stream, int tag) {
+  struct Scope {
+    int tag; cudaStream_t s;
+    Scope(int t, cudaStream_t st) : tag(t), s(st) { time_begin(tag, s); }
+    ~Scope() { time_end(tag, s); }
+  } scope(tag, stream);
   RLT_REQUIRE(T > 0 && M > 0 && N > 0, RLT_INVALID_ARG, "gemm_dw: empty problem T=%d M=%d N=%d", T, M, N);
   if (gemm_backend() == 1) {
     const int tchunk = 2048;
@@ -304,8 +332,36 @@ extern "C" {
 const char* rlt_version(void) { return "rlt_b200 0.1.0 (sm_100a)"; }
 const char* rlt_last_error(void) { return g_err; }
 
+unsigned long long rlt_launch_count(void) { return g_launches.load(); }
+
+int rlt_timing_reset(void) {
+  std::lock_guard<std::mutex> lk(g_time_mu);
+  for (cudaEvent_t e : g_time_events) cudaEventDestroy(e);
+  g_time_events.clear();
+  return RLT_OK;
+}
+
+/* Sum of the bracketed kernel durations since the last reset (synchronises on the recorded events). */
+int rlt_timing_read(double* total_ms, int* count) {
+  RLT_REQUIRE(total_ms && count, RLT_INVALID_ARG, "rlt_timing_read: null pointer");
+  std::lock_guard<std::mutex> lk(g_time_mu);
+  double tot = 0.0;
+  int n = 0;
+  for (size_t i = 0; i + 1 < g_time_events.size(); i += 2) {
+    RLT_CHECK_CUDA(cudaEventSynchronize(g_time_events[i + 1]));
+    float ms = 0.f;
+    RLT_CHECK_CUDA(cudaEventElapsedTime(&ms, g_time_events[i], g_time_events[i + 1]));
+    tot += ms;
+    ++n;
+  }
+  *total_ms = tot;
+  *count = n;
+  return RLT_OK;
+}
+
 int rlt_set_option(const char* key, int value) {
   if (key == nullptr) return set_error(RLT_INVALID_ARG, "rlt_set_option: null key");
+  if (strcmp(key, "time_tag") == 0) { g_time_tag = value; return RLT_OK; }
   if (strcmp(key, "gemm_backend") == 0) { g_gemm_backend = value; return RLT_OK; }
   if (strcmp(key, "tma_round") == 0) { g_tma_round = value; return RLT_OK; }
   return set_error(RLT_INVALID_ARG, "rlt_set_option: unknown option '%s'", key);
@@ -314,6 +370,7 @@ int rlt_get_option(const char* key) {
   if (key == nullptr) return set_error(RLT_INVALID_ARG, "rlt_get_option: null key");
   if (strcmp(key, "gemm_backend") == 0) return g_gemm_backend;
   if (strcmp(key, "tma_round") == 0) return g_tma_round;
+  if (strcmp(key, "time_tag") == 0) return g_time_tag;
   return set_error(RLT_INVALID_ARG, "rlt_get_option: unknown option '%s'", key);
 }
 

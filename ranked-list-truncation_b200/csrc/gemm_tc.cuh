@@ -25,6 +25,7 @@ struct EpiParams {
   int relu;               // max(x, 0)
   int accumulate;         // out += result instead of out = result
   float alpha;            // result scale applied first
+  int tag;                // KernelTag of the call site (in-situ timing; 0 = none)
 };
 
 // Sum v[j] over the 32 lanes of a warp for 32 different j: on return lane j holds the column-j

@@ -1,0 +1,102 @@
+"""GPU parity of the encoder layer (fwd + bwd) and of the Choopy-family models against the oracle and
+the reference goldens.  Tolerances follow SURVEY.md section 8(c): TF32 tensor-core contractions with fp32
+accumulate -> outputs max|d| <= 1e-3 * max|ref|, loss rel <= 1e-3, gradients global rel-L2 <= 2e-3 and
+max|d| <= 1e-3 * max over all tensors |g_ref|."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_model, check_weights, grad_errors, load_golden
+from oracle import rlt_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _layer_sd(d, n_head, seed):
+    import warnings
+    torch.manual_seed(seed)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        layer = torch.nn.TransformerEncoderLayer(d_model=d, nhead=n_head, dropout=0.0)
+    with torch.no_grad():   # make the affine LN parameters non-trivial
+        for n, p in layer.named_parameters():
+            if "norm" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    return {k: v.detach().clone() for k, v in layer.state_dict().items()}
+
+
+@pytest.mark.parametrize("backend", [1, 0])
+@pytest.mark.parametrize("d,n_head,S,L,G", [(128, 8, 5, 40, 1), (128, 8, 16, 300, 1), (256, 4, 7, 33, 2),
+                                            (256, 4, 64, 40, 1), (128, 8, 64, 20, 2)])
+def test_encoder_layer_fwd_bwd_vs_oracle(backend, d, n_head, S, L, G):
+    from rlt_b200 import _lib, ops
+    from rlt_b200.autograd import EncoderStack
+    _lib.set_option("gemm_backend", backend)
+    try:
+        sd = _layer_sd(d, n_head, seed=d + S)
+        torch.manual_seed(7)
+        x = torch.randn(G * S, L, d)
+        dy = torch.randn(G * S, L, d) * 0.01
+        # oracle in float64, group by group
+        sd64 = {("layers.0." + k): v.double().requires_grad_(True) for k, v in sd.items()}
+        x64 = x.double().requires_grad_(True)
+        out64 = torch.cat([O.encoder_stack(x64[g * S:(g + 1) * S], sd64, "", n_head) for g in range(G)])
+        (out64 * dy.double()).sum().backward()
+        params = [sd[n].cuda().requires_grad_(True) for n in ops.ENCODER_PARAM_ORDER]
+        xc = x.cuda().requires_grad_(True)
+        out = EncoderStack.apply(xc, n_head, G, 1e-5, *params)
+        (out * dy.cuda()).sum().backward()
+        # backend 1 (exact fp32 FMA) pins the kernel logic at 2e-5.  backend 0 (TF32 tensor cores): outputs at
+        # 1e-3; for gradients this synthetic test (random upstream gradient, a few hundred tokens) only asserts a
+        # smoke-level bound, because TF32 flips the ReLU mask of ~3e-4 of the hidden units whose pre-activation is
+        # ~0, which alone is a ~1e-2 relative error on linear1.weight / linear1.bias (SURVEY.md section 7 item 4
+        # measured the same on emulated TF32).  The 1e-3 contract of section 8(c) is asserted on the real models.
+        tol = 1e-3 if backend == 0 else 2e-5
+        err = (out.detach().cpu().double() - out64.detach()).abs().max().item()
+        assert err <= tol * out64.abs().max().item(), ("out", err)
+        gtol = 1.5e-2 if backend == 0 else 4e-5
+        gmax = max(sd64["layers.0." + n].grad.abs().max().item() for n in ops.ENCODER_PARAM_ORDER)
+        for n, p in zip(ops.ENCODER_PARAM_ORDER, params):
+            ref = sd64["layers.0." + n].grad
+            e = (p.grad.cpu().double() - ref).abs().max().item()
+            assert e <= gtol * gmax, (n, e, gmax)
+        e = (xc.grad.cpu().double() - x64.grad).abs().max().item()
+        assert e <= gtol * x64.grad.abs().max().item(), ("dx", e)
+    finally:
+        _lib.set_option("gemm_backend", 0)
+
+
+@pytest.mark.parametrize("B", [5, 16])
+@pytest.mark.parametrize("name", ["choopy", "mtchoopy"])
+def test_choopy_family_vs_reference_golden(name, B):
+    from utils import losses
+    g = load_golden(f"model_{name}_B{B}.npz")
+    model = build_model(name)
+    check_weights(model, g)
+    model = model.cuda().train()
+    x, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    out = model(x)
+    outs = out if isinstance(out, list) else [out]
+    for i, o in enumerate(outs):
+        ref = g[f"out{i}"]
+        assert tuple(o.shape) == ref.shape
+        err = np.abs(o.detach().cpu().numpy() - ref).max()
+        assert err <= 1e-3 * np.abs(ref).max(), (name, i, err, np.abs(ref).max())
+    # cut positions identical (reference margin is far above the tolerance on these fixtures)
+    assert np.array_equal(np.argmax(outs[-1].detach().cpu().numpy()[..., 0], 1), np.argmax(g[f"out{len(outs)-1}"][..., 0], 1))
+    torch.manual_seed(0)
+    crit = (losses.ChoopyLoss(metric="f1") if name == "choopy" else
+            losses.MtCutLoss(metric="f1", rerank_weight=0.5, classi_weight=0.5, num_tasks=3)).cuda()
+    loss = crit(out, y)
+    ref_loss = float(g["loss"])
+    assert abs(loss.item() - ref_loss) <= 1e-3 * max(abs(ref_loss), 1e-2), (loss.item(), ref_loss)
+    loss.backward()
+    named = {n: (p.grad if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
+    rel_l2, rel_max, rel_norm = grad_errors(named, g)
+    assert rel_l2 <= 2e-3 and rel_max <= 1e-3, (name, rel_l2, rel_max, rel_norm)
+    # eval mode under no_grad (run.py:166-167) gives the same outputs
+    model.eval()
+    with torch.no_grad():
+        out2 = model(x)
+    o2 = out2[-1] if isinstance(out2, list) else out2
+    assert torch.equal(o2, outs[-1].detach())

@@ -25,19 +25,27 @@ def test_round_tf32_matches_bit_definition():
 
 
 def test_probe_tma_tfloat32_rounding(capsys):
-    """Records what a TFLOAT32 tensor map does to fp32 data (rna / rn / truncate / nothing)."""
+    """What a TFLOAT32 tensor map does to fp32 data while TMA fills shared memory: measured = round to
+    nearest (never truncation); it agrees with cvt.rna.tf32 except on exact ties (~2^-13 of random values),
+    so operands can stay exact fp32 in HBM and be rounded by the copy engine for free."""
     from rlt_b200 import _lib
-    x = (torch.randn(128, 32, device="cuda") * 2).contiguous()
-    out = torch.empty_like(x)
-    _lib.check(_lib.load().rlt_probe_tma_tf32(_lib.ptr(x), _lib.ptr(out), 128, _lib.stream_ptr()), "probe")
-    torch.cuda.synchronize()
-    rna = _tf32(x)
-    trunc = (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
-    kinds = {"identity": torch.equal(out, x), "rna": torch.equal(out, rna), "truncate": torch.equal(out, trunc)}
-    print("TMA TFLOAT32 behaviour:", kinds, "max|out-x|/|x|", ((out - x).abs() / x.abs().clamp_min(1e-30)).max().item())
+    n_rna = n_total = 0
+    worst = 0.0
+    for seed in range(16):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        x = (torch.randn(128, 32, device="cuda", generator=g) * 2).contiguous()
+        out = torch.empty_like(x)
+        _lib.check(_lib.load().rlt_probe_tma_tf32(_lib.ptr(x), _lib.ptr(out), 128, _lib.stream_ptr()), "probe")
+        torch.cuda.synchronize()
+        assert ((out.view(torch.int32) & 0x1FFF) == 0).all()                  # result is a tf32 value
+        n_rna += int((out == _tf32(x)).sum())
+        n_total += x.numel()
+        worst = max(worst, ((out - x).abs() / x.abs().clamp_min(1e-30)).max().item())
     with capsys.disabled():
-        print("\n[probe] TMA TFLOAT32 behaviour:", kinds)
-    assert any(kinds.values()) or ((out - x).abs() <= x.abs() * 2**-10).all()
+        print(f"\n[probe] TMA TFLOAT32: {n_rna}/{n_total} equal cvt.rna.tf32; worst relative change {worst:.3e} "
+              f"(half ulp of tf32 = {2**-11:.3e})")
+    assert worst <= 2 ** -11 * 1.0001          # round-to-nearest, not truncation
+    assert n_rna >= n_total - 64               # differs from rna at most on ties
 
 
 @pytest.mark.parametrize("backend", [1, 0])
