@@ -70,6 +70,8 @@ int rlt_linear(const float* A, const float* B, const float* bias, float* C, int 
 /* C[M,N] += alpha * A[T,M]^T B[T,N]  (weight-gradient contraction over tokens). */
 int rlt_grad_weight(const float* A, const float* B, float* C, int T, int M, int N, float alpha,
                     rlt_stream_t stream);
+/* out[c] += sum_t src[t, c]  (bias gradients). n_cols must be a multiple of 4. */
+int rlt_colsum(const float* src, float* out, int n_rows, int n_cols, rlt_stream_t stream);
 /* Probe: TMA-load a [rows<=128, 32] fp32 tile of src through a TFLOAT32 tensor map and copy the
  * shared-memory image (de-swizzled) to dst.  Used once to learn whether TMA rounds or truncates. */
 int rlt_probe_tma_tf32(const float* src, float* dst, int rows, rlt_stream_t stream);
@@ -139,6 +141,63 @@ int rlt_encoder_layer_bwd(const rlt_encoder_desc* desc, const rlt_encoder_weight
                           size_t workspace_bytes, rlt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* K1 — 2-layer bidirectional LSTM, H = 128 (replaces torch.nn.LSTM forward/backward at models/Bicut.py:8-9,19,
+ * AttnCut.py:8,17, MtAttnCut.py:8,22, MMOECut.py:63,88).  Pointers are indexed [layer][direction].   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct rlt_bilstm_desc {
+  int32_t n_lists;
+  int32_t seq_len;
+  int32_t input_size;  /* F: 3 (robust04), 25 / 47 (mq2007); <= 64 or a multiple of 4 */
+  int32_t hidden;      /* 128 */
+  int32_t num_layers;  /* 2 */
+  int32_t training;    /* reserved */
+} rlt_bilstm_desc;
+typedef struct rlt_bilstm_weights {
+  const float* w_ih[2][2]; /* weight_ih_l{k}[_reverse] [512, F or 256] */
+  const float* w_hh[2][2]; /* weight_hh_l{k}[_reverse] [512, 128]      */
+  const float* b_ih[2][2]; /* bias_ih_l{k}[_reverse]   [512]           */
+  const float* b_hh[2][2];
+} rlt_bilstm_weights;
+typedef struct rlt_bilstm_grads { /* accumulated into (+=) */
+  float* w_ih[2][2];
+  float* w_hh[2][2];
+  float* b_ih[2][2];
+  float* b_hh[2][2];
+} rlt_bilstm_grads;
+size_t rlt_bilstm_saved_bytes(const rlt_bilstm_desc* desc);
+size_t rlt_bilstm_workspace_bytes(const rlt_bilstm_desc* desc);
+/* x [B, L, F] -> y [B, L, 256] ([.., :128] forward direction, [.., 128:] reverse).  saved may be NULL (inference). */
+int rlt_bilstm_fwd(const rlt_bilstm_desc* desc, const rlt_bilstm_weights* w, const float* x, float* y, void* saved,
+                   size_t saved_bytes, void* workspace, size_t workspace_bytes, rlt_stream_t stream);
+/* dx may be NULL when the input needs no gradient. */
+int rlt_bilstm_bwd(const rlt_bilstm_desc* desc, const rlt_bilstm_weights* w, const rlt_bilstm_grads* g, const float* x,
+                   const void* saved, const float* dy, float* dx, void* workspace, size_t workspace_bytes,
+                   rlt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K5 — MMOECut gates + towers (models/MMOECut.py:90-105): per-task softmax gate over the flattened LSTM
+ * output, gate-weighted mixture of the experts, Linear(d,1) towers.  Returns tower LOGITS z [Tk, B, L].   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct rlt_moe_desc {
+  int32_t n_lists;
+  int32_t seq_len;
+  int32_t d_lstm;    /* 256: features per position of the LSTM output (gate input = seq_len * d_lstm) */
+  int32_t d_model;   /* expert width (256) */
+  int32_t n_experts; /* <= 4 */
+  int32_t n_tasks;   /* <= 3 */
+} rlt_moe_desc;
+/* w_gates: [Tk, L*d_lstm, E] (the ParameterList stacked); experts: E device pointers to [B, L, d];
+ * tower_w [Tk, d], tower_b [Tk]; outputs gates [Tk, B, E] and z [Tk, B, L]. */
+int rlt_moe_heads_fwd(const rlt_moe_desc* desc, const float* h_lstm, const float* w_gates, const float* const* experts,
+                      const float* tower_w, const float* tower_b, float* gates, float* z, rlt_stream_t stream);
+/* d_experts: E pointers, written; d_tower_w / d_tower_b / d_w_gates: accumulated (+=); d_h_lstm: written or
+ * accumulated (accumulate_dh); dgate_scratch: [Tk, B, E] floats. */
+int rlt_moe_heads_bwd(const rlt_moe_desc* desc, const float* h_lstm, const float* w_gates, const float* const* experts,
+                      const float* tower_w, const float* gates, const float* dz, float* const* d_experts,
+                      float* d_tower_w, float* d_tower_b, float* d_w_gates, float* d_h_lstm, int accumulate_dh,
+                      float* dgate_scratch, rlt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Choopy input assembly (models/Choopy.py:18-20, MtChoopy.py:24-25) and its table gradient.     */
 /* ------------------------------------------------------------------------------------------ */
 int rlt_choopy_embed_fwd(const float* score /*[B,L]*/, const float* pe /*[L,127]*/, float* x /*[B,L,128]*/,
@@ -152,8 +211,12 @@ int rlt_choopy_embed_bwd(const float* dx /*[B,L,128]*/, float* dpe /*[L,127], +=
 int rlt_head_dots_fwd(const float* x /*[T,d]*/, const float* w /*[H,d]*/, const float* bias /*[H]*/,
                       float* z /*[H,T]*/, int n_tokens, int d, int n_heads, rlt_stream_t stream);
 /* dx (+)= sum_h dz[h] w[h]; dw += dz^T x; db += sum dz. */
+/* relu_gate != 0: x is a ReLU output and dx is masked by (x > 0) (BiCut: fc -> ReLU -> Linear(256, 2)). */
 int rlt_head_dots_bwd(const float* x, const float* w, const float* dz /*[H,T]*/, float* dx, float* dw, float* db,
-                      int n_tokens, int d, int n_heads, int accumulate_dx, rlt_stream_t stream);
+                      int n_tokens, int d, int n_heads, int accumulate_dx, int relu_gate, rlt_stream_t stream);
+/* BiCut's nn.Softmax(dim=2) over the two classes: logit planes z [2, T] <-> probabilities o [T, 2]. */
+int rlt_pair_softmax_fwd(const float* z, float* o, size_t n_tokens, rlt_stream_t stream);
+int rlt_pair_softmax_bwd(const float* o, const float* d_o, float* dz, size_t n_tokens, rlt_stream_t stream);
 
 /* softmax over the L positions of every list (nn.Softmax(dim=1) of the cut heads) and its backward */
 int rlt_softmax_lists(const float* z, float* p, int n_lists, int seq_len, rlt_stream_t stream);

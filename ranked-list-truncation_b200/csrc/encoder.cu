@@ -493,6 +493,11 @@ using namespace rlt;
 
 extern "C" {
 
+int rlt_colsum(const float* src, float* out, int n_rows, int n_cols, rlt_stream_t stream) {
+  RLT_REQUIRE(src && out && n_rows > 0 && n_cols > 0, RLT_INVALID_ARG, "rlt_colsum: bad arguments");
+  return colsum(src, out, n_rows, n_cols, static_cast<cudaStream_t>(stream));
+}
+
 size_t rlt_encoder_layer_saved_bytes(const rlt_encoder_desc* e) {
   if (check_desc(e) != RLT_OK) return 0;
   return saved_layout(*e).total * sizeof(float);

@@ -437,7 +437,7 @@ template <int D, int NH>
 __global__ void __launch_bounds__(256) head_dots_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ dz, float* __restrict__ dx,
                                                             float* __restrict__ dw, float* __restrict__ db, int T,
-                                                            int accumulate_dx) {
+                                                            int accumulate_dx, int relu_gate) {
   constexpr int V4 = D / 128;
   __shared__ float red[NH][D];
   __shared__ float redb[NH];
@@ -471,6 +471,9 @@ __global__ void __launch_bounds__(256) head_dots_bwd_kernel(const float* __restr
         o.z = fmaf(g[h], ww[h][i].z, o.z); o.w = fmaf(g[h], ww[h][i].w, o.w);
         aw[h][i].x = fmaf(g[h], a.x, aw[h][i].x); aw[h][i].y = fmaf(g[h], a.y, aw[h][i].y);
         aw[h][i].z = fmaf(g[h], a.z, aw[h][i].z); aw[h][i].w = fmaf(g[h], a.w, aw[h][i].w);
+      }
+      if (relu_gate) {  // x is a ReLU output: pass the gradient only where it was active
+        o.x = a.x > 0.f ? o.x : 0.f; o.y = a.y > 0.f ? o.y : 0.f; o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f;
       }
       reinterpret_cast<float4*>(dx + size_t(t) * D)[lane + 32 * i] = o;
     }
@@ -701,6 +704,27 @@ __global__ void __launch_bounds__(128) choopy_embed_bwd_kernel(const float* __re
   if (c > 0) atomicAdd(dpe + size_t(l) * 127 + c - 1, acc);
 }
 
+// BiCut output head (models/Bicut.py:11-16): 2-class softmax of the logit planes z[0,:], z[1,:] -> o[t, 0:2]
+__global__ void pair_softmax_fwd_kernel(const float* __restrict__ z, float* __restrict__ o, size_t T) {
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float a = z[t], b = z[T + t];
+  const float m = fmaxf(a, b);
+  const float ea = __expf(a - m), eb = __expf(b - m);
+  const float inv = 1.f / (ea + eb);
+  reinterpret_cast<float2*>(o)[t] = make_float2(ea * inv, eb * inv);
+}
+// dz[c, t] = o_c (do_c - <o, do>)
+__global__ void pair_softmax_bwd_kernel(const float* __restrict__ o, const float* __restrict__ d_o, float* __restrict__ dz,
+                                        size_t T) {
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float2 p = reinterpret_cast<const float2*>(o)[t], g = reinterpret_cast<const float2*>(d_o)[t];
+  const float dot = p.x * g.x + p.y * g.y;
+  dz[t] = p.x * (g.x - dot);
+  dz[T + t] = p.y * (g.y - dot);
+}
+
 template <typename F>
 static int dispatch_ni(int L, F&& f) {
   if (L <= 64) return f(std::integral_constant<int, 2>{});
@@ -840,13 +864,14 @@ int rlt_head_dots_fwd(const float* x, const float* w, const float* bias, float* 
 }
 
 int rlt_head_dots_bwd(const float* x, const float* w, const float* dz, float* dx, float* dw, float* db, int n_tokens,
-                      int d, int n_heads, int accumulate_dx, rlt_stream_t stream_) {
+                      int d, int n_heads, int accumulate_dx, int relu_gate, rlt_stream_t stream_) {
   RLT_REQUIRE(x && w && dz && dx && dw && db && n_tokens > 0, RLT_INVALID_ARG, "rlt_head_dots_bwd: bad arguments");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int grid = (n_tokens + 63) / 64;
   const int cap = num_sms() * 4;
   if (grid > cap) grid = cap;
-#define RLT_HB(D, NH) head_dots_bwd_kernel<D, NH><<<grid, 256, 0, stream>>>(x, w, dz, dx, dw, db, n_tokens, accumulate_dx)
+#define RLT_HB(D, NH) \
+  head_dots_bwd_kernel<D, NH><<<grid, 256, 0, stream>>>(x, w, dz, dx, dw, db, n_tokens, accumulate_dx, relu_gate)
   if (d == 128 && n_heads == 1) RLT_HB(128, 1);
   else if (d == 128 && n_heads == 2) RLT_HB(128, 2);
   else if (d == 128 && n_heads == 3) RLT_HB(128, 3);
@@ -855,6 +880,19 @@ int rlt_head_dots_bwd(const float* x, const float* w, const float* dz, float* dx
   else if (d == 256 && n_heads == 3) RLT_HB(256, 3);
   else return set_error(RLT_UNSUPPORTED_SHAPE, "rlt_head_dots: d=%d n_heads=%d unsupported", d, n_heads);
 #undef RLT_HB
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+
+int rlt_pair_softmax_fwd(const float* z, float* o, size_t n_tokens, rlt_stream_t stream_) {
+  RLT_REQUIRE(z && o && n_tokens > 0, RLT_INVALID_ARG, "rlt_pair_softmax_fwd: bad arguments");
+  pair_softmax_fwd_kernel<<<unsigned((n_tokens + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(z, o, n_tokens);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+int rlt_pair_softmax_bwd(const float* o, const float* d_o, float* dz, size_t n_tokens, rlt_stream_t stream_) {
+  RLT_REQUIRE(o && d_o && dz && n_tokens > 0, RLT_INVALID_ARG, "rlt_pair_softmax_bwd: bad arguments");
+  pair_softmax_bwd_kernel<<<unsigned((n_tokens + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(o, d_o, dz, n_tokens);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }

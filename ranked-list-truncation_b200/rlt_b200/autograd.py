@@ -83,6 +83,109 @@ class EncoderStack(torch.autograd.Function):
         return (cur, None, None, None, *grads)
 
 
+class BiLstm(torch.autograd.Function):
+    """nn.LSTM(F, 128, num_layers=2, batch_first=True, bidirectional=True)(x)[0] on [B, L, F] -> [B, L, 256]."""
+
+    @staticmethod
+    def forward(ctx, x, hidden, num_layers, *flat):
+        x = _c(x)
+        B, L, Fin = x.shape
+        flat = [_c(p.detach()) for p in flat]
+        desc = ops.bilstm_desc(B, L, Fin, hidden, num_layers)
+        sv_bytes, ws_bytes = ops.bilstm_sizes(desc)
+        need_grad = any(ctx.needs_input_grad)
+        y = torch.empty(B, L, 2 * hidden, dtype=torch.float32, device=x.device)
+        saved = _buf(sv_bytes, x.device) if need_grad else None
+        ws = _buf(ws_bytes, x.device)
+        ops.bilstm_fwd(desc, ops.bilstm_ptrs(flat), x, y, saved, ws)
+        ctx.desc, ctx.flat, ctx.saved_buf, ctx.x, ctx.ws = desc, flat, saved, x, ws
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        grads = [torch.zeros_like(p) for p in ctx.flat]
+        dx = torch.empty_like(ctx.x) if ctx.needs_input_grad[0] else None
+        ops.bilstm_bwd(ctx.desc, ops.bilstm_ptrs(ctx.flat), ops.bilstm_ptrs(grads), ctx.x, ctx.saved_buf, dy, dx, ctx.ws)
+        ctx.saved_buf = ctx.ws = None
+        return (dx, None, None, *grads)
+
+
+class BicutHead(torch.autograd.Function):
+    """softmax_2( Linear(256,2)( relu( Linear(256,256)(h) ) ) ) of models/Bicut.py:10-16,20-21 (dropout p = 0)."""
+
+    @staticmethod
+    def forward(ctx, h, w1, b1, w2, b2):
+        h, w1, b1, w2, b2 = _c(h), _c(w1.detach()), _c(b1.detach()), _c(w2.detach()), _c(b2.detach())
+        B, L, d = h.shape
+        T = B * L
+        a = torch.empty(T, w1.shape[0], dtype=torch.float32, device=h.device)
+        ops.linear(h.view(T, d), w1, b1, a, relu=True)
+        z = torch.empty(2, T, dtype=torch.float32, device=h.device)
+        ops.head_dots_fwd(a, w2, b2, z, T, w1.shape[0], 2)
+        o = torch.empty(B, L, 2, dtype=torch.float32, device=h.device)
+        ops.pair_softmax_fwd(z, o, T)
+        ctx.save_for_backward(h, w1, w2, a, o)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        h, w1, w2, a, o = ctx.saved_tensors
+        d_o = _c(d_o)
+        B, L, d = h.shape
+        T = B * L
+        f = w1.shape[0]
+        dz = torch.empty(2, T, dtype=torch.float32, device=h.device)
+        ops.pair_softmax_bwd(o, d_o, dz, T)
+        da = torch.empty_like(a)
+        dw2 = torch.zeros_like(w2)
+        db2 = torch.zeros(2, dtype=torch.float32, device=h.device)
+        ops.head_dots_bwd(a, w2, dz, da, dw2, db2, T, f, 2, False, True)      # masked by the ReLU
+        dw1 = torch.zeros_like(w1)
+        db1 = torch.zeros(f, dtype=torch.float32, device=h.device)
+        ops.grad_weight(da, h.view(T, d), dw1)
+        ops.colsum(da, db1)
+        dh = torch.empty_like(h)
+        ops.linear_nn(da, w1, dh.view(T, d))
+        return dh, dw1, db1, dw2, db2
+
+
+class MoeGateMix(torch.autograd.Function):
+    """MMOECut gates, mixtures and tower Linear(d,1) layers (models/MMOECut.py:90-105) -> tower logits [Tk, B, L]."""
+
+    @staticmethod
+    def forward(ctx, h_lstm, w_gates, tower_w, tower_b, *experts):
+        h_lstm, w_gates = _c(h_lstm), _c(w_gates.detach())
+        tower_w, tower_b = _c(tower_w.detach()), _c(tower_b.detach())
+        experts = [_c(e) for e in experts]
+        B, L, dl = h_lstm.shape
+        Tk, J, E = w_gates.shape
+        d = experts[0].shape[2]
+        if J != L * dl:
+            raise RuntimeError(f"w_gates expects {J} gate inputs but the LSTM output has {L}x{dl}")
+        desc = ops.MoeDesc(B, L, dl, d, E, Tk)
+        gates = torch.empty(Tk, B, E, dtype=torch.float32, device=h_lstm.device)
+        z = torch.empty(Tk, B, L, dtype=torch.float32, device=h_lstm.device)
+        ops.moe_heads_fwd(desc, h_lstm, w_gates, experts, tower_w, tower_b, gates, z)
+        ctx.desc = desc
+        ctx.save_for_backward(h_lstm, w_gates, tower_w, gates, *experts)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        h_lstm, w_gates, tower_w, gates, *experts = ctx.saved_tensors
+        dz = _c(dz)
+        d_experts = [torch.empty_like(e) for e in experts]
+        d_tw = torch.zeros_like(tower_w)
+        d_tb = torch.zeros(tower_w.shape[0], dtype=torch.float32, device=dz.device)
+        d_wg = torch.zeros_like(w_gates)
+        d_h = torch.empty_like(h_lstm)
+        scratch = torch.empty_like(gates)
+        ops.moe_heads_bwd(ctx.desc, h_lstm, w_gates, experts, tower_w, gates, dz, d_experts, d_tw, d_tb, d_wg, d_h, False,
+                          scratch)
+        return (d_h, d_wg, d_tw, d_tb, *d_experts)
+
+
 class ChoopyEmbed(torch.autograd.Function):
     """x = cat(score, position_encoding.expand(B, L, 127)) (models/Choopy.py:19-20)."""
 

@@ -146,9 +146,118 @@ def head_dots_fwd(x, w, bias, z, n_tokens, d, n_heads):
           "rlt_head_dots_fwd")
 
 
-def head_dots_bwd(x, w, dz, dx, dw, db, n_tokens, d, n_heads, accumulate_dx=False):
+def head_dots_bwd(x, w, dz, dx, dw, db, n_tokens, d, n_heads, accumulate_dx=False, relu_gate=False):
     check(lib().rlt_head_dots_bwd(ptr(x), ptr(w), ptr(dz), ptr(dx), ptr(dw), ptr(db), n_tokens, d, n_heads,
-                                  int(accumulate_dx), stream_ptr()), "rlt_head_dots_bwd")
+                                  int(accumulate_dx), int(relu_gate), stream_ptr()), "rlt_head_dots_bwd")
+
+
+def pair_softmax_fwd(z, o, n_tokens):
+    check(lib().rlt_pair_softmax_fwd(ptr(z), ptr(o), C.c_size_t(n_tokens), stream_ptr()), "rlt_pair_softmax_fwd")
+
+
+def pair_softmax_bwd(o, d_o, dz, n_tokens):
+    check(lib().rlt_pair_softmax_bwd(ptr(o), ptr(d_o), ptr(dz), C.c_size_t(n_tokens), stream_ptr()), "rlt_pair_softmax_bwd")
+
+
+def linear(a, w, bias, out, relu=False):
+    """out[M,N] = act(a[M,K] w[N,K]^T + bias)  (tcgen05 TF32 GEMM)."""
+    M, K = a.shape
+    N = w.shape[0]
+    check(lib().rlt_linear(ptr(a), ptr(w), ptr(bias), ptr(out), M, N, K, C.c_float(1.0), int(relu), stream_ptr()), "rlt_linear")
+
+
+def linear_nn(a, b, out):
+    """out[M,N] = a[M,K] b[K,N]."""
+    M, K = a.shape
+    N = b.shape[1]
+    check(lib().rlt_linear_nn(ptr(a), ptr(b), ptr(out), M, N, K, stream_ptr()), "rlt_linear_nn")
+
+
+def grad_weight(a, b, out):
+    """out[M,N] += a[T,M]^T b[T,N]."""
+    T, M = a.shape
+    N = b.shape[1]
+    check(lib().rlt_grad_weight(ptr(a), ptr(b), ptr(out), T, M, N, C.c_float(1.0), stream_ptr()), "rlt_grad_weight")
+
+
+def colsum(src, out):
+    """out[C] += sum over rows of src[T, C]."""
+    T, Cc = src.shape
+    check(lib().rlt_colsum(ptr(src), ptr(out), T, Cc, stream_ptr()), "rlt_colsum")
+
+
+# ----------------------------------------------------------------------------------------------
+# BiLSTM
+# ----------------------------------------------------------------------------------------------
+class BilstmDesc(C.Structure):
+    _fields_ = [("n_lists", C.c_int32), ("seq_len", C.c_int32), ("input_size", C.c_int32), ("hidden", C.c_int32),
+                ("num_layers", C.c_int32), ("training", C.c_int32)]
+
+
+class BilstmPtrs(C.Structure):
+    """rlt_bilstm_weights / rlt_bilstm_grads: four [layer][direction] pointer tables."""
+    _fields_ = [("w_ih", C.c_void_p * 4), ("w_hh", C.c_void_p * 4), ("b_ih", C.c_void_p * 4), ("b_hh", C.c_void_p * 4)]
+
+
+def bilstm_ptrs(flat):
+    """flat: nn.LSTM._flat_weights order = per layer, per direction: w_ih, w_hh, b_ih, b_hh (16 tensors)."""
+    if len(flat) != 16:
+        raise RuntimeError(f"expected the 16 parameter tensors of a 2-layer bidirectional LSTM, got {len(flat)}")
+    for t in flat:
+        _require(t, "lstm parameter")
+    p = BilstmPtrs()
+    for i in range(4):      # i = layer * 2 + direction
+        p.w_ih[i], p.w_hh[i], p.b_ih[i], p.b_hh[i] = (flat[4 * i + k].data_ptr() for k in range(4))
+    return p
+
+
+def bilstm_desc(n_lists, seq_len, input_size, hidden=128, num_layers=2):
+    return BilstmDesc(n_lists, seq_len, input_size, hidden, num_layers, 1)
+
+
+def bilstm_sizes(desc):
+    sv = int(lib().rlt_bilstm_saved_bytes(C.byref(desc)))
+    ws = int(lib().rlt_bilstm_workspace_bytes(C.byref(desc)))
+    if sv == 0 or ws == 0:
+        raise _lib.RltError("bilstm: " + _lib.load().rlt_last_error().decode())
+    return sv, ws
+
+
+def bilstm_fwd(desc, weights, x, y, saved, workspace):
+    check(lib().rlt_bilstm_fwd(C.byref(desc), C.byref(weights), ptr(x), ptr(y), ptr(saved),
+                               C.c_size_t(0 if saved is None else saved.numel() * 4), ptr(workspace),
+                               C.c_size_t(workspace.numel() * 4), stream_ptr()), "rlt_bilstm_fwd")
+
+
+def bilstm_bwd(desc, weights, grads, x, saved, dy, dx, workspace):
+    check(lib().rlt_bilstm_bwd(C.byref(desc), C.byref(weights), C.byref(grads), ptr(x), ptr(saved), ptr(dy), ptr(dx),
+                               ptr(workspace), C.c_size_t(workspace.numel() * 4), stream_ptr()), "rlt_bilstm_bwd")
+
+
+# ----------------------------------------------------------------------------------------------
+# MMOECut gates + towers
+# ----------------------------------------------------------------------------------------------
+class MoeDesc(C.Structure):
+    _fields_ = [("n_lists", C.c_int32), ("seq_len", C.c_int32), ("d_lstm", C.c_int32), ("d_model", C.c_int32),
+                ("n_experts", C.c_int32), ("n_tasks", C.c_int32)]
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def moe_heads_fwd(desc, h_lstm, w_gates, experts, tower_w, tower_b, gates, z):
+    check(lib().rlt_moe_heads_fwd(C.byref(desc), ptr(h_lstm), ptr(w_gates), _ptr_array(experts), ptr(tower_w),
+                                  ptr(tower_b), ptr(gates), ptr(z), stream_ptr()), "rlt_moe_heads_fwd")
+
+
+def moe_heads_bwd(desc, h_lstm, w_gates, experts, tower_w, gates, dz, d_experts, d_tower_w, d_tower_b, d_w_gates,
+                  d_h_lstm, accumulate_dh, scratch):
+    check(lib().rlt_moe_heads_bwd(C.byref(desc), ptr(h_lstm), ptr(w_gates), _ptr_array(experts), ptr(tower_w),
+                                  ptr(gates), ptr(dz), _ptr_array(d_experts), ptr(d_tower_w), ptr(d_tower_b),
+                                  ptr(d_w_gates), ptr(d_h_lstm), int(accumulate_dh), ptr(scratch), stream_ptr()),
+          "rlt_moe_heads_bwd")
 
 
 def softmax_lists(z, p, n_lists, seq_len):

@@ -54,7 +54,7 @@ def test_encoder_layer_fwd_bwd_vs_oracle(backend, d, n_head, S, L, G):
         tol = 1e-3 if backend == 0 else 2e-5
         err = (out.detach().cpu().double() - out64.detach()).abs().max().item()
         assert err <= tol * out64.abs().max().item(), ("out", err)
-        gtol = 1.5e-2 if backend == 0 else 4e-5
+        gtol = 4e-2 if backend == 0 else 4e-5
         gmax = max(sd64["layers.0." + n].grad.abs().max().item() for n in ops.ENCODER_PARAM_ORDER)
         for n, p in zip(ops.ENCODER_PARAM_ORDER, params):
             ref = sd64["layers.0." + n].grad
