@@ -92,7 +92,7 @@ typedef struct rlt_encoder_desc {
   int32_t n_head;
   int32_t d_ff;        /* 2048 (torch default dim_feedforward)                                       */
   int32_t attend_axis; /* 0 = across lists (reference); 1 = within a list (not implemented)          */
-  int32_t training;    /* reserved                                                                   */
+  int32_t accumulate_dx; /* backward: d_x += instead of d_x = (several experts share one input)       */
   float ln_eps;        /* 1e-5                                                                       */
   float dropout_p;     /* must be 0 for now                                                          */
   uint64_t dropout_seed;
@@ -135,7 +135,7 @@ size_t rlt_encoder_layer_workspace_bytes(const rlt_encoder_desc* desc);
 /* x, out: [G*S*L, d].  `saved` receives the activations the backward needs. */
 int rlt_encoder_layer_fwd(const rlt_encoder_desc* desc, const rlt_encoder_weights* w, const float* x, float* out,
                           void* saved, size_t saved_bytes, rlt_stream_t stream);
-/* d_x may alias d_out.  workspace: rlt_encoder_layer_workspace_bytes(). */
+/* d_x must not alias d_out.  workspace: rlt_encoder_layer_workspace_bytes(). */
 int rlt_encoder_layer_bwd(const rlt_encoder_desc* desc, const rlt_encoder_weights* w, const rlt_encoder_grads* gw,
                           const float* x, const void* saved, const float* d_out, float* d_x, void* workspace,
                           size_t workspace_bytes, rlt_stream_t stream);

@@ -8,8 +8,9 @@ orchestration differs (the nn.Module path goes through torch.autograd so that th
 can drive it unchanged).
 
 The criterion follows run.py:59-102: Choopy -> ChoopyLoss, AttnCut -> DivLoss(js, tau .85),
-Mt* / MMOECut -> MtCutLoss (JS cut loss + 0.5 rerank hinge + 0.5 BCE), BiCut -> BiCutLoss.  Losses
-are averaged over groups, i.e. data-parallel training of the reference with per-replica batch S.
+Mt* / MMOECut -> MtCutLoss (JS cut loss + rerank_weight * hinge + classi_weight * BCE), BiCut ->
+BiCutLoss.  Group losses are averaged, i.e. data-parallel training of the reference with per-replica
+batch S.
 """
 from __future__ import annotations
 
@@ -18,9 +19,51 @@ import torch
 from . import ops
 from .ops import ENCODER_PARAM_ORDER
 
+KINDS = ("choopy", "mtchoopy", "bicut", "attncut", "mtattncut", "mmoecut")
+
 
 def _enc_layers(enc):
     return [[dict(layer.named_parameters())[n] for n in ENCODER_PARAM_ORDER] for layer in enc.layers]
+
+
+class _EncStack:
+    """One nn.TransformerEncoder: per-layer pointer tables, activations and saved buffers."""
+
+    def __init__(self, eng, enc, accumulate_dx=False):
+        l0 = enc.layers[0]
+        self.d = l0.linear1.in_features
+        self.desc = ops.encoder_desc(eng.G, eng.S, eng.L, self.d, l0.self_attn.num_heads, l0.linear1.out_features,
+                                     l0.norm1.eps)
+        self.desc_first = ops.encoder_desc(eng.G, eng.S, eng.L, self.d, l0.self_attn.num_heads,
+                                           l0.linear1.out_features, l0.norm1.eps, accumulate_dx=accumulate_dx)
+        layers = _enc_layers(enc)
+        self.n = len(layers)
+        self.w = [ops.encoder_ptrs([p.detach() for p in lw]) for lw in layers]
+        self.g = [ops.encoder_ptrs([eng.grad_of(p) for p in lw]) for lw in layers]
+        f32 = dict(dtype=torch.float32, device=eng.dev)
+        self.outs = [torch.empty(eng.T, self.d, **f32) for _ in range(self.n)]
+        sb = (ops.encoder_saved_bytes(self.desc) + 3) // 4
+        self.saved = [torch.empty(sb, **f32) for _ in range(self.n if eng.training else 1)]
+        self.training = eng.training
+
+    def forward(self, x):
+        cur = x
+        for i in range(self.n):
+            ops.encoder_layer_fwd(self.desc, self.w[i], cur, self.outs[i], self.saved[i if self.training else 0])
+            cur = self.outs[i]
+        return cur
+
+    def backward(self, x, d_out, d_x, scratch, ws):
+        """d_out: gradient w.r.t. the stack output (clobbered); writes (or accumulates into) d_x."""
+        cur = d_out
+        for i in reversed(range(self.n)):
+            inp = x if i == 0 else self.outs[i - 1]
+            if i == 0:
+                dst, desc = d_x, self.desc_first
+            else:
+                dst, desc = (scratch[0] if cur is not scratch[0] else scratch[1]), self.desc
+            ops.encoder_layer_bwd(desc, self.w[i], self.g[i], inp, self.saved[i], cur, dst, ws)
+            cur = dst
 
 
 class Engine:
@@ -28,8 +71,10 @@ class Engine:
                  rerank_weight: float = 0.5, classi_weight: float = 0.5, training: bool = True):
         self.model = model
         self.kind = type(model).__name__.lower()
-        if self.kind not in ("choopy", "mtchoopy"):
-            raise NotImplementedError(f"Engine: model family {type(model).__name__} is not wired yet")
+        if self.kind not in KINDS:
+            raise NotImplementedError(f"Engine: unknown model family {type(model).__name__}")
+        if getattr(model, "num_tasks", 3) != 3:
+            raise NotImplementedError("Engine: only num_tasks == 3 is wired (the nn.Module path handles 2.1 / 2.2)")
         self.G, self.S, self.L = n_groups, group_size, seq_len
         self.B = n_groups * group_size
         self.T = self.B * seq_len
@@ -40,51 +85,89 @@ class Engine:
         if not p0.is_cuda:
             raise RuntimeError("Engine: the model must live on a CUDA device (no CPU path)")
         self.dev = p0.device
-        self.timers = None  # set to a dict by bench.py to time selected kernels with CUDA events
+        f32 = dict(dtype=torch.float32, device=self.dev)
 
         # ---- parameters and the flat gradient bucket (one all-reduce payload)
-        self.named_params = [(n, p) for n, p in model.named_parameters()]
-        total = sum(p.numel() for _, p in self.named_params)
-        pad = lambda n: (n + 63) // 64 * 64  # noqa: E731  keep every view 256-byte aligned
-        self.grad_bucket = torch.zeros(sum(pad(p.numel()) for _, p in self.named_params), dtype=torch.float32,
-                                       device=self.dev)
-        self.n_param = total
-        self.grads = {}
+        self.named_params = list(model.named_parameters())
+        pad = lambda n: (n + 63) // 64 * 64  # noqa: E731  every view stays 256-byte aligned
+        self.grad_bucket = torch.zeros(sum(pad(p.numel()) for _, p in self.named_params), **f32)
+        self.n_param = sum(p.numel() for _, p in self.named_params)
+        self.grads, self._by_id = {}, {}
         off = 0
         for n, p in self.named_params:
             self.grads[n] = self.grad_bucket[off:off + p.numel()].view_as(p)
+            self._by_id[id(p)] = n
             off += pad(p.numel())
-        by_id = {id(p): n for n, p in self.named_params}
-        gof = lambda p: self.grads[by_id[id(p)]]  # noqa: E731
 
-        # ---- encoder stack
-        enc = model.attention_layer if self.kind == "choopy" else model.encoding_layer
-        self.d = enc.layers[0].linear1.in_features
-        self.n_head = enc.layers[0].self_attn.num_heads
-        self.desc = ops.encoder_desc(self.G, self.S, self.L, self.d, self.n_head, enc.layers[0].linear1.out_features,
-                                     enc.layers[0].norm1.eps)
-        self.layers = _enc_layers(enc)
-        self.layer_w = [ops.encoder_ptrs([p.detach() for p in lw]) for lw in self.layers]
-        self.layer_g = [ops.encoder_ptrs([gof(p) for p in lw]) for lw in self.layers]
-        f32 = dict(dtype=torch.float32, device=self.dev)
-        nl = len(self.layers)
-        saved_bytes = ops.encoder_saved_bytes(self.desc)
-        self.acts = [torch.empty(self.T, self.d, **f32) for _ in range(nl + 1)]      # layer inputs / outputs
-        n_saved = nl if training else 1
-        self.saved = [torch.empty((saved_bytes + 3) // 4, **f32) for _ in range(n_saved)]
+        k = self.kind
+        # ---- front end
+        self.lstm = None
+        if k in ("choopy", "mtchoopy"):
+            self.pe = model.position_encoding
+            self.d_front = 128
+        else:
+            self.lstm = {"bicut": "bilstm", "attncut": "encoding_layer"}.get(k, "pre_encoding")
+            mod = getattr(model, self.lstm)
+            self.F = mod.input_size
+            self.lstm_desc = ops.bilstm_desc(self.B, self.L, self.F, mod.hidden_size, mod.num_layers)
+            flat = list(mod._flat_weights)
+            self.lstm_w = ops.bilstm_ptrs([p.detach() for p in flat])
+            self.lstm_g = ops.bilstm_ptrs([self.grad_of(p) for p in flat])
+            sv, ws = ops.bilstm_sizes(self.lstm_desc)
+            self.lstm_saved = torch.empty((sv + 3) // 4, **f32) if training else None
+            self.lstm_ws = torch.empty((ws + 3) // 4, **f32)
+            self.d_front = 2 * mod.hidden_size
+        self.front = torch.empty(self.T, self.d_front, **f32)
+
+        # ---- encoder stacks
+        if k == "choopy":
+            self.stacks = [_EncStack(self, model.attention_layer)]
+        elif k == "mtchoopy":
+            self.stacks = [_EncStack(self, model.encoding_layer)]
+        elif k == "attncut":
+            self.stacks = [_EncStack(self, model.attention_layer)]
+        elif k == "mtattncut":
+            self.stacks = [_EncStack(self, model.encoding_layer)]
+        elif k == "mmoecut":
+            self.stacks = [_EncStack(self, ex.attention_layer, accumulate_dx=True) for ex in model.experts]
+        else:
+            self.stacks = []
+        self.d = self.stacks[0].d if self.stacks else self.d_front
         if training:
-            self.ws = torch.empty((ops.encoder_workspace_bytes(self.desc) + 3) // 4, **f32)
-            self.dact = [torch.empty(self.T, self.d, **f32) for _ in range(2)]
+            if self.stacks:
+                self.enc_ws = torch.empty((ops.encoder_workspace_bytes(self.stacks[0].desc) + 3) // 4, **f32)
+            self.dact = [torch.empty(self.T, self.d, **f32) for _ in range(3)]
 
         # ---- heads
-        if self.kind == "choopy":
+        if k in ("choopy", "attncut"):
             self.head_mods = [model.decison_layer[0]]
-        else:
+        elif k in ("mtchoopy", "mtattncut"):
             self.head_mods = [model.classi[0], model.rerank, model.decison_layer[0]]
-        self.H = len(self.head_mods)
-        self.head_w = torch.empty(self.H, self.d, **f32)
+        elif k == "mmoecut":
+            self.head_mods = [t.linear for t in model.towers]
+            self.w_gate_params = list(model.w_gates)
+            Tk, E = len(self.w_gate_params), len(model.experts)
+            self.moe_desc = ops.MoeDesc(self.B, self.L, self.d_front, self.d, E, Tk)
+            self.w_gates = torch.empty(Tk, self.L * self.d_front, E, **f32)
+            self.d_w_gates = torch.zeros_like(self.w_gates)
+            self.gates = torch.empty(Tk, self.B, E, **f32)
+            self.gate_scratch = torch.empty_like(self.gates)
+            self.rerank_probs = torch.empty(self.B, self.L, **f32)
+            if training:
+                self.d_experts = [torch.empty(self.T, self.d, **f32) for _ in range(E)]
+        else:  # bicut
+            self.head_mods = [model.softmax[1]]
+            self.fc_w, self.fc_b = model.fc.weight, model.fc.bias
+            self.fc_out = torch.empty(self.T, model.fc.out_features, **f32)
+            self.probs2 = torch.empty(self.B, self.L, 2, **f32)
+            self.dprobs2 = torch.empty_like(self.probs2)
+            if training:
+                self.d_fc = torch.empty_like(self.fc_out)
+        self.H = 2 if k == "bicut" else len(self.head_mods)
+        self.d_head = self.fc_out.shape[1] if k == "bicut" else self.d
+        self.head_w = torch.empty(self.H, self.d_head, **f32)
         self.head_b = torch.empty(self.H, **f32)
-        self.head_dw = torch.zeros(self.H, self.d, **f32)
+        self.head_dw = torch.zeros(self.H, self.d_head, **f32)
         self.head_db = torch.zeros(self.H, **f32)
         self.z = torch.empty(self.H, self.B, self.L, **f32)
         self.dz = torch.empty(self.H, self.B, self.L, **f32)
@@ -92,83 +175,120 @@ class Engine:
         self.loss_group = torch.empty(self.G, **f32)
         self.status = torch.zeros(self.G, dtype=torch.int32, device=self.dev)
         self.loss = torch.zeros((), **f32)
-        self.pe = model.position_encoding
-        self.refresh_heads()
+        self.refresh()
 
     # ------------------------------------------------------------------------------------------
-    def refresh_heads(self):
-        """Gather the Linear(d,1) head parameters into one [H, d] operand (call after an optimizer step)."""
+    def grad_of(self, p):
+        return self.grads[self._by_id[id(p)]]
+
+    def refresh(self):
+        """Gather small stacked operands from the module parameters (call after every optimizer step)."""
         with torch.no_grad():
-            for i, m in enumerate(self.head_mods):
-                self.head_w[i].copy_(m.weight[0])
-                self.head_b[i].copy_(m.bias[0])
+            if self.kind == "bicut":
+                self.head_w.copy_(self.head_mods[0].weight)
+                self.head_b.copy_(self.head_mods[0].bias)
+            else:
+                for i, m in enumerate(self.head_mods):
+                    self.head_w[i].copy_(m.weight[0])
+                    self.head_b[i].copy_(m.bias[0])
+            if self.kind == "mmoecut":
+                for t, p in enumerate(self.w_gate_params):
+                    self.w_gates[t].copy_(p)
 
-    def _mark(self, name, start: bool):
-        if self.timers is not None and name in self.timers:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            self.timers[name].append(ev)
-
+    # ------------------------------------------------------------------------------------------
     def _forward(self, x):
-        """x: [B, L, 1] scores.  Returns the final hidden states [T, d]."""
-        ops.choopy_embed_fwd(x, self.pe.detach(), self.acts[0])
-        for i in range(len(self.layers)):
-            sv = self.saved[i if self.training else 0]
-            self._mark("encoder_fwd", True)
-            ops.encoder_layer_fwd(self.desc, self.layer_w[i], self.acts[i], self.acts[i + 1], sv)
-            self._mark("encoder_fwd", False)
-        h = self.acts[-1]
-        ops.head_dots_fwd(h, self.head_w, self.head_b, self.z, self.T, self.d, self.H)
-        return h
+        k = self.kind
+        if self.lstm is None:
+            ops.choopy_embed_fwd(x, self.pe.detach(), self.front)
+        else:
+            ops.bilstm_fwd(self.lstm_desc, self.lstm_w, x, self.front, self.lstm_saved, self.lstm_ws)
+        if k == "bicut":
+            ops.linear(self.front, self.fc_w.detach(), self.fc_b.detach(), self.fc_out, relu=True)
+            ops.head_dots_fwd(self.fc_out, self.head_w, self.head_b, self.z, self.T, self.d_head, 2)
+            ops.pair_softmax_fwd(self.z, self.probs2, self.T)
+            return self.fc_out
+        tops = [st.forward(self.front) for st in self.stacks]
+        if k == "mmoecut":
+            ops.moe_heads_fwd(self.moe_desc, self.front, self.w_gates, tops, self.head_w, self.head_b, self.gates, self.z)
+        else:
+            ops.head_dots_fwd(tops[0], self.head_w, self.head_b, self.z, self.T, self.d, self.H)
+        self._tops = tops
+        return tops[0]
+
+    def _criterion(self, y):
+        """Fills self.loss and self.dz (gradient w.r.t. the head logits)."""
+        k, B, G = self.kind, self.B, self.G
+        cut = self.H - 1
+        if k == "bicut":
+            ops.bicut_loss(self.probs2, y, input_kind=1, metric_nci=False, grad=self.dprobs2,
+                           loss_per_list=self.loss_per_list, loss_out=self.loss, grad_scale=1.0 / B, loss_scale=1.0 / B)
+            ops.pair_softmax_bwd(self.probs2, self.dprobs2, self.dz, self.T)
+            return
+        if k == "choopy":
+            ops.cut_loss(self.z[cut], y, loss_kind="choopy", metric=self.metric, tau=1.0, input_kind=0, grad=self.dz[cut],
+                         loss_per_list=self.loss_per_list, loss_out=self.loss, grad_scale=1.0 / B, loss_scale=1.0 / B)
+            return
+        ops.cut_loss(self.z[cut], y, loss_kind="js", metric=self.metric, tau=0.85, input_kind=0, grad=self.dz[cut],
+                     loss_per_list=self.loss_per_list, loss_out=self.loss, grad_scale=1.0 / B, loss_scale=1.0 / B)
+        if k == "attncut":
+            return
+        ops.aux_heads_loss(self.z[0], self.z[1], y, n_groups=G, group_size=self.S, seq_len=self.L,
+                           rerank_softmax=(k == "mmoecut"), class_weight=self.classi_weight,
+                           rerank_weight=self.rerank_weight, grad_scale=1.0 / G, loss_scale=1.0 / G,
+                           out_r=self.rerank_probs if k == "mmoecut" else None, dzc=self.dz[0], dzr=self.dz[1],
+                           loss_group=self.loss_group, status=self.status, loss_out=self.loss, accumulate=True)
 
     def train_step(self, x, y):
         """Forward + criterion + backward.  Gradients land in self.grad_bucket (zeroed first), the scalar
-        loss in self.loss (device).  x: [B, L, F], y: [B, L]."""
+        loss in self.loss (device tensor).  x: [B, L, F], y: [B, L]."""
         if not self.training:
             raise RuntimeError("Engine built with training=False")
+        k = self.kind
         self.grad_bucket.zero_()
         self.head_dw.zero_()
         self.head_db.zero_()
-        h = self._forward(x)
-        B, G = self.B, self.G
-        cut = self.H - 1
-        if self.kind == "choopy":
-            ops.cut_loss(self.z[cut], y, loss_kind="choopy", metric=self.metric, tau=1.0, input_kind=0, grad=self.dz[cut],
-                         loss_per_list=self.loss_per_list, loss_out=self.loss, grad_scale=1.0 / B, loss_scale=1.0 / B)
+        top = self._forward(x)
+        self._criterion(y)
+        d_front = self.dact[2]
+        if k == "bicut":
+            ops.head_dots_bwd(self.fc_out, self.head_w, self.dz, self.d_fc, self.head_dw, self.head_db, self.T,
+                              self.d_head, 2, False, True)
+            ops.grad_weight(self.d_fc, self.front, self.grad_of(self.fc_w))
+            ops.colsum(self.d_fc, self.grad_of(self.fc_b))
+            ops.linear_nn(self.d_fc, self.fc_w.detach(), d_front)
+            self.grad_of(self.head_mods[0].weight).copy_(self.head_dw)
+            self.grad_of(self.head_mods[0].bias).copy_(self.head_db)
         else:
-            ops.cut_loss(self.z[cut], y, loss_kind="js", metric=self.metric, tau=0.85, input_kind=0, grad=self.dz[cut],
-                         loss_per_list=self.loss_per_list, loss_out=self.loss, grad_scale=1.0 / B, loss_scale=1.0 / B)
-            ops.aux_heads_loss(self.z[0], self.z[1], y, n_groups=G, group_size=self.S, seq_len=self.L,
-                               rerank_softmax=False, class_weight=self.classi_weight,
-                               rerank_weight=self.rerank_weight, grad_scale=1.0 / G, loss_scale=1.0 / G,
-                               dzc=self.dz[0], dzr=self.dz[1], loss_group=self.loss_group, status=self.status,
-                               loss_out=self.loss, accumulate=True)
-        d_h = self.dact[0]
-        ops.head_dots_bwd(h, self.head_w, self.dz, d_h, self.head_dw, self.head_db, self.T, self.d, self.H, False)
-        cur, other = self.dact[0], self.dact[1]
-        for i in reversed(range(len(self.layers))):
-            self._mark("encoder_bwd", True)
-            ops.encoder_layer_bwd(self.desc, self.layer_w[i], self.layer_g[i], self.acts[i], self.saved[i], cur, other,
-                                  self.ws)
-            self._mark("encoder_bwd", False)
-            cur, other = other, cur
-        ops.choopy_embed_bwd(cur, self.grads["position_encoding"], self.B, self.L)
-        # scatter the stacked head gradients back to the per-module views of the bucket
-        for i, m in enumerate(self.head_mods):
-            self.grads[self._name_of(m.weight)].copy_(self.head_dw[i:i + 1])
-            self.grads[self._name_of(m.bias)].copy_(self.head_db[i:i + 1])
+            if k == "mmoecut":
+                self.d_w_gates.zero_()
+                ops.moe_heads_bwd(self.moe_desc, self.front, self.w_gates, self._tops, self.head_w, self.gates, self.dz,
+                                  self.d_experts, self.head_dw, self.head_db, self.d_w_gates, d_front, False,
+                                  self.gate_scratch)
+                for st, dtop in zip(self.stacks, self.d_experts):
+                    st.backward(self.front, dtop, d_front, self.dact[:2], self.enc_ws)   # accumulates into d_front
+                for t, p in enumerate(self.w_gate_params):
+                    self.grad_of(p).copy_(self.d_w_gates[t])
+            else:
+                d_top = self.dact[0]
+                ops.head_dots_bwd(top, self.head_w, self.dz, d_top, self.head_dw, self.head_db, self.T, self.d, self.H,
+                                  False, False)
+                self.stacks[0].backward(self.front, d_top, d_front, self.dact[:2], self.enc_ws)
+            for i, m in enumerate(self.head_mods):
+                self.grad_of(m.weight).copy_(self.head_dw[i:i + 1])
+                self.grad_of(m.bias).copy_(self.head_db[i:i + 1])
+        if self.lstm is None:
+            ops.choopy_embed_bwd(d_front, self.grads["position_encoding"], self.B, self.L)
+        else:
+            ops.bilstm_bwd(self.lstm_desc, self.lstm_w, self.lstm_g, x, self.lstm_saved, d_front, None, self.lstm_ws)
         return self.loss
-
-    def _name_of(self, p):
-        for n, q in self.named_params:
-            if q is p:
-                return n
-        raise KeyError
 
     def infer(self, x, y):
         """Forward + fused cut selection and per-list F1 / DCG (K4).  Returns (k, f1, dcg) device tensors."""
         self._forward(x)
-        k, _, _, f1, dcg = ops.eval_cut(self.z[self.H - 1], y, mode=0)   # argmax of logits == argmax of softmax
+        if self.kind == "bicut":
+            k, _, _, f1, dcg = ops.eval_cut(self.probs2, y, mode=1)
+        else:  # argmax of the logits == argmax of their softmax
+            k, _, _, f1, dcg = ops.eval_cut(self.z[self.H - 1], y, mode=0)
         return k, f1, dcg
 
     def apply_grads_to_module(self):

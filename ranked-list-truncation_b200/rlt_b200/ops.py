@@ -23,7 +23,7 @@ LOSS_KINDS = {"choopy": 0, "raml": 1, "kl": 2, "js": 3}
 
 class EncoderDesc(C.Structure):
     _fields_ = [("n_groups", C.c_int32), ("group_size", C.c_int32), ("seq_len", C.c_int32), ("d_model", C.c_int32),
-                ("n_head", C.c_int32), ("d_ff", C.c_int32), ("attend_axis", C.c_int32), ("training", C.c_int32),
+                ("n_head", C.c_int32), ("d_ff", C.c_int32), ("attend_axis", C.c_int32), ("accumulate_dx", C.c_int32),
                 ("ln_eps", C.c_float), ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64)]
 
 
@@ -96,8 +96,10 @@ def ensure_tables():
 # ----------------------------------------------------------------------------------------------
 # encoder layer
 # ----------------------------------------------------------------------------------------------
-def encoder_desc(n_groups, group_size, seq_len, d_model, n_head, d_ff=2048, ln_eps=1e-5, dropout_p=0.0, seed=0):
-    return EncoderDesc(n_groups, group_size, seq_len, d_model, n_head, d_ff, 0, 1, ln_eps, dropout_p, seed)
+def encoder_desc(n_groups, group_size, seq_len, d_model, n_head, d_ff=2048, ln_eps=1e-5, dropout_p=0.0, seed=0,
+                 accumulate_dx=False):
+    return EncoderDesc(n_groups, group_size, seq_len, d_model, n_head, d_ff, 0, int(accumulate_dx), ln_eps, dropout_p,
+                       seed)
 
 
 def encoder_ptrs(tensors) -> EncoderPtrs:
