@@ -123,7 +123,7 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    from rlt_b200 import _lib, ops
+    from rlt_b200 import _lib, ops, parallel
     from rlt_b200.data import synthetic_lists
     from rlt_b200.engine import Engine
     import models
@@ -157,9 +157,7 @@ def main():
     def step(i):
         c = i % n_chunks
         eng.train_step(x_all[c * B:(c + 1) * B], y_all[c * B:(c + 1) * B])
-        if world > 1:
-            dist.all_reduce(eng.grad_bucket)
-            eng.grad_bucket.mul_(1.0 / world)
+        parallel.allreduce_mean_(eng.grad_bucket, G, G * world)
 
     def barrier():
         if world > 1:
@@ -217,9 +215,7 @@ def main():
         dx.copy_(hx, non_blocking=True)
         dy.copy_(hy, non_blocking=True)
         eng.train_step(dx, dy)
-        if world > 1:
-            dist.all_reduce(eng.grad_bucket)
-            eng.grad_bucket.mul_(1.0 / world)
+        parallel.allreduce_mean_(eng.grad_bucket, G, G * world)
         return eng.loss.item()        # device -> host read of the step's result
     for _ in range(2):
         e2e_step()

@@ -1,0 +1,290 @@
+// Cross-list attention on the warp-level tensor-core path (mma.sync.m16n8k8 TF32, fp32 accumulate).
+//
+// One CTA per (position l, group g, head h); the problem is S x S x dh with S = lists per group (<= 128) and
+// dh in {16, 32, 64, 128}: far below a 128-row tcgen05 tile, so each warp owns a 16-row tile and keeps
+// everything in registers.  Score products use the 3xTF32 split (a_hi b_hi + a_lo b_hi + a_hi b_lo) so that the
+// softmax sees ~fp32-accurate logits; P V and the gradient contractions use single TF32.
+// The contraction index of the second GEMM is permuted so that accumulator fragments (cols 2t, 2t+1) feed the
+// next MMA's A fragment (cols t, t+4) without any shuffle: key 8j+2t -> k-slot t, key 8j+2t+1 -> k-slot t+4, and
+// the B fragment rows are read from shared memory with the same permutation.
+// Backward recomputes P from the saved log-sum-exp (no S x S tensor in HBM): phase A per query tile (dQ),
+// phase B per key tile with the transposed products (dK, dV); no atomics.
+#pragma once
+#include "sm100.cuh"
+
+namespace rlt {
+
+__device__ __forceinline__ uint32_t tf32_bits(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// acc[j] (16 x 8 tiles, j < NT) += A[r0 : r0+16, 0:DH] * B[8j : 8j+8, 0:DH]^T ; rows of A and B live in shared memory
+// with pitch DH + 4 floats (conflict-free fragment loads).
+template <int DH, int NT, bool X3>
+__device__ __forceinline__ void tile_abT(const float* __restrict__ sA, int r0, const float* __restrict__ sB,
+                                         float (&acc)[NT][4], int lane) {
+  constexpr int P = DH + 4;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < DH / 8; ++ks) {
+    const float fa0 = sA[(r0 + g) * P + ks * 8 + t], fa1 = sA[(r0 + g + 8) * P + ks * 8 + t];
+    const float fa2 = sA[(r0 + g) * P + ks * 8 + t + 4], fa3 = sA[(r0 + g + 8) * P + ks * 8 + t + 4];
+    const uint32_t a0 = tf32_bits(fa0), a1 = tf32_bits(fa1), a2 = tf32_bits(fa2), a3 = tf32_bits(fa3);
+    uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+    if (X3) {
+      l0 = tf32_bits(fa0 - __uint_as_float(a0)); l1 = tf32_bits(fa1 - __uint_as_float(a1));
+      l2 = tf32_bits(fa2 - __uint_as_float(a2)); l3 = tf32_bits(fa3 - __uint_as_float(a3));
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const float fb0 = sB[(j * 8 + g) * P + ks * 8 + t], fb1 = sB[(j * 8 + g) * P + ks * 8 + t + 4];
+      const uint32_t b0 = tf32_bits(fb0), b1 = tf32_bits(fb1);
+      if (X3) {
+        const uint32_t m0 = tf32_bits(fb0 - __uint_as_float(b0)), m1 = tf32_bits(fb1 - __uint_as_float(b1));
+        mma_tf32(acc[j], l0, l1, l2, l3, b0, b1);   // small terms first
+        mma_tf32(acc[j], a0, a1, a2, a3, m0, m1);
+      }
+      mma_tf32(acc[j], a0, a1, a2, a3, b0, b1);
+    }
+  }
+}
+
+// o[n] (16 x 8 tiles, n < DH/8) += Pfrag[16, 8*NT] * B[0 : 8*NT, 0:DH], Pfrag given as accumulator fragments.
+template <int DH, int NT>
+__device__ __forceinline__ void tile_pB(const float (&p)[NT][4], const float* __restrict__ sB, float (&o)[DH / 8][4],
+                                        int lane) {
+  constexpr int P = DH + 4;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const uint32_t a0 = tf32_bits(p[j][0]), a1 = tf32_bits(p[j][2]), a2 = tf32_bits(p[j][1]), a3 = tf32_bits(p[j][3]);
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      const uint32_t b0 = tf32_bits(sB[(j * 8 + 2 * t) * P + n * 8 + g]);
+      const uint32_t b1 = tf32_bits(sB[(j * 8 + 2 * t + 1) * P + n * 8 + g]);
+      mma_tf32(o[n], a0, a1, a2, a3, b0, b1);
+    }
+  }
+}
+
+// cooperative load of one head's rows of a [T, ld] matrix into shared memory [rows_pad][DH+4]; rows >= S are zero
+template <int DH>
+__device__ __forceinline__ void load_head_rows(float* __restrict__ dst, const float* __restrict__ src, size_t tok0, int L,
+                                               int ld, int S, int rows_pad, float mul) {
+  constexpr int P = DH + 4;
+  for (int i = threadIdx.x; i < rows_pad * (DH / 4); i += blockDim.x) {
+    const int s = i / (DH / 4), c = (i % (DH / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s < S) {
+      v = *reinterpret_cast<const float4*>(src + (tok0 + size_t(s) * L) * ld + c);
+      v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
+    }
+    *reinterpret_cast<float4*>(dst + s * P + c) = v;
+  }
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+template <int DH, int NT>
+__global__ void __launch_bounds__(128) attn_lists_fwd_mma_kernel(const float* __restrict__ qkv, float* __restrict__ o,
+                                                                 float* __restrict__ lse, int S, int L, int d, int n_head,
+                                                                 float scale) {
+  constexpr int P = DH + 4;
+  constexpr int ROWS = NT * 8;
+  extern __shared__ float sm[];
+  float* sQ = sm;
+  float* sK = sQ + ROWS * P;
+  float* sV = sK + ROWS * P;
+  const int l = blockIdx.x, g_ = blockIdx.y, h = blockIdx.z;
+  const size_t tok0 = (size_t(g_) * S) * L + l;
+  const int ld = 3 * d;
+  // q is pre-multiplied by scale * log2(e): scores come out in the exp2 domain
+  load_head_rows<DH>(sQ, qkv + h * DH, tok0, L, ld, S, ROWS, scale * kLog2e);
+  load_head_rows<DH>(sK, qkv + d + h * DH, tok0, L, ld, S, ROWS, 1.f);
+  load_head_rows<DH>(sV, qkv + 2 * d + h * DH, tok0, L, ld, S, ROWS, 1.f);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  for (int r0 = warp * 16; r0 < S; r0 += 64) {
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    tile_abT<DH, NT, true>(sQ, r0, sK, acc, lane);
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int c = j * 8 + 2 * t;
+      if (c >= S) acc[j][0] = acc[j][2] = -INFINITY;
+      if (c + 1 >= S) acc[j][1] = acc[j][3] = -INFINITY;
+      m0 = fmaxf(m0, fmaxf(acc[j][0], acc[j][1]));
+      m1 = fmaxf(m1, fmaxf(acc[j][2], acc[j][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      acc[j][0] = exp2f(acc[j][0] - m0); acc[j][1] = exp2f(acc[j][1] - m0);
+      acc[j][2] = exp2f(acc[j][2] - m1); acc[j][3] = exp2f(acc[j][3] - m1);
+      s0 += acc[j][0] + acc[j][1];
+      s1 += acc[j][2] + acc[j][3];
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    float oacc[DH / 8][4];
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
+    tile_pB<DH, NT>(acc, sV, oacc, lane);
+    const float i0 = 1.f / s0, i1 = 1.f / s1;
+    const int ra = r0 + gq, rb = r0 + gq + 8;
+    if (ra < S) {
+      float* op = o + (tok0 + size_t(ra) * L) * d + h * DH;
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n)
+        *reinterpret_cast<float2*>(op + n * 8 + 2 * t) = make_float2(oacc[n][0] * i0, oacc[n][1] * i0);
+      if (t == 0 && lse != nullptr) lse[(tok0 + size_t(ra) * L) * n_head + h] = (m0 + log2f(s0)) * kLn2;
+    }
+    if (rb < S) {
+      float* op = o + (tok0 + size_t(rb) * L) * d + h * DH;
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n)
+        *reinterpret_cast<float2*>(op + n * 8 + 2 * t) = make_float2(oacc[n][2] * i1, oacc[n][3] * i1);
+      if (t == 0 && lse != nullptr) lse[(tok0 + size_t(rb) * L) * n_head + h] = (m1 + log2f(s1)) * kLn2;
+    }
+  }
+}
+
+template <int DH, int NT>
+__global__ void __launch_bounds__(128) attn_lists_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ o,
+                                                                 const float* __restrict__ lse,
+                                                                 const float* __restrict__ d_o, float* __restrict__ dqkv,
+                                                                 int S, int L, int d, int n_head, float scale) {
+  constexpr int P = DH + 4;
+  constexpr int ROWS = NT * 8;
+  extern __shared__ float sm[];
+  float* sQ = sm;                 // q * scale * log2e
+  float* sK = sQ + ROWS * P;
+  float* sV = sK + ROWS * P;
+  float* sG = sV + ROWS * P;      // dO
+  float* sL = sG + ROWS * P;      // lse * log2e ; +inf for padded rows
+  float* sD = sL + ROWS;          // D_i = dO_i . O_i
+  const int l = blockIdx.x, g_ = blockIdx.y, h = blockIdx.z;
+  const size_t tok0 = (size_t(g_) * S) * L + l;
+  const int ld = 3 * d;
+  load_head_rows<DH>(sQ, qkv + h * DH, tok0, L, ld, S, ROWS, scale * kLog2e);
+  load_head_rows<DH>(sK, qkv + d + h * DH, tok0, L, ld, S, ROWS, 1.f);
+  load_head_rows<DH>(sV, qkv + 2 * d + h * DH, tok0, L, ld, S, ROWS, 1.f);
+  load_head_rows<DH>(sG, d_o + h * DH, tok0, L, d, S, ROWS, 1.f);
+  for (int s = threadIdx.x; s < ROWS; s += blockDim.x) {
+    float lv = INFINITY, dv = 0.f;
+    if (s < S) {
+      const size_t tok = tok0 + size_t(s) * L;
+      lv = lse[tok * n_head + h] * kLog2e;
+      const float* po = o + tok * d + h * DH;
+      const float* pg = d_o + tok * d + h * DH;
+      for (int c = 0; c < DH; ++c) dv = fmaf(po[c], pg[c], dv);
+    }
+    sL[s] = lv;
+    sD[s] = dv;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  // q was scaled by scale*log2e for the exp2-domain scores: dQ = scale * dS K ; dK = dS^T (q_scaled) / log2e
+  const float inv_log2e = 1.f / kLog2e;
+  // ---------------- phase A: query tiles -> dQ
+  for (int r0 = warp * 16; r0 < S; r0 += 64) {
+    float p[NT][4], dp[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      p[j][0] = p[j][1] = p[j][2] = p[j][3] = 0.f;
+      dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+    }
+    tile_abT<DH, NT, true>(sQ, r0, sK, p, lane);
+    tile_abT<DH, NT, false>(sG, r0, sV, dp, lane);
+    const float la = sL[r0 + gq], lb = sL[r0 + gq + 8], da = sD[r0 + gq], db = sD[r0 + gq + 8];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int c = j * 8 + 2 * t;
+      const bool ok0 = c < S, ok1 = c + 1 < S;
+      p[j][0] = ok0 ? exp2f(p[j][0] - la) * (dp[j][0] - da) : 0.f;
+      p[j][1] = ok1 ? exp2f(p[j][1] - la) * (dp[j][1] - da) : 0.f;
+      p[j][2] = ok0 ? exp2f(p[j][2] - lb) * (dp[j][2] - db) : 0.f;
+      p[j][3] = ok1 ? exp2f(p[j][3] - lb) * (dp[j][3] - db) : 0.f;
+    }
+    float acc[DH / 8][4];
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    tile_pB<DH, NT>(p, sK, acc, lane);
+    const int ra = r0 + gq, rb = r0 + gq + 8;
+    if (ra < S) {
+      float* out = dqkv + (tok0 + size_t(ra) * L) * ld + h * DH;
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n)
+        *reinterpret_cast<float2*>(out + n * 8 + 2 * t) = make_float2(acc[n][0] * scale, acc[n][1] * scale);
+    }
+    if (rb < S) {
+      float* out = dqkv + (tok0 + size_t(rb) * L) * ld + h * DH;
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n)
+        *reinterpret_cast<float2*>(out + n * 8 + 2 * t) = make_float2(acc[n][2] * scale, acc[n][3] * scale);
+    }
+  }
+  // ---------------- phase B: key tiles (transposed products) -> dK, dV
+  for (int c0 = warp * 16; c0 < S; c0 += 64) {
+    float p[NT][4], dp[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      p[j][0] = p[j][1] = p[j][2] = p[j][3] = 0.f;
+      dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+    }
+    tile_abT<DH, NT, true>(sK, c0, sQ, p, lane);     // [key, query] scores (exp2 domain: q carries the scale)
+    tile_abT<DH, NT, false>(sV, c0, sG, dp, lane);   // [key, query] dP^T
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int i = j * 8 + 2 * t;                    // query index of columns 0/2 ; i+1 for columns 1/3
+      const float l0 = sL[i], l1 = sL[i + 1], d0 = sD[i], d1 = sD[i + 1];
+      const float p0 = exp2f(p[j][0] - l0), p1 = exp2f(p[j][1] - l1), p2 = exp2f(p[j][2] - l0), p3 = exp2f(p[j][3] - l1);
+      p[j][0] = p0; p[j][1] = p1; p[j][2] = p2; p[j][3] = p3;              // P^T  (0 for padded queries: lse = +inf)
+      dp[j][0] = p0 * (dp[j][0] - d0); dp[j][1] = p1 * (dp[j][1] - d1);    // dS^T
+      dp[j][2] = p2 * (dp[j][2] - d0); dp[j][3] = p3 * (dp[j][3] - d1);
+    }
+    float ak[DH / 8][4], av[DH / 8][4];
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      ak[n][0] = ak[n][1] = ak[n][2] = ak[n][3] = 0.f;
+      av[n][0] = av[n][1] = av[n][2] = av[n][3] = 0.f;
+    }
+    tile_pB<DH, NT>(dp, sQ, ak, lane);
+    tile_pB<DH, NT>(p, sG, av, lane);
+    const int ka = c0 + gq, kb = c0 + gq + 8;
+    if (ka < S) {
+      float* outk = dqkv + (tok0 + size_t(ka) * L) * ld + d + h * DH;
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) {
+        *reinterpret_cast<float2*>(outk + n * 8 + 2 * t) = make_float2(ak[n][0] * inv_log2e, ak[n][1] * inv_log2e);
+        *reinterpret_cast<float2*>(outk + d + n * 8 + 2 * t) = make_float2(av[n][0], av[n][1]);
+      }
+    }
+    if (kb < S) {
+      float* outk = dqkv + (tok0 + size_t(kb) * L) * ld + d + h * DH;
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) {
+        *reinterpret_cast<float2*>(outk + n * 8 + 2 * t) = make_float2(ak[n][2] * inv_log2e, ak[n][3] * inv_log2e);
+        *reinterpret_cast<float2*>(outk + d + n * 8 + 2 * t) = make_float2(av[n][2], av[n][3]);
+      }
+    }
+  }
+}
+
+}  // namespace rlt

@@ -16,6 +16,7 @@
 //   bwd : the chain of SURVEY.md A.2 in reverse; weight grads are token contractions (gemm_dw).
 #include <math.h>
 
+#include "attention_mma.cuh"
 #include "common.h"
 #include "gemm_tc.cuh"
 
@@ -370,10 +371,44 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_kernel(const float* __rest
   }
 }
 
+template <int DH, int NT>
+static int attention_fwd_mma(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head, float scale,
+                             cudaStream_t stream) {
+  const size_t smem = size_t(3) * NT * 8 * (DH + 4) * sizeof(float);
+  RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_mma_kernel<DH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  time_begin(TAG_ATTN_FWD, stream);
+  attn_lists_fwd_mma_kernel<DH, NT><<<dim3(L, G, n_head), 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale);
+  time_end(TAG_ATTN_FWD, stream);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+template <int DH, int NT>
+static int attention_bwd_mma(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int G,
+                             int S, int L, int d, int n_head, float scale, cudaStream_t stream) {
+  const size_t smem = (size_t(4) * NT * 8 * (DH + 4) + 2 * NT * 8) * sizeof(float);
+  RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_mma_kernel<DH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  time_begin(TAG_ATTN_BWD, stream);
+  attn_lists_bwd_mma_kernel<DH, NT><<<dim3(L, G, n_head), 128, smem, stream>>>(qkv, o, lse, d_o, dqkv, S, L, d, n_head, scale);
+  time_end(TAG_ATTN_BWD, stream);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+// tensor-core path available for S <= 128 and dh in {16, 32, 64}
+static bool attention_mma_ok(int S, int dh) { return gemm_backend() == 0 && S <= 128 && (dh == 16 || dh == 32 || dh == 64); }
+
 static int attention_fwd(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head,
                          cudaStream_t stream) {
   const int dh = d / n_head;
   const float scale = 1.0f / sqrtf(float(dh));
+  if (attention_mma_ok(S, dh)) {
+#define RLT_AF(DH_)                                                                                            \
+  return S <= 64 ? attention_fwd_mma<DH_, 8>(qkv, o, lse, G, S, L, d, n_head, scale, stream)                  \
+                 : attention_fwd_mma<DH_, 16>(qkv, o, lse, G, S, L, d, n_head, scale, stream)
+    if (dh == 16) RLT_AF(16);
+    if (dh == 32) RLT_AF(32);
+    RLT_AF(64);
+#undef RLT_AF
+  }
   const dim3 grid(L, G, n_head);
   const size_t smem = size_t(2) * S * (dh + 1) * sizeof(float);
   RLT_REQUIRE(smem <= 200 * 1024, RLT_UNSUPPORTED_SHAPE, "attention: group of %d lists does not fit in shared memory", S);
@@ -399,6 +434,15 @@ static int attention_bwd(const float* qkv, const float* o, const float* lse, con
                          int S, int L, int d, int n_head, cudaStream_t stream) {
   const int dh = d / n_head;
   const float scale = 1.0f / sqrtf(float(dh));
+  if (attention_mma_ok(S, dh)) {
+#define RLT_AB(DH_)                                                                                                  \
+  return S <= 64 ? attention_bwd_mma<DH_, 8>(qkv, o, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream)             \
+                 : attention_bwd_mma<DH_, 16>(qkv, o, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream)
+    if (dh == 16) RLT_AB(16);
+    if (dh == 32) RLT_AB(32);
+    RLT_AB(64);
+#undef RLT_AB
+  }
   const dim3 grid(L, G, n_head);
   const size_t smem = (size_t(4) * S * (dh + 1) + 2 * S) * sizeof(float);
   RLT_REQUIRE(smem <= 200 * 1024, RLT_UNSUPPORTED_SHAPE, "attention bwd: group of %d lists does not fit in shared memory", S);
