@@ -12,9 +12,11 @@
 //   deferred GEMMs     : dW_hh += dA^T Hprev, dW_ih += dA^T X, dX = dA W_ih, db = colsum(dA)   (tcgen05)
 // Saved per (list, t, dir): i, f, g, o, c_t, h_{t-1}  (6 x 128 fp32).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "gemm_tc.cuh"
+#include "lstm_tc.cuh"
 
 namespace rlt {
 
@@ -185,6 +187,17 @@ __global__ void copy_add_kernel(const float* __restrict__ src, float* __restrict
 
 static bool small_k(int K) { return K % 4 != 0 || K < 32; }
 
+// 0 = persistent tcgen05 recurrence (default), 1 = plain validation kernels
+static int g_lstm_backend = -1;
+int lstm_backend() {
+  if (g_lstm_backend < 0) {
+    const char* v = getenv("RLT_LSTM_BACKEND");
+    g_lstm_backend = v ? atoi(v) : 0;
+  }
+  return gemm_backend() == 1 ? 1 : g_lstm_backend;
+}
+void set_lstm_backend(int v) { g_lstm_backend = v; }
+
 static int check_lstm(const rlt_bilstm_desc* d) {
   RLT_REQUIRE(d != nullptr, RLT_INVALID_ARG, "bilstm: null descriptor");
   RLT_REQUIRE(d->n_lists > 0 && d->seq_len > 0 && d->input_size > 0, RLT_INVALID_ARG, "bilstm: bad sizes");
@@ -280,8 +293,19 @@ int rlt_bilstm_fwd(const rlt_bilstm_desc* d, const rlt_bilstm_weights* w, const 
     float* out = l == 0 ? y0 : y;
     float* sv = saved ? saved + (l == 0 ? sl.s0 : sl.s1) : nullptr;
     time_begin(TAG_LSTM, stream);
-    lstm_rec_fwd_kernel<<<dim3(B, 2), H, 0, stream>>>(P, WT + (l * 2) * size_t(H) * G4, WT + (l * 2 + 1) * size_t(H) * G4, out,
-                                                      sv, L);
+    if (lstm_backend() == 0) {
+      static bool attr = false;
+      if (!attr) {
+        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            int(LstmFwdSmem::TOTAL)));
+        attr = true;
+      }
+      lstm_rec_fwd_tc_kernel<<<dim3((B + 127) / 128, 2), 288, LstmFwdSmem::TOTAL, stream>>>(P, w->w_hh[l][0], w->w_hh[l][1],
+                                                                                           out, sv, B, L);
+    } else {
+      lstm_rec_fwd_kernel<<<dim3(B, 2), H, 0, stream>>>(P, WT + (l * 2) * size_t(H) * G4, WT + (l * 2 + 1) * size_t(H) * G4,
+                                                        out, sv, L);
+    }
     time_end(TAG_LSTM, stream);
     RLT_CHECK_LAUNCH();
   }
@@ -307,7 +331,26 @@ int rlt_bilstm_bwd(const rlt_bilstm_desc* d, const rlt_bilstm_weights* w, const 
     const float* sv = saved + (l == 0 ? sl.s0 : sl.s1);
     const float* dout = l == 1 ? dy : dY0;
     time_begin(TAG_LSTM, stream);
-    lstm_rec_bwd_kernel<<<dim3(B, 2), H, 0, stream>>>(dout, sv, w->w_hh[l][0], w->w_hh[l][1], dA, L);
+    if (lstm_backend() == 0) {
+      // power-of-two scale that brings the incoming gradient into fp16's normal range (unscaled on read-back)
+      unsigned int* amax = reinterpret_cast<unsigned int*>(colsum_scratch + 2 * G4);
+      float* scale = colsum_scratch + 2 * G4 + 4;
+      RLT_CHECK_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), stream));
+      amax_abs_kernel<<<num_sms() * 4, 256, 0, stream>>>(dout, size_t(T) * 2 * H, amax);
+      RLT_CHECK_LAUNCH();
+      grad_scale_kernel<<<1, 1, 0, stream>>>(amax, scale);
+      RLT_CHECK_LAUNCH();
+      static bool attr = false;
+      if (!attr) {
+        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            int(LstmBwdSmem::TOTAL)));
+        attr = true;
+      }
+      lstm_rec_bwd_tc_kernel<<<dim3((B + 127) / 128, 2), 288, LstmBwdSmem::TOTAL, stream>>>(dout, sv, w->w_hh[l][0],
+                                                                                           w->w_hh[l][1], scale, dA, B, L);
+    } else {
+      lstm_rec_bwd_kernel<<<dim3(B, 2), H, 0, stream>>>(dout, sv, w->w_hh[l][0], w->w_hh[l][1], dA, L);
+    }
     time_end(TAG_LSTM, stream);
     RLT_CHECK_LAUNCH();
     // biases: db_ih = db_hh = column sums of dA

@@ -62,6 +62,9 @@ int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int 
 
 // 0 = tcgen05 tensor-core kernels (default), 1 = plain SIMT kernels (validation backend only)
 int gemm_backend();
+// 0 = persistent tcgen05 LSTM recurrence (default), 1 = plain validation kernels (also forced by gemm_backend 1)
+int lstm_backend();
+void set_lstm_backend(int v);
 // true when the TMA tensor maps are encoded as TFLOAT32 (TMA rounds fp32->tf32 while loading), so
 // producers need not materialise rounded operand copies.
 bool tma_rounds();

@@ -362,6 +362,7 @@ int rlt_timing_read(double* total_ms, int* count) {
 int rlt_set_option(const char* key, int value) {
   if (key == nullptr) return set_error(RLT_INVALID_ARG, "rlt_set_option: null key");
   if (strcmp(key, "time_tag") == 0) { g_time_tag = value; return RLT_OK; }
+  if (strcmp(key, "lstm_backend") == 0) { set_lstm_backend(value); return RLT_OK; }
   if (strcmp(key, "gemm_backend") == 0) { g_gemm_backend = value; return RLT_OK; }
   if (strcmp(key, "tma_round") == 0) { g_tma_round = value; return RLT_OK; }
   return set_error(RLT_INVALID_ARG, "rlt_set_option: unknown option '%s'", key);
@@ -371,6 +372,7 @@ int rlt_get_option(const char* key) {
   if (strcmp(key, "gemm_backend") == 0) return g_gemm_backend;
   if (strcmp(key, "tma_round") == 0) return g_tma_round;
   if (strcmp(key, "time_tag") == 0) return g_time_tag;
+  if (strcmp(key, "lstm_backend") == 0) return lstm_backend();
   return set_error(RLT_INVALID_ARG, "rlt_get_option: unknown option '%s'", key);
 }
 

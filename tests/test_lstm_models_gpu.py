@@ -80,3 +80,33 @@ def test_lstm_family_vs_reference_golden(name, B):
         out2 = model(x)
     o2 = out2[-1] if isinstance(out2, list) else out2
     assert torch.allclose(o2, outs[-1].detach(), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("B,L,F", [(3, 17, 3), (130, 40, 3), (257, 23, 25)])
+def test_bilstm_tcgen05_recurrence_matches_plain_kernels(B, L, F):
+    """The persistent tcgen05 recurrence (fp16 operands, fp32 accumulate) against the plain fp32 kernels, forward
+    and backward, including ragged tiles (B not a multiple of 128)."""
+    from rlt_b200 import _lib
+    from rlt_b200.autograd import BiLstm
+    torch.manual_seed(B + L)
+    lstm = torch.nn.LSTM(input_size=F, hidden_size=128, num_layers=2, batch_first=True, bidirectional=True).cuda()
+    x = torch.randn(B, L, F, device="cuda")
+    dy = torch.randn(B, L, 256, device="cuda") * 1e-4
+    res = {}
+    for be in (1, 0):
+        _lib.set_option("lstm_backend", be)
+        try:
+            lstm.zero_grad(set_to_none=True)
+            xc = x.clone().requires_grad_(True)
+            y = BiLstm.apply(xc, 128, 2, *lstm._flat_weights)
+            (y * dy).sum().backward()
+            res[be] = (y.detach().clone(), {n: p.grad.clone() for n, p in lstm.named_parameters()}, xc.grad.clone())
+        finally:
+            _lib.set_option("lstm_backend", 0)
+    y1, g1, dx1 = res[1]
+    y0, g0, dx0 = res[0]
+    assert (y0 - y1).abs().max().item() <= 1e-3
+    gmax = max(v.abs().max().item() for v in g1.values())
+    for n in g1:
+        assert (g0[n] - g1[n]).abs().max().item() <= 2e-3 * gmax, n
+    assert (dx0 - dx1).abs().max().item() <= 2e-3 * dx1.abs().max().item()
