@@ -34,6 +34,27 @@ GROUP = 64
 METRIC = "ranked lists/sec (train step, L=300)"
 
 
+N_FEATURES = {"choopy": 1, "mtchoopy": 1, "bicut": 3, "attncut": 3, "mtattncut": 3, "mmoecut": 3}
+CRITERION = {"choopy": "ChoopyLoss f1", "mtchoopy": "MtCutLoss f1", "bicut": "BiCutLoss", "attncut": "DivLoss js f1",
+             "mtattncut": "MtCutLoss f1", "mmoecut": "MtCutLoss f1"}
+
+
+def build_model(models, name):
+    if name == "choopy":
+        return models.Choopy(seq_len=SEQ_LEN, dropout=0.0)
+    if name == "mtchoopy":
+        return models.MtChoopy(seq_len=SEQ_LEN, num_tasks=3, dropout=0.0)
+    if name == "bicut":
+        return models.BiCut(input_size=3, dropout=0.0)
+    if name == "attncut":
+        return models.AttnCut(input_size=3, dropout=0.0)
+    if name == "mtattncut":
+        return models.MtAttnCut(input_size=3, num_tasks=3, dropout=0.0)
+    if name == "mmoecut":
+        return models.MMOECut(seq_len=SEQ_LEN, num_tasks=3, input_size=3, dropout=0.0, num_experts=3)
+    raise SystemExit(f"unknown model {name}")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -99,7 +120,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     n_batches = 2
-    x, y = synthetic_lists(GROUP * n_batches, SEQ_LEN, 1, seed=20240229, device="cpu")
+    x, y = synthetic_lists(GROUP * n_batches, SEQ_LEN, N_FEATURES[args.model], seed=20240229, device="cpu")
     steps, warm = max(1, min(args.steps, 4)), max(1, min(args.warmup, 1))
     lps, times = torch_port.time_lists_per_s(args.model, x, y, GROUP, "train", steps=steps, warmup=warm)
     ilps, _ = torch_port.time_lists_per_s(args.model, x, y, GROUP, "infer", steps=steps, warmup=warm)
@@ -146,12 +167,11 @@ def main():
     shard = DATASET_LISTS // world                  # lists resident on this GPU
     if shard < B:
         shard = B
-    x_all, y_all = synthetic_lists(shard, SEQ_LEN, 1, seed=20240229 + rank, device=dev)
+    x_all, y_all = synthetic_lists(shard, SEQ_LEN, N_FEATURES[args.model], seed=20240229 + rank, device=dev)
     n_chunks = shard // B
 
     torch.manual_seed(1234)
-    cls = {"choopy": models.Choopy, "mtchoopy": models.MtChoopy}[args.model]
-    model = cls(seq_len=SEQ_LEN, dropout=0.0).to(dev)
+    model = build_model(models, args.model).to(dev)
     eng = Engine(model, n_groups=G, group_size=GROUP, seq_len=SEQ_LEN, training=True)
 
     def step(i):
@@ -241,7 +261,7 @@ def main():
     # ---------------- roofline of the kernel timed in situ
     hbm, tf_burst, tf_sust, src = measured_peaks()
     T = B * SEQ_LEN
-    d, dff = 128, 2048
+    d, dff = eng.d, 2048
     roof = None
     if cnt.value > 0:
         avg_s = tot_ms.value / cnt.value * 1e-3
@@ -264,7 +284,7 @@ def main():
         from oracle import torch_port
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        cx, cy = synthetic_lists(GROUP * 2, SEQ_LEN, 1, seed=20240229, device="cpu")
+        cx, cy = synthetic_lists(GROUP * 2, SEQ_LEN, N_FEATURES[args.model], seed=20240229, device="cpu")
         lps, times = torch_port.time_lists_per_s(args.model, cx, cy, GROUP, "train", steps=3, warmup=1)
         cpu = {"value": lps, "unit": "lists/s", "cores": cores, "kind": "port",
                "sample": f"3 reference-style train steps (fwd + Python-loop criterion + bwd + host metrics) on one batch of "
@@ -273,7 +293,7 @@ def main():
     line = {"metric": METRIC, "value": train_lps, "unit": "lists/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": f"{args.model} train step (fwd + ChoopyLoss f1 + bwd{' + NCCL grad all-reduce' if world > 1 else ''}), "
+            "config": {"workload": f"{args.model} train step (fwd + {CRITERION[args.model]} + bwd{' + NCCL grad all-reduce' if world > 1 else ''}), "
                                    f"{DATASET_LISTS} synthetic robust04-shaped lists x {SEQ_LEN} resident in HBM",
                        "lists_per_step_per_gpu": B, "attention_group": GROUP, "seq_len": SEQ_LEN,
                        "l2": "inputs and activations of one step (>10 GB) exceed the 126 MB L2; no explicit flush",

@@ -115,6 +115,18 @@ lstm_rec_fwd_tc_kernel(const float* __restrict__ P, const float* __restrict__ wh
           umma_commit(&bar_acc[hf]);
         }
       }
+    } else {
+      // lanes 1..31: pull the P rows (2 KB per list, contiguous) of the step that is kPrefetch ahead into L2, paced by
+      // the accumulator barrier, so that the gate warps' dependent loads hit L2 instead of DRAM
+      constexpr int kPrefetch = 3;
+      for (int step = 0; step < L; ++step) {
+        if (step >= kPrefetch) mbar_wait(&bar_acc[0], (step - kPrefetch) & 1);
+        const int t = dir ? (L - 1 - step) : step;
+        for (int r = lane - 1; r < 128; r += 31) {
+          const int bb = tile * 128 + r;
+          if (bb < B) prefetch_l2_bulk(P + (size_t(bb) * L + t) * (2 * LG4) + dir * LG4, LG4 * 4);
+        }
+      }
     }
   } else {
     // ------------------------------ gate warps ------------------------------
@@ -304,6 +316,22 @@ lstm_rec_bwd_tc_kernel(const float* __restrict__ dy, const float* __restrict__ s
           }
         }
         umma_commit(bar_d);
+      }
+    } else {
+      // lanes 1..31: L2 prefetch of the saved record (3 KB) and dy row (512 B) of the step kPrefetch ahead
+      constexpr int kPrefetch = 3;
+      for (int it = 0; it < L; ++it) {
+        if (it >= kPrefetch) mbar_wait(bar_d, (it - kPrefetch) & 1);
+        const int step = L - 1 - it;
+        const int t = dir ? (L - 1 - step) : step;
+        for (int r = lane - 1; r < 128; r += 31) {
+          const int bb = tile * 128 + r;
+          if (bb < B) {
+            const size_t tok = size_t(bb) * L + t;
+            prefetch_l2_bulk(saved + (tok * 2 + dir) * (LSAVE * LH), LSAVE * LH * 4);
+            prefetch_l2_bulk(dy + tok * (2 * LH) + dir * LH, LH * 4);
+          }
+        }
       }
     }
   } else {

@@ -99,6 +99,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// Bulk prefetch of a contiguous global range into L2 (no shared-memory destination).  size: multiple of 16.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // TMEM allocation (whole warp executes; column count power of two >= 32)
 // ------------------------------------------------------------------------------------------
