@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(128) attn_lists_fwd_mma_kernel(const float* __
 }
 
 template <int DH, int NT>
-__global__ void __launch_bounds__(128) attn_lists_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ o,
+__global__ void __launch_bounds__(128, 4) attn_lists_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ o,
                                                                  const float* __restrict__ lse,
                                                                  const float* __restrict__ d_o, float* __restrict__ dqkv,
                                                                  int S, int L, int d, int n_head, float scale) {

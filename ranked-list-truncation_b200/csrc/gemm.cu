@@ -151,11 +151,8 @@ __global__ void gemm_tn_simt_kernel(const float* __restrict__ A, int lda, const 
       const size_t off = size_t(r) * ep.ldo + c;
       if (ep.gate_src) v = ep.gate_src[off] > 0.f ? v : 0.f;
       if (ep.residual) v += ep.residual[off];
-      if (ep.out) {
-        if (ep.accumulate) v += ep.out[off];
-        ep.out[off] = v;
-      }
-      if (ep.out_tf32) ep.out_tf32[off] = to_tf32(v);
+      if (ep.accumulate) v += ep.out[off];
+      ep.out[off] = v;
       if (ep.colsum) atomicAdd(ep.colsum + c, v);
     }
 }
@@ -175,27 +172,55 @@ __global__ void gemm_dw_simt_kernel(const float* __restrict__ A, int lda, const 
 // ------------------------------------------------------------------------------------------
 // front-ends
 // ------------------------------------------------------------------------------------------
+template <int BN, bool kBMajorN, int EF>
+static int launch_tn_ef(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& ep, int grid,
+                        cudaStream_t stream) {
+  using Cfg = GemmTnCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, kBMajorN, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(Cfg::SMEM_BYTES)));
+    attr_set = true;
+  }
+  time_begin(ep.tag, stream);
+  gemm_tn_kernel<BN, kBMajorN, EF><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+  time_end(ep.tag, stream);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+
 template <int BN, bool kBMajorN>
 static int launch_tn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
                      cudaStream_t stream) {
   using Cfg = GemmTnCfg<BN>;
+  RLT_REQUIRE(ep.out != nullptr, RLT_INVALID_ARG, "gemm: null output");
   CUtensorMap tmA, tmB;
   RLT_TRY(make_tmap(&tmA, A, M, K, lda, Cfg::BM, tma_rounds()));
   if (kBMajorN) RLT_TRY(make_tmap(&tmB, B, K, N, ldb, Cfg::BK, tma_rounds(), true));
   else RLT_TRY(make_tmap(&tmB, B, N, K, ldb, BN, tma_rounds()));
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, kBMajorN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        int(Cfg::SMEM_BYTES)));
-    attr_set = true;
+  // grid = a multiple of the number of column blocks (each CTA keeps one column block, see the kernel), at most
+  // one CTA per SM and no more row-block walkers than there are row blocks
+  const int tiles_m = (M + Cfg::BM - 1) / Cfg::BM, tiles_n = N / BN;
+  RLT_REQUIRE(tiles_n <= num_sms(), RLT_UNSUPPORTED_SHAPE, "gemm: N=%d needs more column blocks than there are SMs", N);
+  int walkers = num_sms() / tiles_n;
+  if (walkers > tiles_m) walkers = tiles_m;
+  const int grid = walkers * tiles_n;
+  // epilogue specialisations of the hot call sites (encoder / BiLSTM); anything else takes the run-time epilogue
+  if (BN >= 128) {
+    switch (epi_mask(ep)) {
+#define RLT_EF_CASE(mask) case (mask): return launch_tn_ef<BN, kBMajorN, (mask)>(tmA, tmB, M, N, K, ep, grid, stream)
+      RLT_EF_CASE(0);
+      RLT_EF_CASE(EF_BIAS);
+      RLT_EF_CASE(EF_BIAS | EF_RELU);
+      RLT_EF_CASE(EF_BIAS | EF_RES);
+      RLT_EF_CASE(EF_GATE | EF_COLSUM);
+      RLT_EF_CASE(EF_RES);
+      RLT_EF_CASE(EF_ACC);
+#undef RLT_EF_CASE
+      default: break;
+    }
   }
-  const int tiles = ((M + Cfg::BM - 1) / Cfg::BM) * (N / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  time_begin(ep.tag, stream);
-  gemm_tn_kernel<BN, kBMajorN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
-  time_end(ep.tag, stream);
-  RLT_CHECK_LAUNCH();
-  return RLT_OK;
+  return launch_tn_ef<BN, kBMajorN, EF_RUNTIME>(tmA, tmB, M, N, K, ep, grid, stream);
 }
 
 template <bool kBMajorN>
@@ -305,7 +330,7 @@ __global__ void transpose_round_kernel(const float* __restrict__ src, float* __r
 // ------------------------------------------------------------------------------------------
 __global__ void probe_tma_kernel(const __grid_constant__ CUtensorMap tm, float* __restrict__ dst, int rows) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align1024(smem_raw);
   __shared__ uint64_t bar;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);

@@ -5,18 +5,20 @@
 //                                                         contraction over the token axis, split
 //                                                         over CTAs, fp32 red.add into C)
 //
-// Roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> global), one TMEM lane (= output row) per thread.
-// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the main loop of
-// tile i+1.  Operands are fp32 containers holding TF32-rounded values (see to_tf32()).
+// Roles per CTA (gemm_tn: 320 threads): warp 0 = TMA producer, warp 1 = single-thread MMA issuer,
+// warps 2..9 = epilogue.  An epilogue warp reads its TMEM lane quarter (tcgen05.ld: one output row
+// per thread), transposes the 32x32 chunk through a private swizzled 4 KB shared-memory buffer and
+// then touches global memory with whole 128-byte row segments per 8 lanes (4 L1 wavefronts per
+// 128-bit warp access instead of 32), for the output store as well as for the gate / residual /
+// accumulate reads.  Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Operands are fp32 in HBM; the TFLOAT32 tensor maps round them on load.
 #pragma once
 #include "sm100.cuh"
 
 namespace rlt {
 
 struct EpiParams {
-  float* out;             // [M, ldo] fp32 result (may be null)
-  float* out_tf32;        // same values rounded to tf32 (operand copy for the next GEMM; may be null)
+  float* out;             // [M, ldo] fp32 result
   int ldo;
   const float* bias;      // [N] added to every row (may be null)
   const float* gate_src;  // [M, ldo]: result *= (gate_src > 0)   (ReLU backward; may be null)
@@ -53,86 +55,135 @@ struct GemmTnCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + size_t(STAGES) * STAGE_BYTES + 256 /*barriers*/;
+  static constexpr int EPI_WARPS = 8;               // two warps per TMEM lane quarter (even / odd 32-column chunks)
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // one 32x32 fp32 chunk per epilogue warp
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + size_t(STAGES) * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES +
+                                       BN * 4 /*column sums*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void epilogue_store_chunk(const EpiParams& ep, float (&v)[32], int row, int M,
-                                                     int col0, int lane, float* s_colsum /*per warp [32] or null*/) {
-  const bool row_ok = row < M;
+// Epilogue feature mask (template parameter EF of the kernels): call sites with a known combination get a kernel in
+// which the unused branches do not exist (the fully unrolled epilogue is otherwise ~3700 instructions and the eight
+// epilogue warps thrash the instruction cache: measured +30-45% on the store-bound GEMMs); EF_RUNTIME keeps every
+// branch and tests the EpiParams fields at run time.
+enum : int { EF_BIAS = 1, EF_RELU = 2, EF_GATE = 4, EF_RES = 8, EF_COLSUM = 16, EF_ACC = 32, EF_RUNTIME = 64 };
+__host__ __device__ inline int epi_mask(const EpiParams& ep) {
+  return (ep.bias ? EF_BIAS : 0) | (ep.relu ? EF_RELU : 0) | (ep.gate_src ? EF_GATE : 0) | (ep.residual ? EF_RES : 0) |
+         (ep.colsum ? EF_COLSUM : 0) | (ep.accumulate ? EF_ACC : 0);
+}
+template <int EF> __device__ __forceinline__ bool ef_bias(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.bias != nullptr : (EF & EF_BIAS) != 0; }
+template <int EF> __device__ __forceinline__ bool ef_relu(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.relu != 0 : (EF & EF_RELU) != 0; }
+template <int EF> __device__ __forceinline__ bool ef_gate(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.gate_src != nullptr : (EF & EF_GATE) != 0; }
+template <int EF> __device__ __forceinline__ bool ef_res(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.residual != nullptr : (EF & EF_RES) != 0; }
+template <int EF> __device__ __forceinline__ bool ef_colsum(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.colsum != nullptr : (EF & EF_COLSUM) != 0; }
+template <int EF> __device__ __forceinline__ bool ef_acc(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.accumulate != 0 : (EF & EF_ACC) != 0; }
+
+// Operand of the epilogue that comes from global memory, fetched for a whole 32x32 chunk BEFORE the accumulator is
+// read so that the 8 independent 128-bit loads per lane are in flight together instead of one DRAM round trip per
+// row group (measured: 25 us per tile for the serial form of dH = (dU W2) * [h > 0]).  Only ONE operand is
+// prefetched - the gate source, else the residual, else the running output of an accumulating store; a second one
+// (no call site has it on the hot path) is read inside the loop.
+struct EpiAux {
+  float4 a[8];
+};
+template <int EF>
+__device__ __forceinline__ const float* epi_aux_src(const EpiParams& ep) {
+  if (ef_gate<EF>(ep)) return ep.gate_src;
+  if (ef_res<EF>(ep)) return ep.residual;
+  if (ef_acc<EF>(ep)) return ep.out;
+  return nullptr;
+}
+template <int EF>
+__device__ __forceinline__ void epilogue_fetch_aux(const EpiParams& ep, EpiAux& aux, int row0, int M, int col0, int lane) {
+  const float* src = epi_aux_src<EF>(ep);
+  if (src == nullptr) return;
+  const int col = col0 + (lane & 7) * 4;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
-  if (ep.bias != nullptr) {
-#pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j4);
-      v[4 * j4 + 0] += b.x; v[4 * j4 + 1] += b.y; v[4 * j4 + 2] += b.z; v[4 * j4 + 3] += b.w;
-    }
+  for (int it = 0; it < 8; ++it) {
+    const int row = row0 + it * 4 + (lane >> 3);
+    aux.a[it] = row < M ? *reinterpret_cast<const float4*>(src + size_t(row) * ep.ldo + col) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (ep.relu) {
+}
+
+// One 32 (rows) x 32 (columns) accumulator chunk: v[] holds this lane's ROW (lane = row inside the warp's TMEM lane
+// quarter).  The chunk is transposed through `stage` (4 KB, private to the warp, 16-byte units XOR-swizzled by the
+// row so that both phases are bank-conflict free) and then processed with lane = (row % 4 group, 16-byte column
+// unit): every global access of the warp covers 4 rows x 128 contiguous bytes.  Column sums of the final values
+// (bias gradients) are reduced in the warp and added to the CTA's shared-memory accumulator.
+template <int EF>
+__device__ __forceinline__ void epilogue_store_chunk(const EpiParams& ep, float (&v)[32], const EpiAux& aux, uint8_t* stage,
+                                                     int row0, int M, int col0, int lane,
+                                                     float* s_colsum /* [32] of this chunk */) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-  }
-  const size_t off = size_t(row) * ep.ldo + col0;
-  if (ep.gate_src != nullptr && row_ok) {
+  for (int j4 = 0; j4 < 8; ++j4)
+    *reinterpret_cast<float4*>(stage + lane * 128 + (((j4 ^ lane) & 7) << 4)) =
+        make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+  __syncwarp();
+  const int cu = lane & 7;          // 16-byte unit (4 columns) inside the 128-byte row segment
+  const int rsub = lane >> 3;       // row inside a group of 4
+  const int col = col0 + cu * 4;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ef_bias<EF>(ep)) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  // which optional operand travelled through aux (same priority as epi_aux_src)
+  const bool gate_in_aux = ef_gate<EF>(ep);
+  const bool res_in_aux = !gate_in_aux && ef_res<EF>(ep);
+  const bool acc_in_aux = !gate_in_aux && !res_in_aux && ef_acc<EF>(ep);
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(ep.gate_src + off) + j4);
-      v[4 * j4 + 0] = g.x > 0.f ? v[4 * j4 + 0] : 0.f;
-      v[4 * j4 + 1] = g.y > 0.f ? v[4 * j4 + 1] : 0.f;
-      v[4 * j4 + 2] = g.z > 0.f ? v[4 * j4 + 2] : 0.f;
-      v[4 * j4 + 3] = g.w > 0.f ? v[4 * j4 + 3] : 0.f;
-    }
-  }
-  if (ep.residual != nullptr && row_ok) {
-#pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-      const float4 r = __ldg(reinterpret_cast<const float4*>(ep.residual + off) + j4);
-      v[4 * j4 + 0] += r.x; v[4 * j4 + 1] += r.y; v[4 * j4 + 2] += r.z; v[4 * j4 + 3] += r.w;
-    }
-  }
-  if (row_ok) {
-    if (ep.out != nullptr) {
-      float4* o = reinterpret_cast<float4*>(ep.out + off);
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        float4 r = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-        if (ep.accumulate) {
-          const float4 p = o[j4];
-          r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w;
-          v[4 * j4] = r.x; v[4 * j4 + 1] = r.y; v[4 * j4 + 2] = r.z; v[4 * j4 + 3] = r.w;
-        }
-        o[j4] = r;
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rsub;
+    float4 x = *reinterpret_cast<const float4*>(stage + r * 128 + (((cu ^ r) & 7) << 4));
+    const int row = row0 + r;
+    if (row < M) {
+      x.x = fmaf(x.x, ep.alpha, bias.x); x.y = fmaf(x.y, ep.alpha, bias.y);
+      x.z = fmaf(x.z, ep.alpha, bias.z); x.w = fmaf(x.w, ep.alpha, bias.w);
+      if (ef_relu<EF>(ep)) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+      const size_t off = size_t(row) * ep.ldo + col;
+      if (ef_gate<EF>(ep)) {
+        const float4 g = aux.a[it];
+        x.x = g.x > 0.f ? x.x : 0.f; x.y = g.y > 0.f ? x.y : 0.f;
+        x.z = g.z > 0.f ? x.z : 0.f; x.w = g.w > 0.f ? x.w : 0.f;
       }
-    }
-    if (ep.out_tf32 != nullptr) {
-      float4* o = reinterpret_cast<float4*>(ep.out_tf32 + off);
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        o[j4] = make_float4(to_tf32(v[4 * j4]), to_tf32(v[4 * j4 + 1]), to_tf32(v[4 * j4 + 2]),
-                            to_tf32(v[4 * j4 + 3]));
+      if (ef_res<EF>(ep)) {
+        const float4 q = res_in_aux ? aux.a[it] : *reinterpret_cast<const float4*>(ep.residual + off);
+        x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+      }
+      float4* o = reinterpret_cast<float4*>(ep.out + off);
+      if (ef_acc<EF>(ep)) {
+        const float4 q = acc_in_aux ? aux.a[it] : *o;
+        x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+      }
+      *o = x;
+      if (ef_colsum<EF>(ep)) { cs.x += x.x; cs.y += x.y; cs.z += x.z; cs.w += x.w; }
     }
   }
-  if (ep.colsum != nullptr) {
-    if (!row_ok) {
+  if (ef_colsum<EF>(ep)) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    for (int o = 8; o <= 16; o <<= 1) {
+      cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+      cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
     }
-    const float s = warp_colsum32(v, lane);
-    atomicAdd(ep.colsum + col0 + lane, s);
+    if (lane < 8) {
+      atomicAdd(s_colsum + cu * 4 + 0, cs.x); atomicAdd(s_colsum + cu * 4 + 1, cs.y);
+      atomicAdd(s_colsum + cu * 4 + 2, cs.z); atomicAdd(s_colsum + cu * 4 + 3, cs.w);
+    }
   }
+  __syncwarp();   // the staging buffer is rewritten by the next chunk
 }
 
 // kBMajorN = false: B is [N, K] row-major (K-major operand, nn.Linear weight used as-is: x W^T).
 // kBMajorN = true : B is [K, N] row-major (MN-major operand: x W with W stored [K, N]); its stage is
 //                   BN/32 boxes of 32 k-rows x 32 columns in the SWIZZLE_128B_BASE32B layout.
-template <int BN, bool kBMajorN>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, bool kBMajorN, int EF>
+__global__ void __launch_bounds__(GemmTnCfg<BN>::THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                int K, EpiParams ep) {
   using Cfg = GemmTnCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(Cfg::STAGES) * Cfg::STAGE_BYTES);
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* epi_stage = smem + size_t(Cfg::STAGES) * Cfg::STAGE_BYTES;
+  float* s_colsum = reinterpret_cast<float*>(epi_stage + Cfg::EPI_WARPS * Cfg::EPI_STAGE_BYTES);   // [BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_colsum + BN);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
   uint64_t* tfull = bars + 2 * Cfg::STAGES;
@@ -141,22 +192,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // Tile schedule: gridDim.x is a multiple of tiles_n (launch_tn), CTA b owns the column block n = b % tiles_n for
+  // its whole life and walks the row blocks m = b / tiles_n, + gridDim.x / tiles_n, ...  The CTAs that run side by
+  // side share their A row block through L2, every CTA re-reads the same B slice (L2-resident weights), and the
+  // column sums of a CTA stay in registers until the kernel ends.
   const int tiles_m = (M + Cfg::BM - 1) / Cfg::BM;
   const int tiles_n = N / BN;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + Cfg::BK - 1) / Cfg::BK;
+  const int n0 = (int(blockIdx.x) % tiles_n) * BN;
+  const int m_first = int(blockIdx.x) / tiles_n;
+  const int m_step = int(gridDim.x) / tiles_n;
 
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], Cfg::EPI_WARPS); }
       fence_mbar_init();
     }
     __syncwarp();
     tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
+  for (int j = threadIdx.x; j < BN; j += blockDim.x) s_colsum[j] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -166,9 +224,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * Cfg::BM;
-        const int n0 = (tile % tiles_n) * BN;
+      for (int mt = m_first; mt < tiles_m; mt += m_step) {
+        const int m0 = mt * Cfg::BM;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
@@ -190,7 +247,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kFmtTF32, Cfg::BM, BN, false, kBMajorN);
       uint32_t it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      for (int mt = m_first; mt < tiles_m; mt += m_step, ++lt) {
         const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
         mbar_wait(&tempty[buf], bph ^ 1);
         tc_fence_after();
@@ -217,23 +274,36 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ------------------------------ epilogue ------------------------------
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the only ones this warp may read
+    const int ew = warp - 2;       // 0 .. EPI_WARPS-1
+    constexpr int kColSplit = Cfg::EPI_WARPS / 4;       // warps sharing a lane quarter interleave the 32-column chunks
+    const int csub = ew >> 2;
+    uint8_t* stage = epi_stage + ew * Cfg::EPI_STAGE_BYTES;
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+    for (int mt = m_first; mt < tiles_m; mt += m_step, ++lt) {
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
-      const int m0 = (tile / tiles_n) * Cfg::BM;
-      const int n0 = (tile % tiles_n) * BN;
+      const int m0 = mt * Cfg::BM;
+      // the gate / residual operands of the first chunk do not depend on the accumulator: fetch them while the MMAs run
+      EpiAux aux;
+      epilogue_fetch_aux<EF>(ep, aux, m0 + quarter * 32, M, n0 + csub * 32, lane);
       mbar_wait(&tfull[buf], bph);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = csub; c < BN / 32; c += kColSplit) {
         float v[32];
         tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN + c * 32, v);
-        epilogue_store_chunk(ep, v, row, M, n0 + c * 32, lane, nullptr);
+        const EpiAux cur = aux;
+        if (c + kColSplit < BN / 32)   // next chunk's operands: in flight during this chunk's stores
+          epilogue_fetch_aux<EF>(ep, aux, m0 + quarter * 32, M, n0 + (c + kColSplit) * 32, lane);
+        epilogue_store_chunk<EF>(ep, v, cur, stage, m0 + quarter * 32, M, n0 + c * 32, lane, s_colsum + c * 32);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+    if (ef_colsum<EF>(ep)) {
+      // all epilogue warps have added their partial column sums into s_colsum: one global atomic per column and CTA
+      asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");
+      for (int j = threadIdx.x - 64; j < BN; j += Cfg::EPI_WARPS * 32) atomicAdd(ep.colsum + n0 + j, s_colsum[j]);
     }
   }
   tc_fence_before();
@@ -269,7 +339,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                int N, float* __restrict__ C, int ldc, float alpha) {
   using Cfg = GemmDwCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(Cfg::STAGES) * Cfg::STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;

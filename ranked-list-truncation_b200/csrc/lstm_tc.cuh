@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(288, 1)
 lstm_rec_fwd_tc_kernel(const float* __restrict__ P, const float* __restrict__ whh_f, const float* __restrict__ whh_r,
                        float* __restrict__ y, float* __restrict__ saved, int B, int L) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align1024(smem_raw);
   uint8_t* sB = smem;
   uint8_t* sA = smem + LstmFwdSmem::B_BYTES;
   // h ping-pong: step s reads buffer s&1 (h_{s-1}) and the gate warps write h_s into buffer (s+1)&1, because the
@@ -253,7 +253,7 @@ lstm_rec_bwd_tc_kernel(const float* __restrict__ dy, const float* __restrict__ s
                        const float* __restrict__ whh_r, const float* __restrict__ scale_ptr, float* __restrict__ dA,
                        int B, int L) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align1024(smem_raw);
   uint8_t* sB = smem;
   uint8_t* sRing = smem + LstmBwdSmem::B_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + LstmBwdSmem::RING * LstmBwdSmem::KB_BYTES);

@@ -17,6 +17,11 @@ namespace rlt {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// 1024-byte alignment of the dynamic shared-memory base, written as pointer arithmetic on the __shared__ array so
+// that the compiler keeps the shared address space (an integer round trip turns every access into a generic LD/ST).
+__device__ __forceinline__ uint8_t* align1024(uint8_t* smem_raw) {
+  return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

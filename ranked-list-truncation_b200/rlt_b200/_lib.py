@@ -12,7 +12,7 @@ from pathlib import Path
 
 _PKG_DIR = Path(__file__).resolve().parent.parent          # ranked-list-truncation_b200/
 REPO_ROOT = _PKG_DIR.parent
-LIB_PATH = _PKG_DIR / "librlt_b200.so"
+LIB_PATH = Path(os.environ.get("RLT_B200_LIB", _PKG_DIR / "librlt_b200.so"))   # override: kernel A/B experiments only
 HEADER_PATH = REPO_ROOT / "include" / "rlt_b200.h"
 
 

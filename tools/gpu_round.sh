@@ -15,6 +15,6 @@ cat gpurun_out/${TAG}_bench_ref.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
   python bench.py --steps 2 --warmup 1 --groups 16 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
 # full capture of the dominant kernel
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s 6 -c 3 -o gpurun_out/${TAG}_prof -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:${KREGEX}" -s 6 -c 3 -o gpurun_out/${TAG}_prof -f \
   python bench.py --steps 1 --warmup 1 --groups 16 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out | tail -12
