@@ -287,4 +287,276 @@ __global__ void __launch_bounds__(128, 4) attn_lists_bwd_mma_kernel(const float*
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Persistent, software-pipelined versions: a CTA walks work items (group, position, head) with the head index
+// fastest (neighbouring heads share 128-byte lines of the qkv rows) and stages the next item's rows into the other
+// half of a double buffer with cp.async while the tensor cores work on the current one.  Memory latency is hidden by
+// the pipeline instead of by occupancy (the per-item kernels above are register-limited to 2 CTAs per SM and spend
+// 60% of their samples on the staging loads).  The softmax scale is applied to the accumulator (raw rows are copied).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// rows [0, S) of one head of a [T, ld] matrix -> dst[s][DH + 4] (asynchronous; rows >= S are never written)
+template <int DH>
+__device__ __forceinline__ void stage_head_rows(float* __restrict__ dst, const float* __restrict__ src, size_t tok0, int L,
+                                                int ld, int S) {
+  constexpr int P = DH + 4;
+  for (int i = threadIdx.x; i < S * (DH / 4); i += blockDim.x) {
+    const int s_ = i / (DH / 4), c = (i % (DH / 4)) * 4;
+    cp_async16(dst + s_ * P + c, src + (tok0 + size_t(s_) * L) * ld + c);
+  }
+}
+
+struct AttnItem {
+  size_t tok0;
+  int h;
+};
+__device__ __forceinline__ AttnItem attn_item(long long i, int S, int L, int n_head) {
+  AttnItem it;
+  it.h = int(i % n_head);
+  const long long r = i / n_head;
+  const int l = int(r % L);
+  const long long g = r / L;
+  it.tok0 = size_t(g) * S * L + l;
+  return it;
+}
+
+template <int DH, int NT>
+__global__ void __launch_bounds__(128) attn_lists_fwd_pipe_kernel(const float* __restrict__ qkv, float* __restrict__ o,
+                                                                  float* __restrict__ lse, int S, int L, int d, int n_head,
+                                                                  float scale, long long n_items) {
+  constexpr int P = DH + 4;
+  constexpr int ROWS = NT * 8;
+  constexpr int BUF = 3 * ROWS * P;
+  extern __shared__ float sm[];
+  const int ld = 3 * d;
+  for (int i = threadIdx.x; i < 2 * BUF; i += blockDim.x) sm[i] = 0.f;   // padded rows stay zero for the whole kernel
+  __syncthreads();
+  auto stage = [&](long long item, int b) {
+    const AttnItem it = attn_item(item, S, L, n_head);
+    float* base = sm + b * BUF;
+    stage_head_rows<DH>(base, qkv + it.h * DH, it.tok0, L, ld, S);
+    stage_head_rows<DH>(base + ROWS * P, qkv + d + it.h * DH, it.tok0, L, ld, S);
+    stage_head_rows<DH>(base + 2 * ROWS * P, qkv + 2 * d + it.h * DH, it.tok0, L, ld, S);
+    cp_async_commit();
+  };
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const float sc = scale * kLog2e;
+  long long item = blockIdx.x;
+  if (item < n_items) stage(item, 0);
+  int b = 0;
+  for (; item < n_items; item += gridDim.x, b ^= 1) {
+    const long long nxt = item + gridDim.x;
+    if (nxt < n_items) { stage(nxt, b ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const AttnItem it = attn_item(item, S, L, n_head);
+    const float* sQ = sm + b * BUF;
+    const float* sK = sQ + ROWS * P;
+    const float* sV = sK + ROWS * P;
+    for (int r0 = warp * 16; r0 < S; r0 += 64) {
+      float acc[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      tile_abT<DH, NT, true>(sQ, r0, sK, acc, lane);
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int c = j * 8 + 2 * t;
+        acc[j][0] = c < S ? acc[j][0] * sc : -INFINITY; acc[j][2] = c < S ? acc[j][2] * sc : -INFINITY;
+        acc[j][1] = c + 1 < S ? acc[j][1] * sc : -INFINITY; acc[j][3] = c + 1 < S ? acc[j][3] * sc : -INFINITY;
+        m0 = fmaxf(m0, fmaxf(acc[j][0], acc[j][1]));
+        m1 = fmaxf(m1, fmaxf(acc[j][2], acc[j][3]));
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        acc[j][0] = exp2f(acc[j][0] - m0); acc[j][1] = exp2f(acc[j][1] - m0);
+        acc[j][2] = exp2f(acc[j][2] - m1); acc[j][3] = exp2f(acc[j][3] - m1);
+        s0 += acc[j][0] + acc[j][1];
+        s1 += acc[j][2] + acc[j][3];
+      }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      float oacc[DH / 8][4];
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
+      tile_pB<DH, NT>(acc, sV, oacc, lane);
+      const float i0 = 1.f / s0, i1 = 1.f / s1;
+      const int ra = r0 + gq, rb = r0 + gq + 8;
+      if (ra < S) {
+        float* op = o + (it.tok0 + size_t(ra) * L) * d + it.h * DH;
+#pragma unroll
+        for (int n = 0; n < DH / 8; ++n)
+          *reinterpret_cast<float2*>(op + n * 8 + 2 * t) = make_float2(oacc[n][0] * i0, oacc[n][1] * i0);
+        if (t == 0 && lse != nullptr) lse[(it.tok0 + size_t(ra) * L) * n_head + it.h] = (m0 + log2f(s0)) * kLn2;
+      }
+      if (rb < S) {
+        float* op = o + (it.tok0 + size_t(rb) * L) * d + it.h * DH;
+#pragma unroll
+        for (int n = 0; n < DH / 8; ++n)
+          *reinterpret_cast<float2*>(op + n * 8 + 2 * t) = make_float2(oacc[n][2] * i1, oacc[n][3] * i1);
+        if (t == 0 && lse != nullptr) lse[(it.tok0 + size_t(rb) * L) * n_head + it.h] = (m1 + log2f(s1)) * kLn2;
+      }
+    }
+    __syncthreads();   // every warp is done with buffer b before the next iteration refills it
+  }
+}
+
+// Backward.  D_i = sum_j P_ij dP_ij (= dO_i . O_i) is taken from the phase-A fragments, so the attention output is not
+// read at all.
+template <int DH, int NT>
+__global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* __restrict__ qkv, const float* __restrict__ lse,
+                                                                  const float* __restrict__ d_o, float* __restrict__ dqkv,
+                                                                  int S, int L, int d, int n_head, float scale,
+                                                                  long long n_items) {
+  constexpr int P = DH + 4;
+  constexpr int ROWS = NT * 8;
+  constexpr int BUF = 4 * ROWS * P + ROWS;      // q, k, v, dO rows + lse
+  extern __shared__ float sm[];
+  float* sD = sm + 2 * BUF;                     // [ROWS], shared by both buffers (rewritten per item)
+  const int ld = 3 * d;
+  for (int i = threadIdx.x; i < 2 * BUF; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  for (int b = 0; b < 2; ++b)
+    for (int s_ = S + threadIdx.x; s_ < ROWS; s_ += blockDim.x) sm[b * BUF + 4 * ROWS * P + s_] = INFINITY;  // padded queries: P = 0
+  __syncthreads();
+  auto stage = [&](long long item, int b) {
+    const AttnItem it = attn_item(item, S, L, n_head);
+    float* base = sm + b * BUF;
+    stage_head_rows<DH>(base, qkv + it.h * DH, it.tok0, L, ld, S);
+    stage_head_rows<DH>(base + ROWS * P, qkv + d + it.h * DH, it.tok0, L, ld, S);
+    stage_head_rows<DH>(base + 2 * ROWS * P, qkv + 2 * d + it.h * DH, it.tok0, L, ld, S);
+    stage_head_rows<DH>(base + 3 * ROWS * P, d_o + it.h * DH, it.tok0, L, d, S);
+    for (int s_ = threadIdx.x; s_ < S; s_ += blockDim.x)
+      cp_async4(base + 4 * ROWS * P + s_, lse + (it.tok0 + size_t(s_) * L) * n_head + it.h);
+    cp_async_commit();
+  };
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const float sc = scale * kLog2e;
+  long long item = blockIdx.x;
+  if (item < n_items) stage(item, 0);
+  int b = 0;
+  for (; item < n_items; item += gridDim.x, b ^= 1) {
+    const long long nxt = item + gridDim.x;
+    if (nxt < n_items) { stage(nxt, b ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const AttnItem it = attn_item(item, S, L, n_head);
+    const float* sQ = sm + b * BUF;
+    const float* sK = sQ + ROWS * P;
+    const float* sV = sK + ROWS * P;
+    const float* sG = sV + ROWS * P;
+    const float* sL = sG + ROWS * P;            // natural-log lse
+    // ---------------- phase A: query tiles -> D, dQ
+    for (int r0 = warp * 16; r0 < S; r0 += 64) {
+      float p[NT][4], dp[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        p[j][0] = p[j][1] = p[j][2] = p[j][3] = 0.f;
+        dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+      }
+      tile_abT<DH, NT, true>(sQ, r0, sK, p, lane);
+      tile_abT<DH, NT, false>(sG, r0, sV, dp, lane);
+      const float la = sL[r0 + gq] * kLog2e, lb = sL[r0 + gq + 8] * kLog2e;
+      float da = 0.f, db = 0.f;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int c = j * 8 + 2 * t;
+        const bool ok0 = c < S, ok1 = c + 1 < S;
+        p[j][0] = ok0 ? exp2f(fmaf(p[j][0], sc, -la)) : 0.f;
+        p[j][1] = ok1 ? exp2f(fmaf(p[j][1], sc, -la)) : 0.f;
+        p[j][2] = ok0 ? exp2f(fmaf(p[j][2], sc, -lb)) : 0.f;
+        p[j][3] = ok1 ? exp2f(fmaf(p[j][3], sc, -lb)) : 0.f;
+        da = fmaf(p[j][0], dp[j][0], fmaf(p[j][1], dp[j][1], da));
+        db = fmaf(p[j][2], dp[j][2], fmaf(p[j][3], dp[j][3], db));
+      }
+      da += __shfl_xor_sync(0xffffffffu, da, 1); da += __shfl_xor_sync(0xffffffffu, da, 2);
+      db += __shfl_xor_sync(0xffffffffu, db, 1); db += __shfl_xor_sync(0xffffffffu, db, 2);
+      if (t == 0) { sD[r0 + gq] = da; sD[r0 + gq + 8] = db; }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        p[j][0] *= dp[j][0] - da; p[j][1] *= dp[j][1] - da;
+        p[j][2] *= dp[j][2] - db; p[j][3] *= dp[j][3] - db;
+      }
+      float acc[DH / 8][4];
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+      tile_pB<DH, NT>(p, sK, acc, lane);
+      const int ra = r0 + gq, rb = r0 + gq + 8;
+      if (ra < S) {
+        float* out = dqkv + (it.tok0 + size_t(ra) * L) * ld + it.h * DH;
+#pragma unroll
+        for (int n = 0; n < DH / 8; ++n)
+          *reinterpret_cast<float2*>(out + n * 8 + 2 * t) = make_float2(acc[n][0] * scale, acc[n][1] * scale);
+      }
+      if (rb < S) {
+        float* out = dqkv + (it.tok0 + size_t(rb) * L) * ld + it.h * DH;
+#pragma unroll
+        for (int n = 0; n < DH / 8; ++n)
+          *reinterpret_cast<float2*>(out + n * 8 + 2 * t) = make_float2(acc[n][2] * scale, acc[n][3] * scale);
+      }
+    }
+    __syncthreads();   // sD complete
+    // ---------------- phase B: key tiles (transposed products) -> dK, dV
+    for (int c0 = warp * 16; c0 < S; c0 += 64) {
+      float p[NT][4], dp[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        p[j][0] = p[j][1] = p[j][2] = p[j][3] = 0.f;
+        dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+      }
+      tile_abT<DH, NT, true>(sK, c0, sQ, p, lane);     // [key, query] raw scores
+      tile_abT<DH, NT, false>(sV, c0, sG, dp, lane);   // [key, query] dP^T
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int i = j * 8 + 2 * t;                    // query index of columns 0/2 ; i+1 for columns 1/3
+        const float l0 = sL[i] * kLog2e, l1 = sL[i + 1] * kLog2e, d0 = sD[i], d1 = sD[i + 1];
+        const float p0 = exp2f(fmaf(p[j][0], sc, -l0)), p1 = exp2f(fmaf(p[j][1], sc, -l1));
+        const float p2 = exp2f(fmaf(p[j][2], sc, -l0)), p3 = exp2f(fmaf(p[j][3], sc, -l1));
+        p[j][0] = p0; p[j][1] = p1; p[j][2] = p2; p[j][3] = p3;              // P^T  (0 for padded queries: lse = +inf)
+        dp[j][0] = p0 * (dp[j][0] - d0); dp[j][1] = p1 * (dp[j][1] - d1);    // dS^T
+        dp[j][2] = p2 * (dp[j][2] - d0); dp[j][3] = p3 * (dp[j][3] - d1);
+      }
+      float ak[DH / 8][4], av[DH / 8][4];
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) {
+        ak[n][0] = ak[n][1] = ak[n][2] = ak[n][3] = 0.f;
+        av[n][0] = av[n][1] = av[n][2] = av[n][3] = 0.f;
+      }
+      tile_pB<DH, NT>(dp, sQ, ak, lane);
+      tile_pB<DH, NT>(p, sG, av, lane);
+      const int ka = c0 + gq, kb = c0 + gq + 8;
+      if (ka < S) {
+        float* outk = dqkv + (it.tok0 + size_t(ka) * L) * ld + d + it.h * DH;
+#pragma unroll
+        for (int n = 0; n < DH / 8; ++n) {
+          *reinterpret_cast<float2*>(outk + n * 8 + 2 * t) = make_float2(ak[n][0] * scale, ak[n][1] * scale);
+          *reinterpret_cast<float2*>(outk + d + n * 8 + 2 * t) = make_float2(av[n][0], av[n][1]);
+        }
+      }
+      if (kb < S) {
+        float* outk = dqkv + (it.tok0 + size_t(kb) * L) * ld + d + it.h * DH;
+#pragma unroll
+        for (int n = 0; n < DH / 8; ++n) {
+          *reinterpret_cast<float2*>(outk + n * 8 + 2 * t) = make_float2(ak[n][2] * scale, ak[n][3] * scale);
+          *reinterpret_cast<float2*>(outk + d + n * 8 + 2 * t) = make_float2(av[n][2], av[n][3]);
+        }
+      }
+    }
+    __syncthreads();   // every warp is done with buffer b (and sD) before the next iteration refills them
+  }
+}
+
 }  // namespace rlt

@@ -371,13 +371,26 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_kernel(const float* __rest
   }
 }
 
+// persistent pipelined kernels: as many CTAs as are co-resident (occupancy API), each walking items with stride gridDim.x
 template <int DH, int NT>
 static int attention_fwd_mma(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head, float scale,
                              cudaStream_t stream) {
-  const size_t smem = size_t(3) * NT * 8 * (DH + 4) * sizeof(float);
-  RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_mma_kernel<DH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const size_t smem = size_t(2) * 3 * NT * 8 * (DH + 4) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_pipe_kernel<DH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr_set = true;
+  }
+  const long long n_items = (long long)G * L * n_head;
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_fwd_pipe_kernel<DH, NT>, 128, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
+  long long grid = (long long)num_sms() * per_sm;
+  if (grid > n_items) grid = n_items;
   time_begin(TAG_ATTN_FWD, stream);
-  attn_lists_fwd_mma_kernel<DH, NT><<<dim3(L, G, n_head), 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale);
+  attn_lists_fwd_pipe_kernel<DH, NT><<<int(grid), 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, n_items);
   time_end(TAG_ATTN_FWD, stream);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
@@ -385,10 +398,23 @@ static int attention_fwd_mma(const float* qkv, float* o, float* lse, int G, int 
 template <int DH, int NT>
 static int attention_bwd_mma(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int G,
                              int S, int L, int d, int n_head, float scale, cudaStream_t stream) {
-  const size_t smem = (size_t(4) * NT * 8 * (DH + 4) + 2 * NT * 8) * sizeof(float);
-  RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_mma_kernel<DH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  (void)o;   // D = rowsum(P * dP) is recomputed from the fragments; the attention output is not needed
+  const size_t smem = (size_t(2) * (4 * NT * 8 * (DH + 4) + NT * 8) + NT * 8) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_pipe_kernel<DH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr_set = true;
+  }
+  const long long n_items = (long long)G * L * n_head;
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_bwd_pipe_kernel<DH, NT>, 128, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
+  long long grid = (long long)num_sms() * per_sm;
+  if (grid > n_items) grid = n_items;
   time_begin(TAG_ATTN_BWD, stream);
-  attn_lists_bwd_mma_kernel<DH, NT><<<dim3(L, G, n_head), 128, smem, stream>>>(qkv, o, lse, d_o, dqkv, S, L, d, n_head, scale);
+  attn_lists_bwd_pipe_kernel<DH, NT><<<int(grid), 128, smem, stream>>>(qkv, lse, d_o, dqkv, S, L, d, n_head, scale, n_items);
   time_end(TAG_ATTN_BWD, stream);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
