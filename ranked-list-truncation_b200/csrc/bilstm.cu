@@ -16,7 +16,7 @@
 
 #include "common.h"
 #include "gemm_tc.cuh"
-#include "lstm_tc.cuh"
+#include "lstm_um.cuh"
 
 namespace rlt {
 
@@ -296,12 +296,12 @@ int rlt_bilstm_fwd(const rlt_bilstm_desc* d, const rlt_bilstm_weights* w, const 
     if (lstm_backend() == 0) {
       static bool attr = false;
       if (!attr) {
-        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            int(LstmFwdSmem::TOTAL)));
+        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            int(LstmUmFwdSmem::TOTAL)));
         attr = true;
       }
-      lstm_rec_fwd_tc_kernel<<<dim3((B + 127) / 128, 2), 288, LstmFwdSmem::TOTAL, stream>>>(P, w->w_hh[l][0], w->w_hh[l][1],
-                                                                                           out, sv, B, L);
+      lstm_um_fwd_kernel<<<dim3((B + U_TILE - 1) / U_TILE, 2), U_THREADS, LstmUmFwdSmem::TOTAL, stream>>>(
+          P, w->w_hh[l][0], w->w_hh[l][1], out, sv, B, L);
     } else {
       lstm_rec_fwd_kernel<<<dim3(B, 2), H, 0, stream>>>(P, WT + (l * 2) * size_t(H) * G4, WT + (l * 2 + 1) * size_t(H) * G4,
                                                         out, sv, L);
@@ -342,12 +342,12 @@ int rlt_bilstm_bwd(const rlt_bilstm_desc* d, const rlt_bilstm_weights* w, const 
       RLT_CHECK_LAUNCH();
       static bool attr = false;
       if (!attr) {
-        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            int(LstmBwdSmem::TOTAL)));
+        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            int(LstmUmBwdSmem::TOTAL)));
         attr = true;
       }
-      lstm_rec_bwd_tc_kernel<<<dim3((B + 127) / 128, 2), 288, LstmBwdSmem::TOTAL, stream>>>(dout, sv, w->w_hh[l][0],
-                                                                                           w->w_hh[l][1], scale, dA, B, L);
+      lstm_um_bwd_kernel<<<dim3((B + U_TILE - 1) / U_TILE, 2), U_THREADS, LstmUmBwdSmem::TOTAL, stream>>>(
+          dout, sv, w->w_hh[l][0], w->w_hh[l][1], scale, dA, B, L);
     } else {
       lstm_rec_bwd_kernel<<<dim3(B, 2), H, 0, stream>>>(dout, sv, w->w_hh[l][0], w->w_hh[l][1], dA, L);
     }

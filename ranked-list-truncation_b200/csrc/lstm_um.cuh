@@ -1,0 +1,480 @@
+// K1 — persistent BiLSTM recurrence on tcgen05, "unit-major" mapping.
+//
+// The per-step contraction is computed TRANSPOSED:  a^T[512 gate rows, lists] = W_hh[512, 128] . h^T[128, lists]
+//   * A operand = W_hh as stored by nn.LSTM ([4H, H], gate blocks i,f,g,o), fp16, K-major, resident in shared memory
+//     for the whole scan (128 KB); one M = 128 block per gate.
+//   * B operand = h_{t-1} of the CTA's lists ([lists, 128] fp16, K-major, 8 KB per 32 lists), rewritten every step
+//     by the gate warps.
+//   * D lives in TMEM with lane = hidden unit and column = list, so a gate thread owns ONE hidden unit of a few
+//     lists: consecutive lanes are consecutive hidden units and every global access of the recurrence (P, the saved
+//     gates, y, dy, dA) is a 128-byte contiguous warp access on the plain [token, feature] layouts.  (The earlier
+//     list-per-lane mapping touched 32 cache lines per warp instruction and ran at ~50 us per step.)
+//   * A CTA carries TWO independent halves of 32 lists each (MMA N = 32).  While the gate warps of one half evaluate
+//     the nonlinearities, the tensor core runs the other half's contraction; W_hh is shared by both.
+//   * fp16 operands keep the 10-bit mantissa of TF32 (|h| < 1, |W_hh| small), fp32 accumulation in TMEM; the cell
+//     state c stays in fp32 (shared memory, one private slot per thread and list).
+//   * Nonlinearities: 4 ex2 + ONE rcp for the four gates (the four denominators share a reciprocal), ex2 + rcp for
+//     tanh(c): 7 MUFU operations per cell instead of 10.
+// Backward (BPTT) uses the same mapping: dh_rec^T[128, lists] = W_hh^T[128, 512] . da^T[512, lists] with da in fp16
+// scaled by a power of two taken from max|dy| (unscaled when the accumulator is read).
+//
+// Roles per CTA (576 threads): warp 0 lane 0 issues the MMAs; warps 1..16 are gate warps (half = (warp-1)/8, TMEM
+// lane quarter = warp % 4, list sub-range = ((warp-1)/4) % 2); warp 17 pulls the rows of the coming steps into L2.
+#pragma once
+#include "sm100.cuh"
+
+namespace rlt {
+
+constexpr int UH = 128;          // hidden units
+constexpr int UG4 = 512;         // gate rows
+constexpr int USAVE = 6;         // saved planes per (token, direction): i, f, g, o, c, h_{t-1}
+constexpr int U_TILE = 64;       // lists per CTA
+constexpr int U_HALF = 32;       // lists per pipeline half (= MMA N)
+constexpr int U_CELLS = 16;      // lists per gate thread
+constexpr int U_CHUNK = 4;       // lists per register chunk
+constexpr int U_THREADS = 32 + 16 * 32 + 32;   // MMA warp, 16 gate warps, L2 prefetch warp
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float tanh_2mufu(float x) {
+  // 2 / (1 + e^(-2x)) - 1 ; saturates correctly when the exponential overflows / underflows
+  return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.f * 1.4426950408889634f * x)), -1.f);
+}
+// sigmoid(ai), sigmoid(af), tanh(ag), sigmoid(ao) with one shared reciprocal.  Pre-activations are clamped so that
+// the product of the four denominators stays finite: sigmoid(+-20) and tanh(+-10) are exact to 2e-9.
+__device__ __forceinline__ void lstm_gate_values(float ai, float af, float ag, float ao, float& gi, float& gf, float& gg,
+                                                 float& go) {
+  constexpr float kL = 1.4426950408889634f;
+  ai = fminf(fmaxf(ai, -20.f), 20.f);
+  af = fminf(fmaxf(af, -20.f), 20.f);
+  ao = fminf(fmaxf(ao, -20.f), 20.f);
+  ag = fminf(fmaxf(ag, -10.f), 10.f);
+  const float di = 1.f + ex2_approx(-kL * ai), df = 1.f + ex2_approx(-kL * af);
+  const float dg = 1.f + ex2_approx(-2.f * kL * ag), dO = 1.f + ex2_approx(-kL * ao);
+  const float pa = di * df, pb = dg * dO;
+  const float r = rcp_approx(pa * pb);
+  const float ra = r * pb, rb = r * pa;     // 1 / (di df), 1 / (dg do)
+  gi = ra * df;
+  gf = ra * di;
+  go = rb * dg;
+  gg = fmaf(2.f, rb * dO, -1.f);
+}
+
+__device__ __forceinline__ unsigned short f32_to_f16_bits(float x) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+
+// amax |x| over n floats -> *out (uint bits of a non-negative float; zero-initialised by the caller)
+__global__ void __launch_bounds__(256) amax_abs_kernel(const float* __restrict__ x, size_t n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+// scale[0] = 2^k with amax * 2^k in [32, 64]; scale[1] = 2^-k   (1, 1 when amax is 0 or not finite)
+__global__ void grad_scale_kernel(const unsigned int* __restrict__ amax_bits, float* __restrict__ scale) {
+  const float a = __uint_as_float(*amax_bits);
+  float s = 1.f;
+  if (a > 0.f && a < 3.0e38f) {
+    int e;
+    frexpf(a, &e);              // a = m * 2^e, m in [0.5, 1)
+    s = ldexpf(1.f, 6 - e);     // a * s in [32, 64)
+  }
+  scale[0] = s;
+  scale[1] = 1.f / s;
+}
+
+struct LstmUmFwdSmem {
+  static constexpr int W_BYTES = 2 * UG4 * 128;            // two k-blocks of [512 rows x 128 B]
+  static constexpr int H_BYTES = 2 * U_HALF * 128;         // per half: two k-blocks of [32 rows x 128 B]
+  static constexpr int C_BYTES = U_CELLS * 512 * 4;        // cell state, [cell][gate thread]
+  static constexpr size_t TOTAL = 1024 + W_BYTES + 2 * H_BYTES + C_BYTES + 256;
+};
+
+__global__ void __launch_bounds__(U_THREADS, 1)
+lstm_um_fwd_kernel(const float* __restrict__ P, const float* __restrict__ whh_f, const float* __restrict__ whh_r,
+                   float* __restrict__ y, float* __restrict__ saved, int B, int L) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sW = smem;
+  uint8_t* sH = sW + LstmUmFwdSmem::W_BYTES;
+  float* sC = reinterpret_cast<float*>(sH + 2 * LstmUmFwdSmem::H_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sC) + LstmUmFwdSmem::C_BYTES);
+  uint64_t* bar_h = bars;          // [2] h of the half complete in smem (count 256)
+  uint64_t* bar_acc = bars + 2;    // [2] accumulator of the half ready (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, dir = blockIdx.y;
+  const float* whh = dir ? whh_r : whh_f;
+
+  // ---- one-time: W_hh (fp32 [512,128]) -> fp16 K-major SWIZZLE_128B operand; zero h_0 and c_0
+  for (int i = threadIdx.x; i < UG4 * 16; i += blockDim.x) {
+    const int n = i >> 4, c = i & 15;                 // c: 8-element chunk along k (0..15)
+    const float* src = whh + size_t(n) * UH + c * 8;
+    const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+    uint4 pk;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.x) : "f"(v0.x), "f"(v0.y));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.y) : "f"(v0.z), "f"(v0.w));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.z) : "f"(v1.x), "f"(v1.y));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.w) : "f"(v1.z), "f"(v1.w));
+    *reinterpret_cast<uint4*>(sW + (c >> 3) * (UG4 * 128) + sw128_offset(n, c & 7)) = pk;
+  }
+  for (int i = threadIdx.x; i < (2 * LstmUmFwdSmem::H_BYTES + LstmUmFwdSmem::C_BYTES) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sH)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int h = 0; h < 2; ++h) { mbar_init(&bar_h[h], 256); mbar_init(&bar_acc[h], 1); }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<256>(tmem_slot);
+  }
+  fence_proxy_async_smem();   // generic-proxy writes of sW / sH -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------ MMA issuer ------------------------------
+      constexpr uint32_t idesc = make_idesc(kFmtF16, 128, U_HALF, false, false);
+      const uint32_t w_addr = smem_u32(sW), h_addr = smem_u32(sH);
+      for (int step = 0; step < L; ++step) {
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          if (step > 0) {
+            mbar_wait(&bar_h[hf], (step - 1) & 1);
+            tc_fence_after();
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint64_t da = make_smem_desc_sw128(w_addr + kb * (UG4 * 128) + q * (128 * 128), 16, 1024);
+              const uint64_t db = make_smem_desc_sw128(h_addr + hf * LstmUmFwdSmem::H_BYTES + kb * (U_HALF * 128), 16, 1024);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)   // K = 16 fp16 = 32 B per MMA
+                umma_f16(tmem_base + hf * 128 + q * U_HALF, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&bar_acc[hf]);
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // pull the P rows (2 KB per list and step, contiguous) of the step that is kAhead ahead into L2, paced by the
+    // accumulator barrier of the second half (own warp: never more than one phase behind)
+    constexpr int kAhead = 2;
+    for (int step = 0; step < L; ++step) {
+      if (step >= kAhead) mbar_wait(&bar_acc[1], (step - kAhead) & 1);
+      const int t = dir ? (L - 1 - step) : step;
+      for (int r = lane; r < U_TILE; r += 32) {
+        const int bb = tile * U_TILE + r;
+        if (bb < B) prefetch_l2_bulk(P + (size_t(bb) * L + t) * (2 * UG4) + dir * UG4, UG4 * 4);
+      }
+    }
+  } else {
+    // ------------------------------ gate warps ------------------------------
+    const int gw = warp - 1;
+    const int hf = gw >> 3;                    // pipeline half
+    const int sub = (gw >> 2) & 1;             // which 16 lists of the half
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int u = quarter * 32 + lane;         // hidden unit
+    const int gt = threadIdx.x - 32;           // gate thread index 0..511 (cell-state slot)
+    const int row0 = sub * U_CELLS;            // first list row inside the half
+    const int list0 = tile * U_TILE + hf * U_HALF + row0;
+    const uint32_t t_lane = tmem_base + (uint32_t(quarter * 32) << 16) + hf * 128 + row0;
+    // this thread's 2-byte slot inside a list's h row: k-block u/64, 16-byte unit (u%64)/8
+    uint8_t* hbase = sH + hf * LstmUmFwdSmem::H_BYTES + (u >> 6) * (U_HALF * 128) + (u & 7) * 2;
+    const int hunit = (u & 63) >> 3;
+    const size_t p_list = size_t(L) * (2 * UG4);          // P stride between lists
+    const size_t y_list = size_t(L) * (2 * UH);
+    const size_t s_list = size_t(L) * (2 * USAVE * UH);
+
+    for (int step = 0; step < L; ++step) {
+      const int t = dir ? (L - 1 - step) : step;
+      const int tn = dir ? (t - 1) : (t + 1);            // time index of the next step (for its h_{t-1} plane)
+      const float* p0 = P + (size_t(list0) * L + t) * (2 * UG4) + dir * UG4 + u;
+      float* y0 = y + (size_t(list0) * L + t) * (2 * UH) + dir * UH + u;
+      float* s0 = saved ? saved + ((size_t(list0) * L + t) * 2 + dir) * (USAVE * UH) + u : nullptr;
+      float pc[4][U_CHUNK];
+#pragma unroll
+      for (int li = 0; li < U_CHUNK; ++li) {
+        const bool live = list0 + li < B;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pc[q][li] = live ? __ldg(p0 + li * p_list + q * UH) : 0.f;
+      }
+      mbar_wait(&bar_acc[hf], step & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < U_CELLS / U_CHUNK; ++ch) {
+        float a[4][U_CHUNK];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tmem_ld4(t_lane + q * U_HALF + ch * U_CHUNK, a[q]);
+        float pn[4][U_CHUNK];
+        if (ch + 1 < U_CELLS / U_CHUNK) {
+#pragma unroll
+          for (int li = 0; li < U_CHUNK; ++li) {
+            const bool live = list0 + (ch + 1) * U_CHUNK + li < B;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pn[q][li] = live ? __ldg(p0 + ((ch + 1) * U_CHUNK + li) * p_list + q * UH) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int li = 0; li < U_CHUNK; ++li) {
+          const int cell = ch * U_CHUNK + li;
+          const bool live = list0 + cell < B;
+          float gi, gf, gg, go;
+          lstm_gate_values(a[0][li] + pc[0][li], a[1][li] + pc[1][li], a[2][li] + pc[2][li], a[3][li] + pc[3][li], gi, gf,
+                           gg, go);
+          const float cn = fmaf(gf, sC[cell * 512 + gt], gi * gg);
+          sC[cell * 512 + gt] = cn;
+          const float hv = go * tanh_2mufu(cn);
+          if (live) {
+            if (s0 != nullptr) {
+              float* sv = s0 + cell * s_list;
+              sv[0 * UH] = gi; sv[1 * UH] = gf; sv[2 * UH] = gg; sv[3 * UH] = go; sv[4 * UH] = cn;
+              if (step == 0) sv[5 * UH] = 0.f;
+              // h_t is the "previous h" of the next step's record
+              if (step + 1 < L) saved[((size_t(list0 + cell) * L + tn) * 2 + dir) * (USAVE * UH) + 5 * UH + u] = hv;
+            }
+            y0[cell * y_list] = hv;
+          }
+          const int r = row0 + cell;
+          *reinterpret_cast<unsigned short*>(hbase + (r >> 3) * 1024 + (r & 7) * 128 + (((hunit ^ r) & 7) << 4)) =
+              f32_to_f16_bits(hv);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int li = 0; li < U_CHUNK; ++li) pc[q][li] = pn[q][li];
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&bar_h[hf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Backward recurrence:  dh_rec^T[128 units k, lists] = W_hh^T[128, 512] . da^T[512, lists]
+//   A operand: W_hh^T, fp16 K-major, 8 k-blocks of [128 rows (k) x 64 gate rows n] (128 KB, resident)
+//   B operand: da of the half's 32 lists, [32 rows x 512 n] fp16 K-major (8 k-blocks x 4 KB), scaled by 2^s
+//   D: TMEM lane = hidden unit k, column = list (32 columns per half)
+// ------------------------------------------------------------------------------------------------------------
+struct LstmUmBwdSmem {
+  static constexpr int KB_BYTES = 128 * 128;               // one k-block of W_hh^T
+  static constexpr int W_BYTES = 8 * KB_BYTES;
+  static constexpr int DA_KB = U_HALF * 128;               // one k-block of da (32 rows x 128 B)
+  static constexpr int DA_BYTES = 8 * DA_KB;               // per half
+  static constexpr int C_BYTES = U_CELLS * 512 * 4;        // dc_rec, [cell][gate thread]
+  static constexpr size_t TOTAL = 1024 + W_BYTES + 2 * DA_BYTES + C_BYTES + 256;
+};
+
+__global__ void __launch_bounds__(U_THREADS, 1)
+lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved, const float* __restrict__ whh_f,
+                   const float* __restrict__ whh_r, const float* __restrict__ scale_ptr, float* __restrict__ dA, int B,
+                   int L) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sW = smem;
+  uint8_t* sDA = sW + LstmUmBwdSmem::W_BYTES;
+  float* sDC = reinterpret_cast<float*>(sDA + 2 * LstmUmBwdSmem::DA_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sDC) + LstmUmBwdSmem::C_BYTES);
+  uint64_t* bar_da = bars;         // [2] da of the half complete in smem (count 256)
+  uint64_t* bar_d = bars + 2;      // [2] dh_rec of the half ready (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, dir = blockIdx.y;
+  const float* whh = dir ? whh_r : whh_f;
+
+  // ---- one-time: W_hh^T as fp16 K-major operand: element (row k, col n) = W_hh[n][k]
+  for (int i = threadIdx.x; i < 8 * 8 * 128; i += blockDim.x) {
+    const int k = i & 127, c = (i >> 7) & 7, kb = i >> 10;    // k fastest: coalesced reads of W_hh rows
+    const float* src = whh + size_t(kb * 64 + c * 8) * UH + k;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = src[size_t(e) * UH];
+    uint4 pk;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.x) : "f"(v[0]), "f"(v[1]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.y) : "f"(v[2]), "f"(v[3]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.z) : "f"(v[4]), "f"(v[5]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.w) : "f"(v[6]), "f"(v[7]));
+    *reinterpret_cast<uint4*>(sW + kb * LstmUmBwdSmem::KB_BYTES + sw128_offset(k, c)) = pk;
+  }
+  for (int i = threadIdx.x; i < (2 * LstmUmBwdSmem::DA_BYTES + LstmUmBwdSmem::C_BYTES) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sDA)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int h = 0; h < 2; ++h) { mbar_init(&bar_da[h], 256); mbar_init(&bar_d[h], 1); }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<64>(tmem_slot);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------ MMA issuer ------------------------------
+      constexpr uint32_t idesc = make_idesc(kFmtF16, 128, U_HALF, false, false);
+      const uint32_t w_addr = smem_u32(sW), da_addr = smem_u32(sDA);
+      for (int it = 0; it + 1 < L; ++it) {             // the last processed step has no consumer for dh_rec
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&bar_da[hf], it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {
+            const uint64_t da = make_smem_desc_sw128(w_addr + kb * LstmUmBwdSmem::KB_BYTES, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(da_addr + hf * LstmUmBwdSmem::DA_BYTES + kb * LstmUmBwdSmem::DA_KB, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_base + hf * U_HALF, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bar_d[hf]);
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // L2 prefetch of the saved record (i, f, g, o, c: 2.5 KB) and dy row (512 B) of the step kAhead ahead
+    constexpr int kAhead = 2;
+    for (int it = 0; it < L; ++it) {
+      if (it >= kAhead) mbar_wait(&bar_d[1], (it - kAhead) & 1);
+      const int step = L - 1 - it;
+      const int t = dir ? (L - 1 - step) : step;
+      for (int r = lane; r < U_TILE; r += 32) {
+        const int bb = tile * U_TILE + r;
+        if (bb < B) {
+          const size_t tok = size_t(bb) * L + t;
+          prefetch_l2_bulk(saved + (tok * 2 + dir) * (USAVE * UH), 5 * UH * 4);
+          prefetch_l2_bulk(dy + tok * (2 * UH) + dir * UH, UH * 4);
+        }
+      }
+    }
+  } else {
+    // ------------------------------ gate warps ------------------------------
+    const int gw = warp - 1;
+    const int hf = gw >> 3;
+    const int sub = (gw >> 2) & 1;
+    const int quarter = warp & 3;
+    const int u = quarter * 32 + lane;
+    const int gt = threadIdx.x - 32;
+    const int row0 = sub * U_CELLS;
+    const int list0 = tile * U_TILE + hf * U_HALF + row0;
+    const uint32_t t_lane = tmem_base + (uint32_t(quarter * 32) << 16) + hf * U_HALF + row0;
+    const float scale = scale_ptr[0], inv_scale = scale_ptr[1];
+    // da[list row r][n = q*128 + u]: k-block q*2 + u/64, 16-byte unit (u%64)/8, 2 bytes at (u%8)*2
+    uint8_t* dabase = sDA + hf * LstmUmBwdSmem::DA_BYTES + (u >> 6) * LstmUmBwdSmem::DA_KB + (u & 7) * 2;
+    const int dunit = (u & 63) >> 3;
+    const size_t s_list = size_t(L) * (2 * USAVE * UH);
+    const size_t y_list = size_t(L) * (2 * UH);
+    const size_t a_list = size_t(L) * (2 * UG4);
+
+    for (int it = 0; it < L; ++it) {
+      const int step = L - 1 - it;                      // forward step index being differentiated
+      const int t = dir ? (L - 1 - step) : step;
+      const int tp = dir ? (t + 1) : (t - 1);           // time index of the previous forward step
+      const float* s0 = saved + ((size_t(list0) * L + t) * 2 + dir) * (USAVE * UH) + u;
+      const float* c0 = saved + ((size_t(list0) * L + tp) * 2 + dir) * (USAVE * UH) + 4 * UH + u;   // c_{t-1} (step > 0)
+      const float* dy0 = dy + (size_t(list0) * L + t) * (2 * UH) + dir * UH + u;
+      float* da0 = dA + (size_t(list0) * L + t) * (2 * UG4) + dir * UG4 + u;
+      // operands of the first chunk: in flight while the tensor core finishes dh_rec
+      float vc[7][U_CHUNK];   // i, f, g, o, c, c_prev, dy
+#pragma unroll
+      for (int li = 0; li < U_CHUNK; ++li) {
+        const bool live = list0 + li < B;
+#pragma unroll
+        for (int pl = 0; pl < 5; ++pl) vc[pl][li] = live ? __ldg(s0 + li * s_list + pl * UH) : 0.f;
+        vc[5][li] = (live && step > 0) ? __ldg(c0 + li * s_list) : 0.f;
+        vc[6][li] = live ? __ldg(dy0 + li * y_list) : 0.f;
+      }
+      if (it > 0) {
+        mbar_wait(&bar_d[hf], (it - 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll 1
+      for (int ch = 0; ch < U_CELLS / U_CHUNK; ++ch) {
+        float dhr[U_CHUNK];
+        if (it > 0) {
+          tmem_ld4(t_lane + ch * U_CHUNK, dhr);
+        } else {
+#pragma unroll
+          for (int li = 0; li < U_CHUNK; ++li) dhr[li] = 0.f;
+        }
+        float vn[7][U_CHUNK];
+        if (ch + 1 < U_CELLS / U_CHUNK) {
+#pragma unroll
+          for (int li = 0; li < U_CHUNK; ++li) {
+            const int cell = (ch + 1) * U_CHUNK + li;
+            const bool live = list0 + cell < B;
+#pragma unroll
+            for (int pl = 0; pl < 5; ++pl) vn[pl][li] = live ? __ldg(s0 + cell * s_list + pl * UH) : 0.f;
+            vn[5][li] = (live && step > 0) ? __ldg(c0 + cell * s_list) : 0.f;
+            vn[6][li] = live ? __ldg(dy0 + cell * y_list) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int li = 0; li < U_CHUNK; ++li) {
+          const int cell = ch * U_CHUNK + li;
+          const bool live = list0 + cell < B;
+          const float gi = vc[0][li], gf = vc[1][li], gg = vc[2][li], go = vc[3][li], cc = vc[4][li], cp = vc[5][li];
+          const float dh = fmaf(dhr[li], inv_scale, vc[6][li]);
+          const float tc = tanh_2mufu(cc);
+          const float d_o = dh * tc;
+          const float dc = fmaf(dh * go, 1.f - tc * tc, sDC[cell * 512 + gt]);
+          sDC[cell * 512 + gt] = dc * gf;
+          const float dai = dc * gg * gi * (1.f - gi);
+          const float daf = dc * cp * gf * (1.f - gf);
+          const float dag = dc * gi * (1.f - gg * gg);
+          const float dao = d_o * go * (1.f - go);
+          if (live) {
+            float* o = da0 + cell * a_list;
+            o[0 * UH] = dai; o[1 * UH] = daf; o[2 * UH] = dag; o[3 * UH] = dao;
+          }
+          const int r = row0 + cell;
+          uint8_t* dst = dabase + (r >> 3) * 1024 + (r & 7) * 128 + (((dunit ^ r) & 7) << 4);
+          *reinterpret_cast<unsigned short*>(dst + 0 * 2 * LstmUmBwdSmem::DA_KB) = f32_to_f16_bits(dai * scale);
+          *reinterpret_cast<unsigned short*>(dst + 1 * 2 * LstmUmBwdSmem::DA_KB) = f32_to_f16_bits(daf * scale);
+          *reinterpret_cast<unsigned short*>(dst + 2 * 2 * LstmUmBwdSmem::DA_KB) = f32_to_f16_bits(dag * scale);
+          *reinterpret_cast<unsigned short*>(dst + 3 * 2 * LstmUmBwdSmem::DA_KB) = f32_to_f16_bits(dao * scale);
+        }
+#pragma unroll
+        for (int pl = 0; pl < 7; ++pl)
+#pragma unroll
+          for (int li = 0; li < U_CHUNK; ++li) vc[pl][li] = vn[pl][li];
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&bar_da[hf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem_base);
+}
+
+}  // namespace rlt

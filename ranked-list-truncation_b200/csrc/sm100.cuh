@@ -226,6 +226,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// TMEM -> registers, 4 consecutive fp32 columns of this warp's 32 lanes.
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // 128-byte swizzle used by TMA SWIZZLE_128B and the UMMA SWIZZLE_128B layouts: inside each 1024 B
 // atom (8 rows x 128 B) the 16-byte chunk index is XORed with the row index.
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16) {
