@@ -70,6 +70,15 @@ int rlt_linear(const float* A, const float* B, const float* bias, float* C, int 
 /* C[M,N] += alpha * A[T,M]^T B[T,N]  (weight-gradient contraction over tokens). */
 int rlt_grad_weight(const float* A, const float* B, float* C, int T, int M, int N, float alpha,
                     rlt_stream_t stream);
+/* Half-precision building blocks of the FFN hidden path (fp16 keeps TF32's 11 significant bits; void* = __half*):
+ * dst = half(src * scale[0]) (scale may be NULL); C = act(alpha A B^T + bias) with fp16 A [M,K], B [N,K];
+ * C += alpha A^T B with fp16 A [T,M], B [T,N]; C(fp16) = act(A B^T + bias) with fp32 operands. */
+int rlt_convert_f16(const float* src, void* dst, size_t n, const float* scale, rlt_stream_t stream);
+int rlt_linear_f16(const void* A, const void* B, const float* bias, float* C, int M, int N, int K, float alpha, int relu,
+                   rlt_stream_t stream);
+int rlt_grad_weight_f16(const void* A, const void* B, float* C, int T, int M, int N, float alpha, rlt_stream_t stream);
+int rlt_linear_out_f16(const float* A, const float* B, const float* bias, void* C, int M, int N, int K, int relu,
+                       rlt_stream_t stream);
 /* out[c] += sum_t src[t, c]  (bias gradients). n_cols must be a multiple of 4. */
 int rlt_colsum(const float* src, float* out, int n_rows, int n_cols, rlt_stream_t stream);
 /* Probe: TMA-load a [rows<=128, 32] fp32 tile of src through a TFLOAT32 tensor map and copy the

@@ -1,6 +1,7 @@
 // Library-internal declarations shared by the translation units of librlt_b200.so.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -59,6 +60,17 @@ int gemm_nn(const float* A, int lda, const float* B, int ldb, int M, int N, int 
 // C[M,N] += alpha * sum_t A[t,m] * B[t,n]   (A: [T,lda], B: [T,ldb]; C pre-initialised by the caller)
 int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
             cudaStream_t stream, int tag = 0);
+
+// fp16-operand variants (tensor-core backend only): C = A[M,K] B[N,K]^T and C += alpha * alpha_ptr[0] * A[T,M]^T B[T,N]
+int gemm_tn_h(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const EpiParams& ep,
+              cudaStream_t stream);
+int gemm_dw_h(const __half* A, int lda, const __half* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
+              const float* alpha_ptr, cudaStream_t stream, int tag = 0);
+// dst = half(src * scale[0]) (scale may be null); dst[c, r] = half(src[r, c])
+int convert_f16(const float* src, __half* dst, size_t n, const float* scale, cudaStream_t stream);
+int transpose_f16(const float* src, __half* dst, int rows, int cols, cudaStream_t stream);
+// scale = {2^k, 2^-k} with max|x| * 2^k in [2^(target-1), 2^target); amax_scratch: one device word
+int grad_scale(const float* x, size_t n, unsigned int* amax_scratch, float* scale, int target, cudaStream_t stream);
 
 // 0 = tcgen05 tensor-core kernels (default), 1 = plain SIMT kernels (validation backend only)
 int gemm_backend();

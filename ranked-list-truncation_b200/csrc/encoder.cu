@@ -28,7 +28,8 @@ namespace rlt {
 template <int D>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ u, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, float* __restrict__ y,
-                                                     float* __restrict__ stats, int T, float eps) {
+                                                     float* __restrict__ stats, int T, float eps,
+                                                     __half* __restrict__ y16 /* optional fp16 copy of y */) {
   constexpr int V4 = D / 128;  // float4 per lane
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -58,8 +59,14 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ u
   for (int i = 0; i < V4; ++i) {
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
     const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
-    dst[lane + 32 * i] = make_float4(v[i].x * rstd * g.x + b.x, v[i].y * rstd * g.y + b.y,
-                                     v[i].z * rstd * g.z + b.z, v[i].w * rstd * g.w + b.w);
+    const float4 r = make_float4(v[i].x * rstd * g.x + b.x, v[i].y * rstd * g.y + b.y,
+                                 v[i].z * rstd * g.z + b.z, v[i].w * rstd * g.w + b.w);
+    dst[lane + 32 * i] = r;
+    if (y16 != nullptr) {
+      const __half2 lo = __floats2half2_rn(r.x, r.y), hi = __floats2half2_rn(r.z, r.w);
+      reinterpret_cast<uint2*>(y16 + size_t(row) * D)[lane + 32 * i] =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
   }
   if (stats != nullptr && lane == 0) {
     stats[2 * size_t(row)] = mu;
@@ -491,11 +498,11 @@ static int attention_bwd(const float* qkv, const float* o, const float* lse, con
 }
 
 static int layer_norm_fwd(const float* u, const float* gamma, const float* beta, float* y, float* stats, int T, int d,
-                          float eps, cudaStream_t stream) {
+                          float eps, cudaStream_t stream, __half* y16 = nullptr) {
   const int rows_per_cta = 8;
   const int grid = (T + rows_per_cta - 1) / rows_per_cta;
-  if (d == 128) ln_fwd_kernel<128><<<grid, 256, 0, stream>>>(u, gamma, beta, y, stats, T, eps);
-  else if (d == 256) ln_fwd_kernel<256><<<grid, 256, 0, stream>>>(u, gamma, beta, y, stats, T, eps);
+  if (d == 128) ln_fwd_kernel<128><<<grid, 256, 0, stream>>>(u, gamma, beta, y, stats, T, eps, y16);
+  else if (d == 256) ln_fwd_kernel<256><<<grid, 256, 0, stream>>>(u, gamma, beta, y, stats, T, eps, y16);
   else return set_error(RLT_UNSUPPORTED_SHAPE, "layer_norm: d_model %d not in {128, 256}", d);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
@@ -516,10 +523,13 @@ static int layer_norm_bwd(const float* dy, const float* u, const float* stats, c
 
 // ------------------------------------------------------------------------------------------
 // saved-for-backward layout of one layer (floats per token): qkv 3d | o d | u1 d | y d | h dff | u2 d |
-// stats1 2 | stats2 2 | lse n_head
+// stats1 2 | stats2 2 | lse n_head | y16 d/2, plus fp16 copies of the FFN weights.
+// On the tensor-core backend the FFN hidden h (and dH in the backward workspace) are stored in fp16 — the 11
+// significant bits the TF32 contraction would keep anyway — inside the fp32-sized regions (first half used):
+// this halves the HBM traffic of the six hidden-sized GEMMs, which bound the layer.
 // ------------------------------------------------------------------------------------------
 struct SavedLayout {
-  size_t qkv, o, u1, y, h, u2, st1, st2, lse, total;
+  size_t qkv, o, u1, y, h, u2, st1, st2, lse, y16, wh, total;
 };
 static SavedLayout saved_layout(const rlt_encoder_desc& e) {
   const size_t T = size_t(e.n_groups) * e.group_size * e.seq_len;
@@ -536,9 +546,14 @@ static SavedLayout saved_layout(const rlt_encoder_desc& e) {
   s.st1 = take(T * 2);
   s.st2 = take(T * 2);
   s.lse = take(T * e.n_head);
+  s.y16 = take(T * d / 2);      // fp16 copy of y (operand of the dW1 contraction)
+  s.wh = take(d * f);           // fp16 copies of the FFN weights: W2 [d, f] and W1^T [d, f]
   s.total = off;
   return s;
 }
+
+// fp16 hidden activations: tensor-core backend, shapes the fp16 GEMMs take (d_ff multiple of 128)
+static bool hidden_f16(const rlt_encoder_desc& e) { return gemm_backend() == 0 && e.d_ff % 128 == 0 && e.d_model % 128 == 0; }
 
 static int check_desc(const rlt_encoder_desc* e) {
   RLT_REQUIRE(e != nullptr, RLT_INVALID_ARG, "encoder: null descriptor");
@@ -602,13 +617,26 @@ int rlt_encoder_layer_fwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   // u1 = x + o Wo^T + b_o ; y = LN1(u1)
   ep = EpiParams{}; ep.alpha = 1.f; ep.out = sv + sl.u1; ep.ldo = d; ep.bias = w->out_proj_b; ep.residual = x; ep.tag = TAG_OUT_PROJ;
   RLT_TRY(gemm_tn(sv + sl.o, d, w->out_proj_w, d, T, d, d, ep, stream));
-  RLT_TRY(layer_norm_fwd(sv + sl.u1, w->norm1_w, w->norm1_b, sv + sl.y, sv + sl.st1, T, d, e->ln_eps, stream));
+  const bool h16 = hidden_f16(*e);
+  __half* y16 = reinterpret_cast<__half*>(sv + sl.y16);
+  __half* hh = reinterpret_cast<__half*>(sv + sl.h);
+  __half* w2h = reinterpret_cast<__half*>(sv + sl.wh);
+  __half* w1th = w2h + size_t(d) * f;
+  RLT_TRY(layer_norm_fwd(sv + sl.u1, w->norm1_w, w->norm1_b, sv + sl.y, sv + sl.st1, T, d, e->ln_eps, stream,
+                         h16 ? y16 : nullptr));
   // h = relu(y W1^T + b1)
-  ep = EpiParams{}; ep.alpha = 1.f; ep.out = sv + sl.h; ep.ldo = f; ep.bias = w->lin1_b; ep.relu = 1; ep.tag = TAG_FFN1;
+  ep = EpiParams{}; ep.alpha = 1.f; ep.ldo = f; ep.bias = w->lin1_b; ep.relu = 1; ep.tag = TAG_FFN1;
+  if (h16) ep.out_h = hh; else ep.out = sv + sl.h;
   RLT_TRY(gemm_tn(sv + sl.y, d, w->lin1_w, d, T, f, d, ep, stream));
   // u2 = y + h W2^T + b2 ; out = LN2(u2)
   ep = EpiParams{}; ep.alpha = 1.f; ep.out = sv + sl.u2; ep.ldo = d; ep.bias = w->lin2_b; ep.residual = sv + sl.y; ep.tag = TAG_FFN2;
-  RLT_TRY(gemm_tn(sv + sl.h, f, w->lin2_w, f, T, d, f, ep, stream));
+  if (h16) {
+    RLT_TRY(convert_f16(w->lin2_w, w2h, size_t(d) * f, nullptr, stream));      // [d, f] as stored
+    RLT_TRY(transpose_f16(w->lin1_w, w1th, f, d, stream));                     // [f, d] -> [d, f] (backward dY)
+    RLT_TRY(gemm_tn_h(hh, f, w2h, f, T, d, f, ep, stream));
+  } else {
+    RLT_TRY(gemm_tn(sv + sl.h, f, w->lin2_w, f, T, d, f, ep, stream));
+  }
   RLT_TRY(layer_norm_fwd(sv + sl.u2, w->norm2_w, w->norm2_b, out, sv + sl.st2, T, d, e->ln_eps, stream));
   return RLT_OK;
 }
@@ -632,17 +660,44 @@ int rlt_encoder_layer_bwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   // LN2 backward: dU2, dgamma2, dbeta2, db2 (= column sums of dU2)
   RLT_TRY(layer_norm_bwd(d_out, sv + sl.u2, sv + sl.st2, w->norm2_w, d_u, gw->norm2_w, gw->norm2_b, gw->lin2_b, T, d,
                          stream));
-  // dW2 += dU2^T h
-  RLT_TRY(gemm_dw(d_u, d, sv + sl.h, f, T, d, f, gw->lin2_w, f, 1.f, stream, TAG_DW_FFN2));
-  // dHpre = (dU2 W2) * (h > 0) ; db1 += colsum(dHpre)
+  if (hidden_f16(*e)) {
+    const __half* hh = reinterpret_cast<const __half*>(sv + sl.h);
+    const __half* y16 = reinterpret_cast<const __half*>(sv + sl.y16);
+    const __half* w1th = reinterpret_cast<const __half*>(sv + sl.wh) + size_t(d) * f;
+    __half* dh16 = reinterpret_cast<__half*>(wide);                           // [T, f] fp16, scaled by s
+    __half* du16 = reinterpret_cast<__half*>(wide + size_t(T) * f / 2);       // [T, d] fp16, scaled by s
+    float* scale = ws + size_t(T) * (2 * size_t(d) + (size_t(f) > 3 * size_t(d) ? f : 3 * d));   // {s, 1/s}
+    unsigned int* amax = reinterpret_cast<unsigned int*>(scale + 2);
+    // power-of-two scale s: max|dU2| * s in [32, 64) -> dU2, dH = dU2 W2 stay far from fp16's limits on both sides
+    RLT_TRY(grad_scale(d_u, size_t(T) * d, amax, scale, 6, stream));
+    RLT_TRY(convert_f16(d_u, du16, size_t(T) * d, scale, stream));
+    // dW2 += dU2^T h
+    RLT_TRY(gemm_dw_h(du16, d, hh, f, T, d, f, gw->lin2_w, f, 1.f, scale + 1, stream, TAG_DW_FFN2));
+    // dHpre = s * (dU2 W2) * (h > 0) -> fp16 ; db1 += colsum(dHpre) / s
+    EpiParams ep{};
+    ep.alpha = 1.f; ep.out_h = dh16; ep.ldo = f; ep.gate_h = hh; ep.colsum = gw->lin1_b; ep.scale_ptr = scale;
+    ep.scale_mode = 1; ep.tag = TAG_D_FFN2;
+    RLT_TRY(gemm_nn(d_u, d, w->lin2_w, f, T, f, d, ep, stream));
+    // dW1 += dHpre^T y
+    RLT_TRY(gemm_dw_h(dh16, f, y16, d, T, f, d, gw->lin1_w, d, 1.f, scale + 1, stream, TAG_DW_FFN1));
+    // dY = dU2 + (dHpre W1) / s
+    ep = EpiParams{}; ep.alpha = 1.f; ep.out = d_y; ep.ldo = d; ep.residual = d_u; ep.scale_ptr = scale; ep.scale_mode = 2;
+    ep.tag = TAG_D_FFN1;
+    RLT_TRY(gemm_tn_h(dh16, f, w1th, f, T, d, f, ep, stream));
+  } else {
+    // dW2 += dU2^T h
+    RLT_TRY(gemm_dw(d_u, d, sv + sl.h, f, T, d, f, gw->lin2_w, f, 1.f, stream, TAG_DW_FFN2));
+    // dHpre = (dU2 W2) * (h > 0) ; db1 += colsum(dHpre)
+    EpiParams ep{};
+    ep.alpha = 1.f; ep.out = wide; ep.ldo = f; ep.gate_src = sv + sl.h; ep.colsum = gw->lin1_b; ep.tag = TAG_D_FFN2;
+    RLT_TRY(gemm_nn(d_u, d, w->lin2_w, f, T, f, d, ep, stream));
+    // dW1 += dHpre^T y
+    RLT_TRY(gemm_dw(wide, f, sv + sl.y, d, T, f, d, gw->lin1_w, d, 1.f, stream, TAG_DW_FFN1));
+    // dY = dU2 + dHpre W1
+    ep = EpiParams{}; ep.alpha = 1.f; ep.out = d_y; ep.ldo = d; ep.residual = d_u; ep.tag = TAG_D_FFN1;
+    RLT_TRY(gemm_nn(wide, f, w->lin1_w, d, T, d, f, ep, stream));
+  }
   EpiParams ep{};
-  ep.alpha = 1.f; ep.out = wide; ep.ldo = f; ep.gate_src = sv + sl.h; ep.colsum = gw->lin1_b; ep.tag = TAG_D_FFN2;
-  RLT_TRY(gemm_nn(d_u, d, w->lin2_w, f, T, f, d, ep, stream));
-  // dW1 += dHpre^T y
-  RLT_TRY(gemm_dw(wide, f, sv + sl.y, d, T, f, d, gw->lin1_w, d, 1.f, stream, TAG_DW_FFN1));
-  // dY = dU2 + dHpre W1
-  ep = EpiParams{}; ep.alpha = 1.f; ep.out = d_y; ep.ldo = d; ep.residual = d_u; ep.tag = TAG_D_FFN1;
-  RLT_TRY(gemm_nn(wide, f, w->lin1_w, d, T, d, f, ep, stream));
   // LN1 backward: dU1 (into d_u), dgamma1, dbeta1, db_o
   RLT_TRY(layer_norm_bwd(d_y, sv + sl.u1, sv + sl.st1, w->norm1_w, d_u, gw->norm1_w, gw->norm1_b, gw->out_proj_b, T, d,
                          stream));

@@ -8,6 +8,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.h"
 #include "gemm_tc.cuh"
 
@@ -88,26 +90,32 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D row-major fp32 matrix [rows, cols] with leading dimension ld (elements); box = box_rows x 32
-// columns (128 B), SWIZZLE_128B, zero fill outside the matrix.
-static int make_tmap(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                     uint32_t box_rows, bool round_tf32, bool atom32 = false) {
+// 2-D row-major matrix [rows, cols] with leading dimension ld (elements); box = box_rows x (128 bytes of columns:
+// 32 fp32 or 64 fp16), SWIZZLE_128B (or the 32-byte-atom variant for MN-major fp32 operands), zero fill outside.
+static int make_tmap_any(CUtensorMap* out, const void* base, int elem_bytes, CUtensorMapDataType dtype, uint64_t rows,
+                         uint64_t cols, uint64_t ld, uint32_t box_rows, bool atom32) {
   EncodeTiledFn fn = encode_fn();
   RLT_REQUIRE(fn != nullptr, RLT_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from the driver");
-  RLT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld % 4) == 0, RLT_INVALID_ARG,
-              "TMA operand must be 16-byte aligned with a leading dimension that is a multiple of 4 floats "
-              "(ptr=%p ld=%llu)", (const void*)base, (unsigned long long)ld);
+  RLT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * elem_bytes) % 16 == 0, RLT_INVALID_ARG,
+              "TMA operand must be 16-byte aligned with a row pitch that is a multiple of 16 bytes "
+              "(ptr=%p ld=%llu)", base, (unsigned long long)ld);
   const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {ld * sizeof(float)};
-  const cuuint32_t box[2] = {32u, box_rows};
+  const cuuint64_t strides[1] = {ld * elem_bytes};
+  const cuuint32_t box[2] = {cuuint32_t(128 / elem_bytes), box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
-  const CUresult r = fn(out, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                        const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const CUresult r = fn(out, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RLT_REQUIRE(r == CUDA_SUCCESS, RLT_CUDA_ERROR, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
   return RLT_OK;
+}
+static int make_tmap(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_rows, bool round_tf32, bool atom32 = false) {
+  return make_tmap_any(out, base, 4, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rows,
+                       cols, ld, box_rows, atom32);
+}
+static int make_tmap_h(CUtensorMap* out, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  return make_tmap_any(out, base, 2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rows, cols, ld, box_rows, false);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -145,15 +153,22 @@ __global__ void gemm_tn_simt_kernel(const float* __restrict__ A, int lda, const 
     for (int j = 0; j < 4; ++j) {
       const int r = m0 + ty * 4 + i, c = n0 + tx * 4 + j;
       if (r >= M || c >= N) continue;
-      float v = acc[i][j] * ep.alpha;
+      float alpha = ep.alpha;
+      if (ep.scale_mode) alpha *= ep.scale_ptr[ep.scale_mode == 1 ? 0 : 1];
+      float v = acc[i][j] * alpha;
       if (ep.bias) v += ep.bias[c];
       if (ep.relu) v = fmaxf(v, 0.f);
       const size_t off = size_t(r) * ep.ldo + c;
       if (ep.gate_src) v = ep.gate_src[off] > 0.f ? v : 0.f;
+      if (ep.gate_h) v = __half2float(ep.gate_h[off]) > 0.f ? v : 0.f;
       if (ep.residual) v += ep.residual[off];
-      if (ep.accumulate) v += ep.out[off];
-      ep.out[off] = v;
-      if (ep.colsum) atomicAdd(ep.colsum + c, v);
+      if (ep.out_h) {
+        ep.out_h[off] = __float2half_rn(v);
+      } else {
+        if (ep.accumulate) v += ep.out[off];
+        ep.out[off] = v;
+      }
+      if (ep.colsum) atomicAdd(ep.colsum + c, ep.scale_mode == 1 ? v * ep.scale_ptr[1] : v);
     }
 }
 
@@ -172,32 +187,38 @@ __global__ void gemm_dw_simt_kernel(const float* __restrict__ A, int lda, const 
 // ------------------------------------------------------------------------------------------
 // front-ends
 // ------------------------------------------------------------------------------------------
-template <int BN, bool kBMajorN, int EF>
+template <int BN, int OP, int EF>
 static int launch_tn_ef(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& ep, int grid,
                         cudaStream_t stream) {
   using Cfg = GemmTnCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, kBMajorN, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, OP, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         int(Cfg::SMEM_BYTES)));
     attr_set = true;
   }
   time_begin(ep.tag, stream);
-  gemm_tn_kernel<BN, kBMajorN, EF><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+  gemm_tn_kernel<BN, OP, EF><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
   time_end(ep.tag, stream);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }
 
-template <int BN, bool kBMajorN>
-static int launch_tn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
+template <int BN, int OP>
+static int launch_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const EpiParams& ep,
                      cudaStream_t stream) {
   using Cfg = GemmTnCfg<BN>;
-  RLT_REQUIRE(ep.out != nullptr, RLT_INVALID_ARG, "gemm: null output");
+  RLT_REQUIRE(ep.out != nullptr || ep.out_h != nullptr, RLT_INVALID_ARG, "gemm: null output");
+  RLT_REQUIRE(ep.scale_mode == 0 || ep.scale_ptr != nullptr, RLT_INVALID_ARG, "gemm: scale_mode without scale_ptr");
   CUtensorMap tmA, tmB;
-  RLT_TRY(make_tmap(&tmA, A, M, K, lda, Cfg::BM, tma_rounds()));
-  if (kBMajorN) RLT_TRY(make_tmap(&tmB, B, K, N, ldb, Cfg::BK, tma_rounds(), true));
-  else RLT_TRY(make_tmap(&tmB, B, N, K, ldb, BN, tma_rounds()));
+  if (OP == OP_F16_K) {
+    RLT_TRY(make_tmap_h(&tmA, static_cast<const __half*>(A), M, K, lda, Cfg::BM));
+    RLT_TRY(make_tmap_h(&tmB, static_cast<const __half*>(B), N, K, ldb, BN));
+  } else {
+    RLT_TRY(make_tmap(&tmA, static_cast<const float*>(A), M, K, lda, Cfg::BM, tma_rounds()));
+    if (OP == OP_TF32_N) RLT_TRY(make_tmap(&tmB, static_cast<const float*>(B), K, N, ldb, Cfg::BK, tma_rounds(), true));
+    else RLT_TRY(make_tmap(&tmB, static_cast<const float*>(B), N, K, ldb, BN, tma_rounds()));
+  }
   // grid = a multiple of the number of column blocks (each CTA keeps one column block, see the kernel), at most
   // one CTA per SM and no more row-block walkers than there are row blocks
   const int tiles_m = (M + Cfg::BM - 1) / Cfg::BM, tiles_n = N / BN;
@@ -208,7 +229,7 @@ static int launch_tn(const float* A, int lda, const float* B, int ldb, int M, in
   // epilogue specialisations of the hot call sites (encoder / BiLSTM); anything else takes the run-time epilogue
   if (BN >= 128) {
     switch (epi_mask(ep)) {
-#define RLT_EF_CASE(mask) case (mask): return launch_tn_ef<BN, kBMajorN, (mask)>(tmA, tmB, M, N, K, ep, grid, stream)
+#define RLT_EF_CASE(mask) case (mask): return launch_tn_ef<BN, OP, (mask)>(tmA, tmB, M, N, K, ep, grid, stream)
       RLT_EF_CASE(0);
       RLT_EF_CASE(EF_BIAS);
       RLT_EF_CASE(EF_BIAS | EF_RELU);
@@ -216,51 +237,71 @@ static int launch_tn(const float* A, int lda, const float* B, int ldb, int M, in
       RLT_EF_CASE(EF_GATE | EF_COLSUM);
       RLT_EF_CASE(EF_RES);
       RLT_EF_CASE(EF_ACC);
+      RLT_EF_CASE(EF_BIAS | EF_RELU | EF_OUT_H);                    // FFN1 -> fp16 hidden
+      RLT_EF_CASE(EF_GATE_H | EF_COLSUM | EF_OUT_H | EF_SCALE);     // dH = s (dU W2) [h > 0] -> fp16
+      RLT_EF_CASE(EF_RES | EF_SCALE);                               // dY = dU + (dH W1) / s
 #undef RLT_EF_CASE
       default: break;
     }
   }
-  return launch_tn_ef<BN, kBMajorN, EF_RUNTIME>(tmA, tmB, M, N, K, ep, grid, stream);
+  return launch_tn_ef<BN, OP, EF_RUNTIME>(tmA, tmB, M, N, K, ep, grid, stream);
 }
 
-template <bool kBMajorN>
-static int gemm_any(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
+template <int OP>
+static int gemm_any(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const EpiParams& ep,
                     cudaStream_t stream) {
   RLT_REQUIRE(M > 0 && N > 0 && K > 0, RLT_INVALID_ARG, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  if (gemm_backend() == 1) {
-    dim3 grid((N + 63) / 64, (M + 63) / 64);
-    gemm_tn_simt_kernel<<<grid, 256, 0, stream>>>(A, lda, B, ldb, M, N, K, ep, kBMajorN ? 1 : 0);
-    RLT_CHECK_LAUNCH();
-    return RLT_OK;
-  }
   RLT_REQUIRE(N % 32 == 0, RLT_UNSUPPORTED_SHAPE, "gemm: N=%d must be a multiple of 32", N);
   RLT_REQUIRE(ep.ldo % 4 == 0, RLT_UNSUPPORTED_SHAPE, "gemm: output leading dimension %d must be a multiple of 4",
               ep.ldo);
-  if (N % 256 == 0) return launch_tn<256, kBMajorN>(A, lda, B, ldb, M, N, K, ep, stream);
-  if (N % 128 == 0) return launch_tn<128, kBMajorN>(A, lda, B, ldb, M, N, K, ep, stream);
-  if (N % 64 == 0) return launch_tn<64, kBMajorN>(A, lda, B, ldb, M, N, K, ep, stream);
-  return launch_tn<32, kBMajorN>(A, lda, B, ldb, M, N, K, ep, stream);
+  if (N % 256 == 0) return launch_tn<256, OP>(A, lda, B, ldb, M, N, K, ep, stream);
+  if (N % 128 == 0) return launch_tn<128, OP>(A, lda, B, ldb, M, N, K, ep, stream);
+  if (OP == OP_F16_K) return set_error(RLT_UNSUPPORTED_SHAPE, "gemm (fp16 operands): N=%d must be a multiple of 128", N);
+  if (N % 64 == 0) return launch_tn<64, OP == OP_F16_K ? OP_TF32_K : OP>(A, lda, B, ldb, M, N, K, ep, stream);
+  return launch_tn<32, OP == OP_F16_K ? OP_TF32_K : OP>(A, lda, B, ldb, M, N, K, ep, stream);
+}
+
+static int gemm_simt(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
+                     cudaStream_t stream, int b_major_n) {
+  RLT_REQUIRE(M > 0 && N > 0 && K > 0, RLT_INVALID_ARG, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  gemm_tn_simt_kernel<<<grid, 256, 0, stream>>>(A, lda, B, ldb, M, N, K, ep, b_major_n);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
 }
 
 int gemm_tn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
             cudaStream_t stream) {
-  return gemm_any<false>(A, lda, B, ldb, M, N, K, ep, stream);
+  if (gemm_backend() == 1) return gemm_simt(A, lda, B, ldb, M, N, K, ep, stream, 0);
+  return gemm_any<OP_TF32_K>(A, lda, B, ldb, M, N, K, ep, stream);
 }
 int gemm_nn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
             cudaStream_t stream) {
-  return gemm_any<true>(A, lda, B, ldb, M, N, K, ep, stream);
+  if (gemm_backend() == 1) return gemm_simt(A, lda, B, ldb, M, N, K, ep, stream, 1);
+  return gemm_any<OP_TF32_N>(A, lda, B, ldb, M, N, K, ep, stream);
+}
+int gemm_tn_h(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const EpiParams& ep,
+              cudaStream_t stream) {
+  RLT_REQUIRE(gemm_backend() == 0, RLT_INVALID_ARG, "gemm_tn_h: fp16 operands exist only on the tensor-core backend");
+  RLT_REQUIRE(K % 8 == 0, RLT_UNSUPPORTED_SHAPE, "gemm_tn_h: K=%d must be a multiple of 8", K);
+  return gemm_any<OP_F16_K>(A, lda, B, ldb, M, N, K, ep, stream);
 }
 
-template <int BN>
-static int launch_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int N, float* C, int ldc,
-                     float alpha, cudaStream_t stream) {
-  using Cfg = GemmDwCfg<BN>;
+template <int BN, bool kF16>
+static int launch_dw(const void* A, int lda, const void* B, int ldb, int T, int M, int N, float* C, int ldc,
+                     float alpha, const float* alpha_ptr, cudaStream_t stream) {
+  using Cfg = GemmDwCfg<BN, kF16>;
   CUtensorMap tmA, tmB;
-  RLT_TRY(make_tmap(&tmA, A, T, M, lda, Cfg::BT, tma_rounds(), true));
-  RLT_TRY(make_tmap(&tmB, B, T, N, ldb, Cfg::BT, tma_rounds(), true));
+  if (kF16) {
+    RLT_TRY(make_tmap_h(&tmA, static_cast<const __half*>(A), T, M, lda, Cfg::BT));
+    RLT_TRY(make_tmap_h(&tmB, static_cast<const __half*>(B), T, N, ldb, Cfg::BT));
+  } else {
+    RLT_TRY(make_tmap(&tmA, static_cast<const float*>(A), T, M, lda, Cfg::BT, tma_rounds(), true));
+    RLT_TRY(make_tmap(&tmB, static_cast<const float*>(B), T, N, ldb, Cfg::BT, tma_rounds(), true));
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_dw_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_dw_kernel<BN, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         int(Cfg::SMEM_BYTES)));
     attr_set = true;
   }
@@ -271,18 +312,20 @@ static int launch_dw(const float* A, int lda, const float* B, int ldb, int T, in
   if (splits < 1) splits = 1;
   const int max_splits = (num_tb + 7) / 8;
   if (splits > max_splits) splits = max_splits;
-  gemm_dw_kernel<BN><<<dim3(tiles, splits), 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, T, M, N, C, ldc, alpha);
+  gemm_dw_kernel<BN, kF16><<<dim3(tiles, splits), 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, T, M, N, C, ldc, alpha, alpha_ptr);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }
 
+struct TimeScope {
+  int tag; cudaStream_t s;
+  TimeScope(int t, cudaStream_t st) : tag(t), s(st) { time_begin(tag, s); }
+  ~TimeScope() { time_end(tag, s); }
+};
+
 int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
             cudaStream_t stream, int tag) {
-  struct Scope {
-    int tag; cudaStream_t s;
-    Scope(int t, cudaStream_t st) : tag(t), s(st) { time_begin(tag, s); }
-    ~Scope() { time_end(tag, s); }
-  } scope(tag, stream);
+  TimeScope scope(tag, stream);
   RLT_REQUIRE(T > 0 && M > 0 && N > 0, RLT_INVALID_ARG, "gemm_dw: empty problem T=%d M=%d N=%d", T, M, N);
   if (gemm_backend() == 1) {
     const int tchunk = 2048;
@@ -292,10 +335,100 @@ int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int 
     return RLT_OK;
   }
   RLT_REQUIRE(N % 32 == 0, RLT_UNSUPPORTED_SHAPE, "gemm_dw: N=%d must be a multiple of 32", N);
-  if (N % 256 == 0) return launch_dw<256>(A, lda, B, ldb, T, M, N, C, ldc, alpha, stream);
-  if (N % 128 == 0) return launch_dw<128>(A, lda, B, ldb, T, M, N, C, ldc, alpha, stream);
-  if (N % 64 == 0) return launch_dw<64>(A, lda, B, ldb, T, M, N, C, ldc, alpha, stream);
-  return launch_dw<32>(A, lda, B, ldb, T, M, N, C, ldc, alpha, stream);
+  if (N % 256 == 0) return launch_dw<256, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, nullptr, stream);
+  if (N % 128 == 0) return launch_dw<128, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, nullptr, stream);
+  if (N % 64 == 0) return launch_dw<64, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, nullptr, stream);
+  return launch_dw<32, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, nullptr, stream);
+}
+
+int gemm_dw_h(const __half* A, int lda, const __half* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
+              const float* alpha_ptr, cudaStream_t stream, int tag) {
+  TimeScope scope(tag, stream);
+  RLT_REQUIRE(T > 0 && M > 0 && N > 0, RLT_INVALID_ARG, "gemm_dw_h: empty problem T=%d M=%d N=%d", T, M, N);
+  RLT_REQUIRE(gemm_backend() == 0, RLT_INVALID_ARG, "gemm_dw_h: fp16 operands exist only on the tensor-core backend");
+  RLT_REQUIRE(N % 128 == 0 && M % 64 == 0, RLT_UNSUPPORTED_SHAPE, "gemm_dw_h: M=%d N=%d must be multiples of 64 / 128", M, N);
+  if (N % 256 == 0) return launch_dw<256, true>(A, lda, B, ldb, T, M, N, C, ldc, alpha, alpha_ptr, stream);
+  return launch_dw<128, true>(A, lda, B, ldb, T, M, N, C, ldc, alpha, alpha_ptr, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// fp16 operand copies
+// ------------------------------------------------------------------------------------------
+// dst = half(src * (scale ? scale[0] : 1)), n a multiple of 4
+__global__ void __launch_bounds__(256) convert_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n4,
+                                                          const float* __restrict__ scale) {
+  const float s = scale != nullptr ? scale[0] : 1.f;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const __half2 lo = __floats2half2_rn(v.x * s, v.y * s), hi = __floats2half2_rn(v.z * s, v.w * s);
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+  }
+}
+int convert_f16(const float* src, __half* dst, size_t n, const float* scale, cudaStream_t stream) {
+  RLT_REQUIRE(n % 4 == 0, RLT_INVALID_ARG, "convert_f16: n must be a multiple of 4");
+  size_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > size_t(num_sms()) * 16) blocks = size_t(num_sms()) * 16;
+  convert_f16_kernel<<<unsigned(blocks), 256, 0, stream>>>(src, dst, n / 4, scale);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+// dst[c, r] = half(src[r, c])   ([rows, cols] -> [cols, rows])
+__global__ void transpose_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[size_t(r) * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[size_t(c) * rows + r] = __float2half_rn(tile[threadIdx.x][i]);
+  }
+}
+int transpose_f16(const float* src, __half* dst, int rows, int cols, cudaStream_t stream) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_f16_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, dst, rows, cols);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+// amax |x| -> bits of a non-negative float in *out (zero-initialised by the caller); n4 = n / 4
+__global__ void __launch_bounds__(256) amax_abs4_kernel(const float4* __restrict__ x, size_t n4, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = x[i];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+// scale[0] = 2^k with amax * 2^k in [2^(target-1), 2^target), scale[1] = 2^-k  (1, 1 when amax is 0 or not finite)
+__global__ void pow2_scale_kernel(const unsigned int* __restrict__ amax_bits, float* __restrict__ scale, int target) {
+  const float a = __uint_as_float(*amax_bits);
+  float s = 1.f;
+  if (a > 0.f && a < 3.0e38f) {
+    int e;
+    frexpf(a, &e);                   // a = m * 2^e, m in [0.5, 1)
+    s = ldexpf(1.f, target - e);
+  }
+  scale[0] = s;
+  scale[1] = 1.f / s;
+}
+int grad_scale(const float* x, size_t n, unsigned int* amax_scratch, float* scale, int target, cudaStream_t stream) {
+  RLT_REQUIRE(n % 4 == 0, RLT_INVALID_ARG, "grad_scale: n must be a multiple of 4");
+  RLT_CHECK_CUDA(cudaMemsetAsync(amax_scratch, 0, sizeof(unsigned int), stream));
+  size_t blocks = (n / 4 + 255) / 256;
+  if (blocks > size_t(num_sms()) * 16) blocks = size_t(num_sms()) * 16;
+  if (blocks < 1) blocks = 1;
+  amax_abs4_kernel<<<unsigned(blocks), 256, 0, stream>>>(reinterpret_cast<const float4*>(x), n / 4, amax_scratch);
+  RLT_CHECK_LAUNCH();
+  pow2_scale_kernel<<<1, 1, 0, stream>>>(amax_scratch, scale, target);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -447,6 +580,43 @@ int rlt_grad_weight(const float* A, const float* B, float* C, int T, int M, int 
                     rlt_stream_t stream) {
   RLT_REQUIRE(A && B && C, RLT_INVALID_ARG, "rlt_grad_weight: null pointer");
   return gemm_dw(A, M, B, N, T, M, N, C, N, alpha, static_cast<cudaStream_t>(stream));
+}
+
+int rlt_convert_f16(const float* src, void* dst, size_t n, const float* scale, rlt_stream_t stream) {
+  RLT_REQUIRE(src && dst, RLT_INVALID_ARG, "rlt_convert_f16: null pointer");
+  return convert_f16(src, static_cast<__half*>(dst), n, scale, static_cast<cudaStream_t>(stream));
+}
+
+int rlt_linear_f16(const void* A, const void* B, const float* bias, float* C, int M, int N, int K, float alpha, int relu,
+                   rlt_stream_t stream) {
+  RLT_REQUIRE(A && B && C, RLT_INVALID_ARG, "rlt_linear_f16: null pointer");
+  EpiParams ep{};
+  ep.out = C;
+  ep.ldo = N;
+  ep.bias = bias;
+  ep.relu = relu;
+  ep.alpha = alpha;
+  return gemm_tn_h(static_cast<const __half*>(A), K, static_cast<const __half*>(B), K, M, N, K, ep,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int rlt_grad_weight_f16(const void* A, const void* B, float* C, int T, int M, int N, float alpha, rlt_stream_t stream) {
+  RLT_REQUIRE(A && B && C, RLT_INVALID_ARG, "rlt_grad_weight_f16: null pointer");
+  return gemm_dw_h(static_cast<const __half*>(A), M, static_cast<const __half*>(B), N, T, M, N, C, N, alpha, nullptr,
+                   static_cast<cudaStream_t>(stream), 0);
+}
+
+/* C (fp16) = relu(A B^T + bias): the FFN1 form (fp32 operands, half-precision result). */
+int rlt_linear_out_f16(const float* A, const float* B, const float* bias, void* C, int M, int N, int K, int relu,
+                       rlt_stream_t stream) {
+  RLT_REQUIRE(A && B && C, RLT_INVALID_ARG, "rlt_linear_out_f16: null pointer");
+  EpiParams ep{};
+  ep.out_h = static_cast<__half*>(C);
+  ep.ldo = N;
+  ep.bias = bias;
+  ep.relu = relu;
+  ep.alpha = 1.f;
+  return gemm_tn(A, K, B, K, M, N, K, ep, static_cast<cudaStream_t>(stream));
 }
 
 int rlt_probe_tma_tf32(const float* src, float* dst, int rows, rlt_stream_t stream) {

@@ -13,12 +13,14 @@
 // accumulate reads.  Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the
 // main loop of tile i+1.  Operands are fp32 in HBM; the TFLOAT32 tensor maps round them on load.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "sm100.cuh"
 
 namespace rlt {
 
 struct EpiParams {
-  float* out;             // [M, ldo] fp32 result
+  float* out;             // [M, ldo] fp32 result (null when out_h is used)
   int ldo;
   const float* bias;      // [N] added to every row (may be null)
   const float* gate_src;  // [M, ldo]: result *= (gate_src > 0)   (ReLU backward; may be null)
@@ -28,6 +30,14 @@ struct EpiParams {
   int accumulate;         // out += result instead of out = result
   float alpha;            // result scale applied first
   int tag;                // KernelTag of the call site (in-situ timing; 0 = none)
+  // ---- half-precision activations of the FFN hidden layer (fp16 = the 11 significant bits of TF32)
+  __half* out_h;          // [M, ldo] fp16 result instead of `out`
+  const __half* gate_h;   // [M, ldo] fp16 gate source instead of `gate_src`
+  // device-side power-of-two scale {s, 1/s} (gradients are ~1e-6: fp16 needs them scaled into its normal range):
+  //   scale_mode 1: result *= s and the column sums are multiplied by 1/s (they stay unscaled)
+  //   scale_mode 2: result *= 1/s (unscale a contraction over scaled operands)
+  const float* scale_ptr;
+  int scale_mode;
 };
 
 // Sum v[j] over the 32 lanes of a warp for 32 different j: on return lane j holds the column-j
@@ -66,10 +76,12 @@ struct GemmTnCfg {
 // which the unused branches do not exist (the fully unrolled epilogue is otherwise ~3700 instructions and the eight
 // epilogue warps thrash the instruction cache: measured +30-45% on the store-bound GEMMs); EF_RUNTIME keeps every
 // branch and tests the EpiParams fields at run time.
-enum : int { EF_BIAS = 1, EF_RELU = 2, EF_GATE = 4, EF_RES = 8, EF_COLSUM = 16, EF_ACC = 32, EF_RUNTIME = 64 };
+enum : int { EF_BIAS = 1, EF_RELU = 2, EF_GATE = 4, EF_RES = 8, EF_COLSUM = 16, EF_ACC = 32, EF_RUNTIME = 64,
+              EF_OUT_H = 128, EF_GATE_H = 256, EF_SCALE = 512 };
 __host__ __device__ inline int epi_mask(const EpiParams& ep) {
   return (ep.bias ? EF_BIAS : 0) | (ep.relu ? EF_RELU : 0) | (ep.gate_src ? EF_GATE : 0) | (ep.residual ? EF_RES : 0) |
-         (ep.colsum ? EF_COLSUM : 0) | (ep.accumulate ? EF_ACC : 0);
+         (ep.colsum ? EF_COLSUM : 0) | (ep.accumulate ? EF_ACC : 0) | (ep.out_h ? EF_OUT_H : 0) |
+         (ep.gate_h ? EF_GATE_H : 0) | (ep.scale_mode ? EF_SCALE : 0);
 }
 template <int EF> __device__ __forceinline__ bool ef_bias(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.bias != nullptr : (EF & EF_BIAS) != 0; }
 template <int EF> __device__ __forceinline__ bool ef_relu(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.relu != 0 : (EF & EF_RELU) != 0; }
@@ -77,6 +89,9 @@ template <int EF> __device__ __forceinline__ bool ef_gate(const EpiParams& ep) {
 template <int EF> __device__ __forceinline__ bool ef_res(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.residual != nullptr : (EF & EF_RES) != 0; }
 template <int EF> __device__ __forceinline__ bool ef_colsum(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.colsum != nullptr : (EF & EF_COLSUM) != 0; }
 template <int EF> __device__ __forceinline__ bool ef_acc(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.accumulate != 0 : (EF & EF_ACC) != 0; }
+template <int EF> __device__ __forceinline__ bool ef_out_h(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.out_h != nullptr : (EF & EF_OUT_H) != 0; }
+template <int EF> __device__ __forceinline__ bool ef_gate_h(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.gate_h != nullptr : (EF & EF_GATE_H) != 0; }
+template <int EF> __device__ __forceinline__ bool ef_scale(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.scale_mode != 0 : (EF & EF_SCALE) != 0; }
 
 // Operand of the epilogue that comes from global memory, fetched for a whole 32x32 chunk BEFORE the accumulator is
 // read so that the 8 independent 128-bit loads per lane are in flight together instead of one DRAM round trip per
@@ -95,9 +110,20 @@ __device__ __forceinline__ const float* epi_aux_src(const EpiParams& ep) {
 }
 template <int EF>
 __device__ __forceinline__ void epilogue_fetch_aux(const EpiParams& ep, EpiAux& aux, int row0, int M, int col0, int lane) {
+  const int col = col0 + (lane & 7) * 4;
+  if (ef_gate_h<EF>(ep)) {   // fp16 gate source: 4 halves = 8 bytes per lane, kept in the .x/.y words
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row0 + it * 4 + (lane >> 3);
+      uint2 g = make_uint2(0u, 0u);
+      if (row < M) g = *reinterpret_cast<const uint2*>(ep.gate_h + size_t(row) * ep.ldo + col);
+      aux.a[it].x = __uint_as_float(g.x);
+      aux.a[it].y = __uint_as_float(g.y);
+    }
+    return;
+  }
   const float* src = epi_aux_src<EF>(ep);
   if (src == nullptr) return;
-  const int col = col0 + (lane & 7) * 4;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int row = row0 + it * 4 + (lane >> 3);
@@ -124,9 +150,11 @@ __device__ __forceinline__ void epilogue_store_chunk(const EpiParams& ep, float 
   const int col = col0 + cu * 4;
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ef_bias<EF>(ep)) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+  float alpha = ep.alpha;
+  if (ef_scale<EF>(ep)) alpha *= ep.scale_ptr[ep.scale_mode == 1 ? 0 : 1];
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   // which optional operand travelled through aux (same priority as epi_aux_src)
-  const bool gate_in_aux = ef_gate<EF>(ep);
+  const bool gate_in_aux = ef_gate<EF>(ep) || ef_gate_h<EF>(ep);
   const bool res_in_aux = !gate_in_aux && ef_res<EF>(ep);
   const bool acc_in_aux = !gate_in_aux && !res_in_aux && ef_acc<EF>(ep);
 #pragma unroll
@@ -135,11 +163,16 @@ __device__ __forceinline__ void epilogue_store_chunk(const EpiParams& ep, float 
     float4 x = *reinterpret_cast<const float4*>(stage + r * 128 + (((cu ^ r) & 7) << 4));
     const int row = row0 + r;
     if (row < M) {
-      x.x = fmaf(x.x, ep.alpha, bias.x); x.y = fmaf(x.y, ep.alpha, bias.y);
-      x.z = fmaf(x.z, ep.alpha, bias.z); x.w = fmaf(x.w, ep.alpha, bias.w);
+      x.x = fmaf(x.x, alpha, bias.x); x.y = fmaf(x.y, alpha, bias.y);
+      x.z = fmaf(x.z, alpha, bias.z); x.w = fmaf(x.w, alpha, bias.w);
       if (ef_relu<EF>(ep)) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
       const size_t off = size_t(row) * ep.ldo + col;
-      if (ef_gate<EF>(ep)) {
+      if (ef_gate_h<EF>(ep)) {
+        // fp16 values are >= +0 after the ReLU: "> 0" is "any bit set" of the 16-bit pattern
+        const uint32_t g0 = __float_as_uint(aux.a[it].x), g1 = __float_as_uint(aux.a[it].y);
+        x.x = (g0 & 0xffffu) ? x.x : 0.f; x.y = (g0 >> 16) ? x.y : 0.f;
+        x.z = (g1 & 0xffffu) ? x.z : 0.f; x.w = (g1 >> 16) ? x.w : 0.f;
+      } else if (ef_gate<EF>(ep)) {
         const float4 g = aux.a[it];
         x.x = g.x > 0.f ? x.x : 0.f; x.y = g.y > 0.f ? x.y : 0.f;
         x.z = g.z > 0.f ? x.z : 0.f; x.w = g.w > 0.f ? x.w : 0.f;
@@ -148,12 +181,18 @@ __device__ __forceinline__ void epilogue_store_chunk(const EpiParams& ep, float 
         const float4 q = res_in_aux ? aux.a[it] : *reinterpret_cast<const float4*>(ep.residual + off);
         x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
       }
-      float4* o = reinterpret_cast<float4*>(ep.out + off);
-      if (ef_acc<EF>(ep)) {
-        const float4 q = acc_in_aux ? aux.a[it] : *o;
-        x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+      if (ef_out_h<EF>(ep)) {
+        const __half2 lo = __floats2half2_rn(x.x, x.y), hi = __floats2half2_rn(x.z, x.w);
+        *reinterpret_cast<uint2*>(ep.out_h + off) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      } else {
+        float4* o = reinterpret_cast<float4*>(ep.out + off);
+        if (ef_acc<EF>(ep)) {
+          const float4 q = acc_in_aux ? aux.a[it] : *o;
+          x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+        }
+        *o = x;
       }
-      *o = x;
       if (ef_colsum<EF>(ep)) { cs.x += x.x; cs.y += x.y; cs.z += x.z; cs.w += x.w; }
     }
   }
@@ -171,14 +210,21 @@ __device__ __forceinline__ void epilogue_store_chunk(const EpiParams& ep, float 
   __syncwarp();   // the staging buffer is rewritten by the next chunk
 }
 
-// kBMajorN = false: B is [N, K] row-major (K-major operand, nn.Linear weight used as-is: x W^T).
-// kBMajorN = true : B is [K, N] row-major (MN-major operand: x W with W stored [K, N]); its stage is
+// Operand kinds (template parameter OP):
+//   OP_TF32_K : A [M, K] fp32, B [N, K] fp32 row-major (K-major operands, nn.Linear weight used as-is: x W^T)
+//   OP_TF32_N : A [M, K] fp32, B [K, N] fp32 row-major (MN-major B: x W with W stored [K, N])
+//   OP_F16_K  : A [M, K] fp16, B [N, K] fp16 (K-major, kind::f16: 64 elements per 128-byte swizzle row)
+enum : int { OP_TF32_K = 0, OP_TF32_N = 1, OP_F16_K = 2 };
+// MN-major B: its stage is
 //                   BN/32 boxes of 32 k-rows x 32 columns in the SWIZZLE_128B_BASE32B layout.
-template <int BN, bool kBMajorN, int EF>
+template <int BN, int OP, int EF>
 __global__ void __launch_bounds__(GemmTnCfg<BN>::THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                int K, EpiParams ep) {
   using Cfg = GemmTnCfg<BN>;
+  constexpr bool kBMajorN = OP == OP_TF32_N;
+  constexpr bool kF16 = OP == OP_F16_K;
+  constexpr int BKE = kF16 ? 64 : 32;     // elements per k-block (always 128 bytes)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* epi_stage = smem + size_t(Cfg::STAGES) * Cfg::STAGE_BYTES;
@@ -198,7 +244,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // column sums of a CTA stay in registers until the kernel ends.
   const int tiles_m = (M + Cfg::BM - 1) / Cfg::BM;
   const int tiles_n = N / BN;
-  const int num_kb = (K + Cfg::BK - 1) / Cfg::BK;
+  const int num_kb = (K + BKE - 1) / BKE;
   const int n0 = (int(blockIdx.x) % tiles_n) * BN;
   const int m_first = int(blockIdx.x) / tiles_n;
   const int m_step = int(gridDim.x) / tiles_n;
@@ -231,13 +277,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + size_t(s) * Cfg::STAGE_BYTES;
-          tma_load_2d(sa, &tmA, &full[s], kb * Cfg::BK, m0);
+          tma_load_2d(sa, &tmA, &full[s], kb * BKE, m0);
           if constexpr (!kBMajorN) {
-            tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], kb * Cfg::BK, n0);
+            tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], kb * BKE, n0);
           } else {
 #pragma unroll
             for (int b = 0; b < BN / 32; ++b)
-              tma_load_2d(sa + Cfg::A_BYTES + b * 4096, &tmB, &full[s], n0 + b * 32, kb * Cfg::BK);
+              tma_load_2d(sa + Cfg::A_BYTES + b * 4096, &tmB, &full[s], n0 + b * 32, kb * BKE);
           }
         }
       }
@@ -245,7 +291,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kFmtTF32, Cfg::BM, BN, false, kBMajorN);
+      constexpr uint32_t idesc = make_idesc(kF16 ? kFmtF16 : kFmtTF32, Cfg::BM, BN, false, kBMajorN);
       uint32_t it = 0, lt = 0;
       for (int mt = m_first; mt < tiles_m; mt += m_step, ++lt) {
         const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
@@ -264,8 +310,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // MN-major B advances 8 k-rows = 1024 B (+64)
           constexpr uint64_t kBStep = kBMajorN ? 64 : 2;
 #pragma unroll
-          for (int k = 0; k < Cfg::BK / 8; ++k)
-            umma_tf32(d_tmem, da + uint64_t(2 * k), db + kBStep * uint64_t(k), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {   // 32 bytes of K per MMA: 8 tf32 or 16 fp16
+            if constexpr (kF16) umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_tf32(d_tmem, da + uint64_t(2 * k), db + kBStep * uint64_t(k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty[s]);
         }
         umma_commit(&tfull[buf]);
@@ -303,7 +351,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (ef_colsum<EF>(ep)) {
       // all epilogue warps have added their partial column sums into s_colsum: one global atomic per column and CTA
       asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");
-      for (int j = threadIdx.x - 64; j < BN; j += Cfg::EPI_WARPS * 32) atomicAdd(ep.colsum + n0 + j, s_colsum[j]);
+      const float cscale = (ef_scale<EF>(ep) && ep.scale_mode == 1) ? ep.scale_ptr[1] : 1.f;
+      for (int j = threadIdx.x - 64; j < BN; j += Cfg::EPI_WARPS * 32) atomicAdd(ep.colsum + n0 + j, s_colsum[j] * cscale);
     }
   }
   tc_fence_before();
@@ -320,24 +369,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // grid = (tiles_m * tiles_n, splits); every CTA reduces a contiguous token range and red.adds its
 // partial tile into C (C must be initialised by the caller: zeros or the running gradient).
 // -----------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool kF16>
 struct GemmDwCfg {
   static constexpr int BM = 128;
-  static constexpr int BT = 32;  // tokens per stage (4 MMAs of K = 8)
-  static constexpr int BOX_BYTES = 32 * BT * 4;  // 4 KB
-  static constexpr int A_BYTES = (BM / 32) * BOX_BYTES;
-  static constexpr int B_BYTES = (BN / 32) * BOX_BYTES;
+  static constexpr int BT = kF16 ? 64 : 32;           // tokens per stage (4 MMAs of K = 8 tf32 / 16 fp16)
+  static constexpr int BOX_COLS = kF16 ? 64 : 32;     // 128-byte rows
+  static constexpr int BOX_BYTES = 128 * BT;          // 4 KB (tf32) / 8 KB (fp16)
+  static constexpr int A_BYTES = (BM / BOX_COLS) * BOX_BYTES;
+  static constexpr int B_BYTES = (BN / BOX_COLS) * BOX_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
+  static constexpr int STAGES = (STAGE_BYTES >= 48 * 1024) ? 4 : 6;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   static constexpr size_t SMEM_BYTES = 1024 + size_t(STAGES) * STAGE_BYTES + 256;
 };
 
-template <int BN>
+// kF16: both operands fp16, MN-major with the plain SWIZZLE_128B layout (an atom is 8 tokens x 128 B = 64 columns;
+// SBO = 1024 B to the next 8 tokens, LBO = one box to the next 64 columns; one K = 16 MMA spans two atoms).
+// alpha_ptr (optional): the partial tile is multiplied by alpha * alpha_ptr[0] (device-side unscale of fp16 gradients).
+template <int BN, bool kF16>
 __global__ void __launch_bounds__(192, 1)
 gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int T, int M,
-               int N, float* __restrict__ C, int ldc, float alpha) {
-  using Cfg = GemmDwCfg<BN>;
+               int N, float* __restrict__ C, int ldc, float alpha, const float* __restrict__ alpha_ptr) {
+  using Cfg = GemmDwCfg<BN, kF16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(Cfg::STAGES) * Cfg::STAGE_BYTES);
@@ -384,31 +437,39 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem + size_t(s) * Cfg::STAGE_BYTES;
           const int t0 = (tb0 + i) * Cfg::BT;
 #pragma unroll
-          for (int b = 0; b < Cfg::BM / 32; ++b) tma_load_2d(sa + b * Cfg::BOX_BYTES, &tmA, &full[s], m0 + b * 32, t0);
+          for (int b = 0; b < Cfg::BM / Cfg::BOX_COLS; ++b)
+            tma_load_2d(sa + b * Cfg::BOX_BYTES, &tmA, &full[s], m0 + b * Cfg::BOX_COLS, t0);
 #pragma unroll
-          for (int b = 0; b < BN / 32; ++b)
-            tma_load_2d(sa + Cfg::A_BYTES + b * Cfg::BOX_BYTES, &tmB, &full[s], n0 + b * 32, t0);
+          for (int b = 0; b < BN / Cfg::BOX_COLS; ++b)
+            tma_load_2d(sa + Cfg::A_BYTES + b * Cfg::BOX_BYTES, &tmB, &full[s], n0 + b * Cfg::BOX_COLS, t0);
         }
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc(kFmtTF32, Cfg::BM, BN, true, true);
+        constexpr uint32_t idesc = make_idesc(kF16 ? kFmtF16 : kFmtTF32, Cfg::BM, BN, true, true);
+        constexpr uint32_t kLayout = kF16 ? kLayoutSw128 : kLayoutSw128Base32;
+        constexpr uint32_t kSbo = kF16 ? 1024 : 512;
+        // next MMA: 8 tf32 tokens = 1024 B (+64 in the address field), 16 fp16 tokens = 2048 B (+128)
+        constexpr uint64_t kStep = kF16 ? 128 : 64;
         for (int i = 0; i < nblk; ++i) {
           const uint32_t s = i % Cfg::STAGES, ph = (i / Cfg::STAGES) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + size_t(s) * Cfg::STAGE_BYTES);
-          const uint64_t da = make_smem_desc_sw128(a_addr, Cfg::BOX_BYTES, 512, kLayoutSw128Base32);
-          const uint64_t db = make_smem_desc_sw128(a_addr + Cfg::A_BYTES, Cfg::BOX_BYTES, 512, kLayoutSw128Base32);
+          const uint64_t da = make_smem_desc_sw128(a_addr, Cfg::BOX_BYTES, kSbo, kLayout);
+          const uint64_t db = make_smem_desc_sw128(a_addr + Cfg::A_BYTES, Cfg::BOX_BYTES, kSbo, kLayout);
 #pragma unroll
-          for (int k = 0; k < Cfg::BT / 8; ++k)  // next 8 tokens = +1024 B: +64 in the address field
-            umma_tf32(tmem_base, da + uint64_t(64 * k), db + uint64_t(64 * k), idesc, (i | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            if constexpr (kF16) umma_f16(tmem_base, da + kStep * uint64_t(k), db + kStep * uint64_t(k), idesc, (i | k) != 0 ? 1u : 0u);
+            else umma_tf32(tmem_base, da + kStep * uint64_t(k), db + kStep * uint64_t(k), idesc, (i | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty[s]);
         }
         umma_commit(&tfull[0]);
       }
     } else {
       const int quarter = warp & 3;
+      const float a = alpha_ptr != nullptr ? alpha * alpha_ptr[0] : alpha;
       mbar_wait(&tfull[0], 0);
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
@@ -419,7 +480,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (row < M) {
           float* dst = C + size_t(row) * ldc + n0 + c * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, alpha * v[j]);
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, a * v[j]);
         }
       }
     }

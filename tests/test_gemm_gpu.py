@@ -92,3 +92,69 @@ def test_grad_weight(backend, T, M, N):
         assert err < 3e-5 * max(1.0, ref.abs().max().item()) * max(1.0, (T / 256) ** 0.5), (backend, T, M, N, err)
     finally:
         _lib.set_option("gemm_backend", 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# fp16-operand building blocks of the FFN hidden path
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 128, 2048), (777, 128, 2048), (1500, 256, 512), (300, 128, 64), (19200, 128, 2048)])
+def test_linear_f16_operands(M, N, K):
+    from rlt_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    B = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    C = torch.full((M, N), float("nan"), device="cuda")
+    _lib.check(lib.rlt_linear_f16(_lib.ptr(A), _lib.ptr(B), _lib.ptr(bias), _lib.ptr(C), M, N, K, ctypes.c_float(0.5), 0,
+                                  _lib.stream_ptr()), "rlt_linear_f16")
+    torch.cuda.synchronize()
+    ref = 0.5 * (A.double() @ B.double().t()) + bias.double()
+    err = (C.double() - ref).abs().max().item()
+    assert err < 2e-5 * max(1.0, ref.abs().max().item()), (M, N, K, err)
+
+
+@pytest.mark.parametrize("T,M,N", [(256, 128, 128), (1500, 128, 2048), (19200, 2048, 128), (5000, 256, 256), (333, 64, 128)])
+def test_grad_weight_f16_operands(T, M, N):
+    from rlt_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(T + M + N)
+    A = torch.randn(T, M, device="cuda", generator=g).half()
+    B = torch.randn(T, N, device="cuda", generator=g).half()
+    C0 = torch.randn(M, N, device="cuda", generator=g)
+    C = C0.clone()
+    _lib.check(lib.rlt_grad_weight_f16(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), T, M, N, ctypes.c_float(0.5),
+                                       _lib.stream_ptr()), "rlt_grad_weight_f16")
+    torch.cuda.synchronize()
+    ref = C0.double() + 0.5 * (A.double().t() @ B.double())
+    err = (C.double() - ref).abs().max().item()
+    assert err < 3e-5 * max(1.0, ref.abs().max().item()) * max(1.0, (T / 256) ** 0.5), (T, M, N, err)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 2048, 128), (1500, 256, 256)])
+def test_linear_half_precision_output(M, N, K):
+    from rlt_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + 1)
+    A = _tf32(torch.randn(M, K, device="cuda", generator=g))
+    B = _tf32(torch.randn(N, K, device="cuda", generator=g) / K ** 0.5)
+    bias = torch.randn(N, device="cuda", generator=g)
+    C = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+    _lib.check(lib.rlt_linear_out_f16(_lib.ptr(A), _lib.ptr(B), _lib.ptr(bias), _lib.ptr(C), M, N, K, 1, _lib.stream_ptr()),
+               "rlt_linear_out_f16")
+    torch.cuda.synchronize()
+    ref = torch.relu(A.double() @ B.double().t() + bias.double())
+    err = ((C.double() - ref).abs() / ref.abs().clamp_min(1.0)).max().item()
+    assert err < 2 ** -11 * 1.01, (M, N, K, err)          # one fp16 rounding of an fp32-accurate value
+
+
+def test_convert_f16_with_device_scale():
+    from rlt_b200 import _lib
+    lib = _lib.load()
+    x = torch.randn(4096 * 12, device="cuda") * 1e-5
+    scale = torch.tensor([2.0 ** 20, 2.0 ** -20], device="cuda")
+    out = torch.empty(x.numel(), device="cuda", dtype=torch.float16)
+    _lib.check(lib.rlt_convert_f16(_lib.ptr(x), _lib.ptr(out), ctypes.c_size_t(x.numel()), _lib.ptr(scale), _lib.stream_ptr()),
+               "rlt_convert_f16")
+    torch.cuda.synchronize()
+    assert torch.equal(out, (x * 2.0 ** 20).half())
