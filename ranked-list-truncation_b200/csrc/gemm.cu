@@ -38,6 +38,7 @@ static int g_gemm_backend = env_int("RLT_GEMM_BACKEND", 0);
 // exact ties), so operands stay exact fp32 in HBM and no rounded copies are materialised.  Without it the
 // tensor core would truncate the low 13 mantissa bits (a systematic -2^-11 relative bias per operand).
 static int g_tma_round = env_int("RLT_TMA_ROUND", 1);
+static int g_b_resident = env_int("RLT_B_RESIDENT", 1);   // gemm_tn: keep the CTA's B slice in shared memory when it fits
 
 static std::atomic<unsigned long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -191,6 +192,11 @@ template <int BN, int OP, int EF>
 static int launch_tn_ef(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& ep, int grid,
                         cudaStream_t stream) {
   using Cfg = GemmTnCfg<BN>;
+  // B-resident mode: every k-block of the CTA's B slice fits next to an A ring, and there is more than one row block
+  const int num_kb = (K + (OP == OP_F16_K ? 64 : 32) - 1) / (OP == OP_F16_K ? 64 : 32);
+  const int tiles_m = (M + Cfg::BM - 1) / Cfg::BM, tiles_n = N / BN;
+  const int b_res = (g_b_resident != 0 && BN >= 128 && size_t(num_kb) * Cfg::B_BYTES <= size_t(Cfg::RES_B_BYTES) &&
+                     tiles_m >= 2 * (grid / tiles_n)) ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
     RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, OP, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -198,7 +204,7 @@ static int launch_tn_ef(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, i
     attr_set = true;
   }
   time_begin(ep.tag, stream);
-  gemm_tn_kernel<BN, OP, EF><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+  gemm_tn_kernel<BN, OP, EF><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep, b_res);
   time_end(ep.tag, stream);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
@@ -523,12 +529,14 @@ int rlt_set_option(const char* key, int value) {
   if (strcmp(key, "lstm_backend") == 0) { set_lstm_backend(value); return RLT_OK; }
   if (strcmp(key, "gemm_backend") == 0) { g_gemm_backend = value; return RLT_OK; }
   if (strcmp(key, "tma_round") == 0) { g_tma_round = value; return RLT_OK; }
+  if (strcmp(key, "b_resident") == 0) { g_b_resident = value; return RLT_OK; }
   return set_error(RLT_INVALID_ARG, "rlt_set_option: unknown option '%s'", key);
 }
 int rlt_get_option(const char* key) {
   if (key == nullptr) return set_error(RLT_INVALID_ARG, "rlt_get_option: null key");
   if (strcmp(key, "gemm_backend") == 0) return g_gemm_backend;
   if (strcmp(key, "tma_round") == 0) return g_tma_round;
+  if (strcmp(key, "b_resident") == 0) return g_b_resident;
   if (strcmp(key, "time_tag") == 0) return g_time_tag;
   if (strcmp(key, "lstm_backend") == 0) return lstm_backend();
   return set_error(RLT_INVALID_ARG, "rlt_get_option: unknown option '%s'", key);

@@ -65,6 +65,9 @@ struct GemmTnCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int RES_B_BYTES = BN >= 128 ? 128 * 1024 : 0;   // B-resident mode (BN >= 128): the CTA's whole B slice ...
+  static constexpr int RES_STAGES = BN >= 128 ? (STAGES * STAGE_BYTES - RES_B_BYTES) / A_BYTES : 1;   // ... and an A-only ring
+  static_assert(BN < 128 || RES_STAGES >= 4, "A ring of the B-resident mode");
   static constexpr int EPI_WARPS = 8;               // two warps per TMEM lane quarter (even / odd 32-column chunks)
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // one 32x32 fp32 chunk per epilogue warp
@@ -139,7 +142,7 @@ __device__ __forceinline__ void epilogue_fetch_aux(const EpiParams& ep, EpiAux& 
 template <int EF>
 __device__ __forceinline__ void epilogue_store_chunk(const EpiParams& ep, float (&v)[32], const EpiAux& aux, uint8_t* stage,
                                                      int row0, int M, int col0, int lane,
-                                                     float* s_colsum /* [32] of this chunk */) {
+                                                     float* s_colsum /* [32] of this chunk */, float alpha, float4 bias) {
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4)
     *reinterpret_cast<float4*>(stage + lane * 128 + (((j4 ^ lane) & 7) << 4)) =
@@ -148,10 +151,6 @@ __device__ __forceinline__ void epilogue_store_chunk(const EpiParams& ep, float 
   const int cu = lane & 7;          // 16-byte unit (4 columns) inside the 128-byte row segment
   const int rsub = lane >> 3;       // row inside a group of 4
   const int col = col0 + cu * 4;
-  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ef_bias<EF>(ep)) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-  float alpha = ep.alpha;
-  if (ef_scale<EF>(ep)) alpha *= ep.scale_ptr[ep.scale_mode == 1 ? 0 : 1];
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   // which optional operand travelled through aux (same priority as epi_aux_src)
   const bool gate_in_aux = ef_gate<EF>(ep) || ef_gate_h<EF>(ep);
@@ -220,7 +219,7 @@ enum : int { OP_TF32_K = 0, OP_TF32_N = 1, OP_F16_K = 2 };
 template <int BN, int OP, int EF>
 __global__ void __launch_bounds__(GemmTnCfg<BN>::THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-               int K, EpiParams ep) {
+               int K, EpiParams ep, int b_res) {
   using Cfg = GemmTnCfg<BN>;
   constexpr bool kBMajorN = OP == OP_TF32_N;
   constexpr bool kF16 = OP == OP_F16_K;
@@ -234,7 +233,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty = bars + Cfg::STAGES;
   uint64_t* tfull = bars + 2 * Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* bres = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
+  // b_res (B-resident mode, chosen by the host when all k-blocks of the CTA's B slice fit in RES_B_BYTES): the slice is
+  // loaded ONCE - the column-stationary schedule never changes it - and only A streams through a ring of RES_STAGES
+  // stages behind it.  For the K = 128 GEMMs (FFN1, dH, QKV) this removes 2/3 of the L2 -> SM operand traffic.
+  uint8_t* a_ring = smem + Cfg::RES_B_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -255,6 +259,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tma_prefetch_desc(&tmB);
       for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], Cfg::EPI_WARPS); }
+      mbar_init(bres, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -270,20 +275,42 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       uint32_t it = 0;
-      for (int mt = m_first; mt < tiles_m; mt += m_step) {
-        const int m0 = mt * Cfg::BM;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const uint32_t s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-          uint8_t* sa = smem + size_t(s) * Cfg::STAGE_BYTES;
-          tma_load_2d(sa, &tmA, &full[s], kb * BKE, m0);
+      if (b_res) {
+        mbar_expect_tx(bres, uint32_t(num_kb) * Cfg::B_BYTES);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          uint8_t* sb = smem + size_t(kb) * Cfg::B_BYTES;
           if constexpr (!kBMajorN) {
-            tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], kb * BKE, n0);
+            tma_load_2d(sb, &tmB, bres, kb * BKE, n0);
           } else {
 #pragma unroll
-            for (int b = 0; b < BN / 32; ++b)
-              tma_load_2d(sa + Cfg::A_BYTES + b * 4096, &tmB, &full[s], n0 + b * 32, kb * BKE);
+            for (int b = 0; b < BN / 32; ++b) tma_load_2d(sb + b * 4096, &tmB, bres, n0 + b * 32, kb * BKE);
+          }
+        }
+        for (int mt = m_first; mt < tiles_m; mt += m_step) {
+          const int m0 = mt * Cfg::BM;
+          for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const uint32_t s = it % Cfg::RES_STAGES, ph = (it / Cfg::RES_STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], Cfg::A_BYTES);
+            tma_load_2d(a_ring + size_t(s) * Cfg::A_BYTES, &tmA, &full[s], kb * BKE, m0);
+          }
+        }
+      } else {
+        for (int mt = m_first; mt < tiles_m; mt += m_step) {
+          const int m0 = mt * Cfg::BM;
+          for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const uint32_t s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+            uint8_t* sa = smem + size_t(s) * Cfg::STAGE_BYTES;
+            tma_load_2d(sa, &tmA, &full[s], kb * BKE, m0);
+            if constexpr (!kBMajorN) {
+              tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], kb * BKE, n0);
+            } else {
+#pragma unroll
+              for (int b = 0; b < BN / 32; ++b)
+                tma_load_2d(sa + Cfg::A_BYTES + b * 4096, &tmB, &full[s], n0 + b * 32, kb * BKE);
+            }
           }
         }
       }
@@ -293,19 +320,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kF16 ? kFmtF16 : kFmtTF32, Cfg::BM, BN, false, kBMajorN);
       uint32_t it = 0, lt = 0;
+      if (b_res) mbar_wait(bres, 0);
       for (int mt = m_first; mt < tiles_m; mt += m_step, ++lt) {
         const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
         mbar_wait(&tempty[buf], bph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const uint32_t s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
+          const uint32_t nst = b_res ? Cfg::RES_STAGES : Cfg::STAGES;
+          const uint32_t s = it % nst, ph = (it / nst) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + size_t(s) * Cfg::STAGE_BYTES);
+          const uint32_t a_addr = b_res ? smem_u32(a_ring + size_t(s) * Cfg::A_BYTES) : smem_u32(smem + size_t(s) * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = b_res ? smem_u32(smem + size_t(kb) * Cfg::B_BYTES) : a_addr + Cfg::A_BYTES;
           const uint64_t da = make_smem_desc_sw128(a_addr, 16, 1024);
-          const uint64_t db = kBMajorN ? make_smem_desc_sw128(a_addr + Cfg::A_BYTES, 4096, 512, kLayoutSw128Base32)
-                                       : make_smem_desc_sw128(a_addr + Cfg::A_BYTES, 16, 1024);
+          const uint64_t db = kBMajorN ? make_smem_desc_sw128(b_addr, 4096, 512, kLayoutSw128Base32)
+                                       : make_smem_desc_sw128(b_addr, 16, 1024);
           // per MMA (K = 8): A advances 32 B inside its 128 B row (+2); a K-major B likewise, an
           // MN-major B advances 8 k-rows = 1024 B (+64)
           constexpr uint64_t kBStep = kBMajorN ? 64 : 2;
@@ -326,6 +356,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int kColSplit = Cfg::EPI_WARPS / 4;       // warps sharing a lane quarter interleave the 32-column chunks
     const int csub = ew >> 2;
     uint8_t* stage = epi_stage + ew * Cfg::EPI_STAGE_BYTES;
+    // result scale: the host value times the device-side power-of-two factor (read once, not per chunk)
+    float alpha = ep.alpha;
+    if (ef_scale<EF>(ep)) alpha *= ep.scale_ptr[ep.scale_mode == 1 ? 0 : 1];
+    // result scale: the host value times the device-side power-of-two factor (read once, not per chunk)
+    float alpha = ep.alpha;
+    if (ef_scale<EF>(ep)) alpha *= ep.scale_ptr[ep.scale_mode == 1 ? 0 : 1];
     uint32_t lt = 0;
     for (int mt = m_first; mt < tiles_m; mt += m_step, ++lt) {
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
@@ -337,12 +373,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
 #pragma unroll 1
       for (int c = csub; c < BN / 32; c += kColSplit) {
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);   // this lane's 4 columns; in flight during the TMEM read
+        if (ef_bias<EF>(ep)) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c * 32 + (lane & 7) * 4));
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);   // this lane's 4 columns; in flight during the TMEM read
+        if (ef_bias<EF>(ep)) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c * 32 + (lane & 7) * 4));
         float v[32];
         tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN + c * 32, v);
         const EpiAux cur = aux;
         if (c + kColSplit < BN / 32)   // next chunk's operands: in flight during this chunk's stores
           epilogue_fetch_aux<EF>(ep, aux, m0 + quarter * 32, M, n0 + (c + kColSplit) * 32, lane);
-        epilogue_store_chunk<EF>(ep, v, cur, stage, m0 + quarter * 32, M, n0 + c * 32, lane, s_colsum + c * 32);
+        epilogue_store_chunk<EF>(ep, v, cur, stage, m0 + quarter * 32, M, n0 + c * 32, lane, s_colsum + c * 32, alpha, bias);
       }
       tc_fence_before();
       __syncwarp();
