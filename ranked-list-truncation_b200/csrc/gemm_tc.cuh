@@ -359,9 +359,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // result scale: the host value times the device-side power-of-two factor (read once, not per chunk)
     float alpha = ep.alpha;
     if (ef_scale<EF>(ep)) alpha *= ep.scale_ptr[ep.scale_mode == 1 ? 0 : 1];
-    // result scale: the host value times the device-side power-of-two factor (read once, not per chunk)
-    float alpha = ep.alpha;
-    if (ef_scale<EF>(ep)) alpha *= ep.scale_ptr[ep.scale_mode == 1 ? 0 : 1];
     uint32_t lt = 0;
     for (int mt = m_first; mt < tiles_m; mt += m_step, ++lt) {
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
@@ -373,8 +370,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
 #pragma unroll 1
       for (int c = csub; c < BN / 32; c += kColSplit) {
-        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);   // this lane's 4 columns; in flight during the TMEM read
-        if (ef_bias<EF>(ep)) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c * 32 + (lane & 7) * 4));
         float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);   // this lane's 4 columns; in flight during the TMEM read
         if (ef_bias<EF>(ep)) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c * 32 + (lane & 7) * 4));
         float v[32];
