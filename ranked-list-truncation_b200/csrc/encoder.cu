@@ -547,7 +547,7 @@ static SavedLayout saved_layout(const rlt_encoder_desc& e) {
   s.st2 = take(T * 2);
   s.lse = take(T * e.n_head);
   s.y16 = take(T * d / 2);      // fp16 copy of y (operand of the dW1 contraction)
-  s.wh = take(d * f);           // fp16 copies of the FFN weights: W2 [d, f] and W1^T [d, f]
+  s.wh = take(2 * d * f);       // fp16 copies of the FFN weights: W2 [d, f], W1^T [d, f], W1 [f, d], W2^T [f, d]
   s.total = off;
   return s;
 }
@@ -624,10 +624,21 @@ int rlt_encoder_layer_fwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   __half* w1th = w2h + size_t(d) * f;
   RLT_TRY(layer_norm_fwd(sv + sl.u1, w->norm1_w, w->norm1_b, sv + sl.y, sv + sl.st1, T, d, e->ln_eps, stream,
                          h16 ? y16 : nullptr));
+  __half* w1h = w1th + size_t(d) * f;
+  __half* w2th = w1h + size_t(d) * f;
   // h = relu(y W1^T + b1)
   ep = EpiParams{}; ep.alpha = 1.f; ep.ldo = f; ep.bias = w->lin1_b; ep.relu = 1; ep.tag = TAG_FFN1;
-  if (h16) ep.out_h = hh; else ep.out = sv + sl.h;
-  RLT_TRY(gemm_tn(sv + sl.y, d, w->lin1_w, d, T, f, d, ep, stream));
+  if (h16) {
+    // fp16 operands (y16 is written by LN1, W1 is copied once per call): half the shared-memory operand traffic of
+    // the TF32 form - the store-bound K = 128 GEMM is limited by the SM's shared-memory pipe, not by the tensor core
+    ep.out_h = hh;
+    RLT_TRY(convert_f16(w->lin1_w, w1h, size_t(d) * f, nullptr, stream));
+    RLT_TRY(transpose_f16(w->lin2_w, w2th, d, f, stream));                     // [d, f] -> [f, d] (backward dH)
+    RLT_TRY(gemm_tn_h(y16, d, w1h, d, T, f, d, ep, stream));
+  } else {
+    ep.out = sv + sl.h;
+    RLT_TRY(gemm_tn(sv + sl.y, d, w->lin1_w, d, T, f, d, ep, stream));
+  }
   // u2 = y + h W2^T + b2 ; out = LN2(u2)
   ep = EpiParams{}; ep.alpha = 1.f; ep.out = sv + sl.u2; ep.ldo = d; ep.bias = w->lin2_b; ep.residual = sv + sl.y; ep.tag = TAG_FFN2;
   if (h16) {
@@ -673,11 +684,12 @@ int rlt_encoder_layer_bwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
     RLT_TRY(convert_f16(d_u, du16, size_t(T) * d, scale, stream));
     // dW2 += dU2^T h
     RLT_TRY(gemm_dw_h(du16, d, hh, f, T, d, f, gw->lin2_w, f, 1.f, scale + 1, stream, TAG_DW_FFN2));
-    // dHpre = s * (dU2 W2) * (h > 0) -> fp16 ; db1 += colsum(dHpre) / s
+    // dHpre = ((s dU2) W2) * (h > 0) -> fp16 (the scale rides on the fp16 operand) ; db1 += colsum(dHpre) / s
+    const __half* w2th = w1th + 2 * size_t(d) * f;
     EpiParams ep{};
     ep.alpha = 1.f; ep.out_h = dh16; ep.ldo = f; ep.gate_h = hh; ep.colsum = gw->lin1_b; ep.scale_ptr = scale;
-    ep.scale_mode = 1; ep.tag = TAG_D_FFN2;
-    RLT_TRY(gemm_nn(d_u, d, w->lin2_w, f, T, f, d, ep, stream));
+    ep.scale_mode = 3; ep.tag = TAG_D_FFN2;
+    RLT_TRY(gemm_tn_h(du16, d, w2th, d, T, f, d, ep, stream));
     // dW1 += dHpre^T y
     RLT_TRY(gemm_dw_h(dh16, f, y16, d, T, f, d, gw->lin1_w, d, 1.f, scale + 1, stream, TAG_DW_FFN1));
     // dY = dU2 + (dHpre W1) / s

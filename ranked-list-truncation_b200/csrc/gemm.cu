@@ -155,7 +155,7 @@ __global__ void gemm_tn_simt_kernel(const float* __restrict__ A, int lda, const 
       const int r = m0 + ty * 4 + i, c = n0 + tx * 4 + j;
       if (r >= M || c >= N) continue;
       float alpha = ep.alpha;
-      if (ep.scale_mode) alpha *= ep.scale_ptr[ep.scale_mode == 1 ? 0 : 1];
+      if (ep.scale_mode == 1 || ep.scale_mode == 2) alpha *= ep.scale_ptr[ep.scale_mode == 1 ? 0 : 1];
       float v = acc[i][j] * alpha;
       if (ep.bias) v += ep.bias[c];
       if (ep.relu) v = fmaxf(v, 0.f);
@@ -169,7 +169,7 @@ __global__ void gemm_tn_simt_kernel(const float* __restrict__ A, int lda, const 
         if (ep.accumulate) v += ep.out[off];
         ep.out[off] = v;
       }
-      if (ep.colsum) atomicAdd(ep.colsum + c, ep.scale_mode == 1 ? v * ep.scale_ptr[1] : v);
+      if (ep.colsum) atomicAdd(ep.colsum + c, (ep.scale_mode == 1 || ep.scale_mode == 3) ? v * ep.scale_ptr[1] : v);
     }
 }
 

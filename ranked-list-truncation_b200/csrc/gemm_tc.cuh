@@ -36,6 +36,7 @@ struct EpiParams {
   // device-side power-of-two scale {s, 1/s} (gradients are ~1e-6: fp16 needs them scaled into its normal range):
   //   scale_mode 1: result *= s and the column sums are multiplied by 1/s (they stay unscaled)
   //   scale_mode 2: result *= 1/s (unscale a contraction over scaled operands)
+  //   scale_mode 3: the result is left as it is (an operand already carries s); column sums are multiplied by 1/s
   const float* scale_ptr;
   int scale_mode;
 };
@@ -358,7 +359,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* stage = epi_stage + ew * Cfg::EPI_STAGE_BYTES;
     // result scale: the host value times the device-side power-of-two factor (read once, not per chunk)
     float alpha = ep.alpha;
-    if (ef_scale<EF>(ep)) alpha *= ep.scale_ptr[ep.scale_mode == 1 ? 0 : 1];
+    if (ef_scale<EF>(ep) && ep.scale_mode != 3) alpha *= ep.scale_ptr[ep.scale_mode == 1 ? 0 : 1];
     uint32_t lt = 0;
     for (int mt = m_first; mt < tiles_m; mt += m_step, ++lt) {
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
@@ -386,7 +387,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (ef_colsum<EF>(ep)) {
       // all epilogue warps have added their partial column sums into s_colsum: one global atomic per column and CTA
       asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");
-      const float cscale = (ef_scale<EF>(ep) && ep.scale_mode == 1) ? ep.scale_ptr[1] : 1.f;
+      const float cscale = (ef_scale<EF>(ep) && ep.scale_mode != 2) ? ep.scale_ptr[1] : 1.f;
       for (int j = threadIdx.x - 64; j < BN; j += Cfg::EPI_WARPS * 32) atomicAdd(ep.colsum + n0 + j, s_colsum[j] * cscale);
     }
   }
