@@ -191,7 +191,7 @@ __global__ void gemm_dw_simt_kernel(const float* __restrict__ A, int lda, const 
 template <int BN, int OP, int EF>
 static int launch_tn_ef(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& ep, int grid,
                         cudaStream_t stream) {
-  using Cfg = GemmTnCfg<BN>;
+  using Cfg = GemmTnCfg<BN, OP>;
   // B-resident mode: every k-block of the CTA's B slice fits next to an A ring, and there is more than one row block
   const int num_kb = (K + (OP == OP_F16_K ? 64 : 32) - 1) / (OP == OP_F16_K ? 64 : 32);
   const int tiles_m = (M + Cfg::BM - 1) / Cfg::BM, tiles_n = N / BN;
@@ -213,7 +213,7 @@ static int launch_tn_ef(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, i
 template <int BN, int OP>
 static int launch_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const EpiParams& ep,
                      cudaStream_t stream) {
-  using Cfg = GemmTnCfg<BN>;
+  using Cfg = GemmTnCfg<BN, OP>;
   RLT_REQUIRE(ep.out != nullptr || ep.out_h != nullptr, RLT_INVALID_ARG, "gemm: null output");
   RLT_REQUIRE(ep.scale_mode == 0 || ep.scale_ptr != nullptr, RLT_INVALID_ARG, "gemm: scale_mode without scale_ptr");
   CUtensorMap tmA, tmB;

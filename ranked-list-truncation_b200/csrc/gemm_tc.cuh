@@ -57,23 +57,34 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int BN>
+// Operand kinds (template parameter OP):
+//   OP_TF32_K : A [M, K] fp32, B [N, K] fp32 row-major (K-major operands, nn.Linear weight used as-is: x W^T)
+//   OP_TF32_N : A [M, K] fp32, B [K, N] fp32 row-major (MN-major B: x W with W stored [K, N])
+//   OP_F16_K  : A [M, K] fp16, B [N, K] fp16 (K-major, kind::f16: 64 elements per 128-byte swizzle row)
+enum : int { OP_TF32_K = 0, OP_TF32_N = 1, OP_F16_K = 2 };
+
+template <int BN, int OP>
 struct GemmTnCfg {
   static constexpr int BM = 128;
-  static constexpr int BK = 32;  // 32 tf32 = 128 B = one swizzle row
+  static constexpr int BK = 32;  // 32 tf32 = 128 B = one swizzle row (64 fp16)
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  // The epilogue of these store-bound GEMMs is a latency chain per warp (TMEM read -> smem transpose -> global), so
+  // the fp16-operand kernels (FFN hidden path) trade one pipeline stage for 16 epilogue warps instead of 8.
+  static constexpr int EPI_WARPS = (OP == OP_F16_K && BN >= 128) ? 16 : 8;   // warps per TMEM lane quarter: 4 or 2
+  static constexpr int STAGES = (BN >= 256) ? (EPI_WARPS == 16 ? 3 : 4) : (BN >= 128 ? (EPI_WARPS == 16 ? 5 : 6) : 8);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int RES_B_BYTES = BN >= 128 ? 128 * 1024 : 0;   // B-resident mode (BN >= 128): the CTA's whole B slice ...
+  static constexpr int RES_B_BYTES = BN < 128 ? 0 : (EPI_WARPS == 16 ? 64 * 1024 : 128 * 1024);   // B-resident mode: the CTA's B slice ...
   static constexpr int RES_STAGES = BN >= 128 ? (STAGES * STAGE_BYTES - RES_B_BYTES) / A_BYTES : 1;   // ... and an A-only ring
   static_assert(BN < 128 || RES_STAGES >= 4, "A ring of the B-resident mode");
-  static constexpr int EPI_WARPS = 8;               // two warps per TMEM lane quarter (even / odd 32-column chunks)
+  static constexpr int NBAR = STAGES > RES_STAGES ? STAGES : RES_STAGES;   // full / empty barrier pairs
+  static_assert(2 * NBAR + 6 <= 31, "barrier block");
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // one 32x32 fp32 chunk per epilogue warp
   static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + size_t(STAGES) * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES +
                                        BN * 4 /*column sums*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 // Epilogue feature mask (template parameter EF of the kernels): call sites with a known combination get a kernel in
@@ -210,18 +221,13 @@ __device__ __forceinline__ void epilogue_store_chunk(const EpiParams& ep, float 
   __syncwarp();   // the staging buffer is rewritten by the next chunk
 }
 
-// Operand kinds (template parameter OP):
-//   OP_TF32_K : A [M, K] fp32, B [N, K] fp32 row-major (K-major operands, nn.Linear weight used as-is: x W^T)
-//   OP_TF32_N : A [M, K] fp32, B [K, N] fp32 row-major (MN-major B: x W with W stored [K, N])
-//   OP_F16_K  : A [M, K] fp16, B [N, K] fp16 (K-major, kind::f16: 64 elements per 128-byte swizzle row)
-enum : int { OP_TF32_K = 0, OP_TF32_N = 1, OP_F16_K = 2 };
 // MN-major B: its stage is
 //                   BN/32 boxes of 32 k-rows x 32 columns in the SWIZZLE_128B_BASE32B layout.
 template <int BN, int OP, int EF>
-__global__ void __launch_bounds__(GemmTnCfg<BN>::THREADS, 1)
+__global__ void __launch_bounds__(GemmTnCfg<BN, OP>::THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                int K, EpiParams ep, int b_res) {
-  using Cfg = GemmTnCfg<BN>;
+  using Cfg = GemmTnCfg<BN, OP>;
   constexpr bool kBMajorN = OP == OP_TF32_N;
   constexpr bool kF16 = OP == OP_F16_K;
   constexpr int BKE = kF16 ? 64 : 32;     // elements per k-block (always 128 bytes)
@@ -231,8 +237,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* s_colsum = reinterpret_cast<float*>(epi_stage + Cfg::EPI_WARPS * Cfg::EPI_STAGE_BYTES);   // [BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_colsum + BN);
   uint64_t* full = bars;
-  uint64_t* empty = bars + Cfg::STAGES;
-  uint64_t* tfull = bars + 2 * Cfg::STAGES;
+  uint64_t* empty = bars + Cfg::NBAR;
+  uint64_t* tfull = bars + 2 * Cfg::NBAR;
   uint64_t* tempty = tfull + 2;
   uint64_t* bres = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
@@ -258,7 +264,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
-      for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < Cfg::NBAR; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], Cfg::EPI_WARPS); }
       mbar_init(bres, 1);
       fence_mbar_init();
