@@ -63,7 +63,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="choopy")
     ap.add_argument("--groups", type=int, default=64, help="attention groups (of 64 lists) per GPU per step")
-    ap.add_argument("--time-tag", type=int, default=3, help="kernel class timed in situ for the roofline (3 = FFN1 GEMM)")
+    ap.add_argument("--time-tag", type=int, default=-1,
+                    help="call site timed in situ for the roofline (-1 = all tagged sites, the largest is reported)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -204,7 +205,6 @@ def main():
     _lib.set_option("time_tag", 0)
     tot_ms, cnt = ctypes.c_double(0), ctypes.c_int(0)
     _lib.check(lib.rlt_timing_read(ctypes.byref(tot_ms), ctypes.byref(cnt)), "rlt_timing_read")
-    lib.rlt_timing_reset()
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -258,25 +258,52 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---------------- roofline of the kernel timed in situ
+    # ---------------- roofline of the dominant kernel, timed in situ (CUDA events on the launch stream)
     hbm, tf_burst, tf_sust, src = measured_peaks()
     T = B * SEQ_LEN
-    d, dff = eng.d, 2048
-    roof = None
-    if cnt.value > 0:
-        avg_s = tot_ms.value / cnt.value * 1e-3
-        if args.time_tag == 3:      # FFN1 GEMM: reads y [T,d] + W1 + b1, writes relu(h) [T,dff] — HBM(write)-bound unfused
-            bytes_ = T * (d + dff) * 4 + dff * d * 4 + dff * 4
-            roof = {"kernel": "gemm_tn_kernel<256> (encoder FFN1: relu(y W1^T + b1), TF32 tcgen05)", "bound": "hbm",
-                    "achieved": bytes_ / avg_s / 1e9, "peak": hbm, "unit": "GB/s", "traffic": None,
-                    "tensor_tflops": 2.0 * T * d * dff / avg_s / 1e12}
-        else:
-            roof = {"kernel": f"tag {args.time_tag}", "bound": "hbm", "achieved": None, "peak": hbm, "unit": "GB/s",
-                    "traffic": None}
-        if roof.get("achieved"):
-            roof["frac"] = roof["achieved"] / roof["peak"]
-        roof.update({"peak_source": src, "avg_launch_ms": avg_s * 1e3, "launches_timed": cnt.value,
-                     "share_of_step": tot_ms.value / ms})
+    d, dff, nh = eng.d, 2048, getattr(eng, "n_head", 8)
+    # algorithmic HBM bytes per launch of every tagged call site (T tokens per launch)
+    site_bytes = {
+        1: ("QKV projection (gemm_tn, TF32)", T * (d + 3 * d) * 4 + 3 * d * d * 4),
+        2: ("attention out-projection + residual (gemm_tn, TF32)", T * 3 * d * 4 + d * d * 4),
+        3: ("FFN1: h = relu(y W1^T + b1), fp16 operands -> fp16 hidden (gemm_tn, tcgen05 kind::f16)", T * (d + dff) * 2 + dff * d * 2),
+        4: ("FFN2: u2 = y + h W2^T + b2, fp16 hidden (gemm_tn, kind::f16)", T * dff * 2 + T * 2 * d * 4 + dff * d * 2),
+        5: ("dH = s (dU2 W2) [h > 0], fp16 in / fp16 out + bias-gradient column sums (gemm_tn, kind::f16)",
+            T * d * 2 + T * 2 * dff * 2 + dff * d * 2),
+        6: ("dY = dU2 + dH W1 / s (gemm_tn, kind::f16)", T * dff * 2 + T * 2 * d * 4 + dff * d * 2),
+        7: ("dW2 += dU2^T h (gemm_dw, kind::f16, MN-major operands)", T * (d + dff) * 2),
+        8: ("dW1 += dH^T y (gemm_dw, kind::f16, MN-major operands)", T * (d + dff) * 2),
+        9: ("cross-list attention forward (mma.sync TF32, cp.async pipeline)", T * (3 * d + d + nh) * 4),
+        10: ("cross-list attention backward (mma.sync TF32, cp.async pipeline)", T * (3 * d + d + nh + 3 * d) * 4),
+        12: ("BiLSTM recurrence (tcgen05 kind::f16, unit-major)", T * (1024 + 2 * 6 * 128 + 256) * 4),
+    }
+    roof, kernels = None, {}
+    if args.time_tag == -1:
+        for tag, (label, nbytes) in site_bytes.items():
+            tm, tc = ctypes.c_double(0), ctypes.c_int(0)
+            _lib.check(lib.rlt_timing_read_tag(tag, ctypes.byref(tm), ctypes.byref(tc)), "rlt_timing_read_tag")
+            if tc.value:
+                kernels[tag] = {"site": label, "launches": tc.value, "avg_launch_ms": tm.value / tc.value,
+                                "share_of_step": tm.value / ms, "gbs": nbytes / (tm.value / tc.value * 1e-3) / 1e9}
+        top = max(kernels, key=lambda k: kernels[k]["share_of_step"]) if kernels else None
+    else:
+        top = args.time_tag if cnt.value > 0 and args.time_tag in site_bytes else None
+        if top is not None:
+            kernels[top] = {"site": site_bytes[top][0], "launches": cnt.value, "avg_launch_ms": tot_ms.value / cnt.value,
+                            "share_of_step": tot_ms.value / ms,
+                            "gbs": site_bytes[top][1] / (tot_ms.value / cnt.value * 1e-3) / 1e9}
+    lib.rlt_timing_reset()
+    if top is not None:
+        k = kernels[top]
+        traffic = None
+        tp = ROOT / "profiles" / "ncu_traffic.json"      # dram bytes per token of one launch, from `ncu --set full`
+        if tp.exists():
+            per_tok = json.loads(tp.read_text()).get(str(top), {}).get("dram_bytes_per_token")
+            traffic = per_tok * T if per_tok else None
+        roof = {"kernel": k["site"], "bound": "hbm", "achieved": k["gbs"], "peak": hbm, "unit": "GB/s",
+                "frac": k["gbs"] / hbm, "traffic": traffic, "algorithmic_bytes_per_launch": site_bytes[top][1],
+                "peak_source": src + " (STREAM-style copy, MEASURED_PEAKS.json)" if src == "measured" else src,
+                "avg_launch_ms": k["avg_launch_ms"], "launches_timed": k["launches"], "share_of_step": k["share_of_step"]}
 
     # ---------------- CPU baseline on this box's host cores (bounded sample)
     cpu = None
@@ -292,7 +319,7 @@ def main():
 
     line = {"metric": METRIC, "value": train_lps, "unit": "lists/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "tf32 / fp16 operands (11-bit significand), fp32 accumulate, fp32 master tensors", "data": "synthetic",
             "config": {"workload": f"{args.model} train step (fwd + {CRITERION[args.model]} + bwd{' + NCCL grad all-reduce' if world > 1 else ''}), "
                                    f"{DATASET_LISTS} synthetic robust04-shaped lists x {SEQ_LEN} resident in HBM",
                        "lists_per_step_per_gpu": B, "attention_group": GROUP, "seq_len": SEQ_LEN,
@@ -302,6 +329,8 @@ def main():
             "e2e": {"value": e2e_lps, "unit": "lists/s", "h2d_bytes_per_step": int(hx.numel() * 4 + hy.numel() * 4),
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "loss": loss_val, "clocks": sampler.summary(), "roofline": roof,
+            "kernels": {str(k): {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()}
+                        for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["share_of_step"])},
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:

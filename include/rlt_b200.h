@@ -56,6 +56,8 @@ unsigned long long rlt_launch_count(void);
  * matching launches are bracketed by CUDA events on their stream.  rlt_timing_read sums them. */
 int rlt_timing_reset(void);
 int rlt_timing_read(double* total_ms, int* count);
+/* With time_tag = -1 every tagged call site is bracketed; this reads the sum for one site. */
+int rlt_timing_read_tag(int tag, double* total_ms, int* count);
 
 /* ------------------------------------------------------------------------------------------ */
 /* building blocks exported for tests and probes                                              */

@@ -46,13 +46,16 @@ void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static int g_time_tag = 0;
 static std::mutex g_time_mu;
 static std::vector<cudaEvent_t> g_time_events;  // begin/end pairs
+static std::vector<int> g_time_tags;            // tag of every event
+// time_tag option: 0 = off, t > 0 = bracket the launches of call site t, -1 = bracket every tagged call site
 void time_begin(int tag, cudaStream_t stream) {
-  if (tag == 0 || tag != g_time_tag) return;
+  if (tag == 0 || (tag != g_time_tag && g_time_tag != -1)) return;
   cudaEvent_t e;
   if (cudaEventCreate(&e) != cudaSuccess) return;
   cudaEventRecord(e, stream);
   std::lock_guard<std::mutex> lk(g_time_mu);
   g_time_events.push_back(e);
+  g_time_tags.push_back(tag);
 }
 void time_end(int tag, cudaStream_t stream) { time_begin(tag, stream); }
 
@@ -502,6 +505,7 @@ int rlt_timing_reset(void) {
   std::lock_guard<std::mutex> lk(g_time_mu);
   for (cudaEvent_t e : g_time_events) cudaEventDestroy(e);
   g_time_events.clear();
+  g_time_tags.clear();
   return RLT_OK;
 }
 
@@ -512,6 +516,25 @@ int rlt_timing_read(double* total_ms, int* count) {
   double tot = 0.0;
   int n = 0;
   for (size_t i = 0; i + 1 < g_time_events.size(); i += 2) {
+    RLT_CHECK_CUDA(cudaEventSynchronize(g_time_events[i + 1]));
+    float ms = 0.f;
+    RLT_CHECK_CUDA(cudaEventElapsedTime(&ms, g_time_events[i], g_time_events[i + 1]));
+    tot += ms;
+    ++n;
+  }
+  *total_ms = tot;
+  *count = n;
+  return RLT_OK;
+}
+
+/* Same for one call site (KernelTag) when every site was bracketed (time_tag = -1). */
+int rlt_timing_read_tag(int tag, double* total_ms, int* count) {
+  RLT_REQUIRE(total_ms && count, RLT_INVALID_ARG, "rlt_timing_read_tag: null pointer");
+  std::lock_guard<std::mutex> lk(g_time_mu);
+  double tot = 0.0;
+  int n = 0;
+  for (size_t i = 0; i + 1 < g_time_events.size(); i += 2) {
+    if (g_time_tags[i] != tag) continue;
     RLT_CHECK_CUDA(cudaEventSynchronize(g_time_events[i + 1]));
     float ms = 0.f;
     RLT_CHECK_CUDA(cudaEventElapsedTime(&ms, g_time_events[i], g_time_events[i + 1]));

@@ -32,6 +32,7 @@ class _EncStack:
     def __init__(self, eng, enc, accumulate_dx=False):
         l0 = enc.layers[0]
         self.d = l0.linear1.in_features
+        self.n_head = l0.self_attn.num_heads
         self.desc = ops.encoder_desc(eng.G, eng.S, eng.L, self.d, l0.self_attn.num_heads, l0.linear1.out_features,
                                      l0.norm1.eps)
         self.desc_first = ops.encoder_desc(eng.G, eng.S, eng.L, self.d, l0.self_attn.num_heads,
@@ -133,6 +134,7 @@ class Engine:
         else:
             self.stacks = []
         self.d = self.stacks[0].d if self.stacks else self.d_front
+        self.n_head = self.stacks[0].n_head if self.stacks else 0
         if training:
             if self.stacks:
                 self.enc_ws = torch.empty((ops.encoder_workspace_bytes(self.stacks[0].desc) + 3) // 4, **f32)
