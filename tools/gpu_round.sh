@@ -1,20 +1,21 @@
 #!/bin/bash
-# One GPU visit: parity tests, the default bench line (both arms), the ncu launch list of the same bench command and one
-# `--set full` capture of the kernel named in $1 (regex).  Outputs under gpurun_out/<tag>_*.
-TAG=${2:-r1}
-KREGEX=${1:-gemm_tn_kernel}
+# One GPU visit (1 GPU): parity tests, the default bench line (both arms), the ncu launch list of the same bench command
+# and `--set full` captures of the dominant kernels.  Outputs under gpurun_out/<tag>_*.   usage: gpu_round.sh <tag>
+TAG=${1:-r1}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_gpu_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_gpu_tests.log
 tail -3 gpurun_out/${TAG}_gpu_tests.log
-timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
-cat gpurun_out/${TAG}_bench.json
-timeout 600 python bench.py --impl reference > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
-cat gpurun_out/${TAG}_bench_ref.json
-# launch list of the same bench command (short: 2 steps, smaller batch to keep ncu serialisation bounded)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
-  python bench.py --steps 2 --warmup 1 --groups 16 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
-# full capture of the dominant kernel
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:${KREGEX}" -s 6 -c 3 -o gpurun_out/${TAG}_prof -f \
-  python bench.py --steps 1 --warmup 1 --groups 16 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
-ls -la gpurun_out | tail -12
+timeout 600 python bench.py --impl reference > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench.err
+timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2>> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+cat gpurun_out/${TAG}_bench_ref.json gpurun_out/${TAG}_bench.json | cut -c1-600
+B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
+# launch list of the same bench command (1 warm-up + 1 timed step, full batch)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${TAG}_launches.csv $B > gpurun_out/${TAG}_ncu_bench.log 2>&1
+# full captures: dH GEMM (13th gemm_tn launch of a step), FFN1 (3rd), attention backward / forward
+N="ncu --set full --clock-control none --import-source on"
+timeout 600 $N -k regex:gemm_tn_kernel -s 12 -c 1 -o gpurun_out/${TAG}_dh -f $B > gpurun_out/${TAG}_ncu_full.log 2>&1
+timeout 600 $N -k regex:gemm_tn_kernel -s 2 -c 1 -o gpurun_out/${TAG}_ffn1 -f $B >> gpurun_out/${TAG}_ncu_full.log 2>&1
+timeout 600 $N -k regex:attn_lists_bwd -s 1 -c 1 -o gpurun_out/${TAG}_attn_bwd -f $B >> gpurun_out/${TAG}_ncu_full.log 2>&1
+timeout 600 $N -k regex:attn_lists_fwd -s 1 -c 1 -o gpurun_out/${TAG}_attn_fwd -f $B >> gpurun_out/${TAG}_ncu_full.log 2>&1
+ls -la gpurun_out | tail -14
