@@ -81,6 +81,10 @@ int rlt_linear_f16(const void* A, const void* B, const float* bias, float* C, in
 int rlt_grad_weight_f16(const void* A, const void* B, float* C, int T, int M, int N, float alpha, rlt_stream_t stream);
 int rlt_linear_out_f16(const float* A, const float* B, const float* bias, void* C, int M, int N, int K, int relu,
                        rlt_stream_t stream);
+/* Test hook for train-mode dropout: out[i] = 0 or 1/(1-p) exactly as the kernels apply it at dropout site `site`
+ * (1 attention probabilities, index (item*S + query)*S + key with S = group_size; 2 after the attention block;
+ * 3 FFN hidden; 4 after the FFN; 5 BiCut logits; index = linear element index). */
+int rlt_dropout_mask(uint64_t seed, int site, float p, size_t n, int group_size, float* out, rlt_stream_t stream);
 /* out[c] += sum_t src[t, c]  (bias gradients). n_cols must be a multiple of 4. */
 int rlt_colsum(const float* src, float* out, int n_rows, int n_cols, rlt_stream_t stream);
 /* Probe: TMA-load a [rows<=128, 32] fp32 tile of src through a TFLOAT32 tensor map and copy the
@@ -105,7 +109,7 @@ typedef struct rlt_encoder_desc {
   int32_t attend_axis; /* 0 = across lists (reference); 1 = within a list (not implemented)          */
   int32_t accumulate_dx; /* backward: d_x += instead of d_x = (several experts share one input)       */
   float ln_eps;        /* 1e-5                                                                       */
-  float dropout_p;     /* must be 0 for now                                                          */
+  float dropout_p;     /* train-mode dropout probability (0 = eval / no dropout)                     */
   uint64_t dropout_seed;
 } rlt_encoder_desc;
 
@@ -226,8 +230,10 @@ int rlt_head_dots_fwd(const float* x /*[T,d]*/, const float* w /*[H,d]*/, const 
 int rlt_head_dots_bwd(const float* x, const float* w, const float* dz /*[H,T]*/, float* dx, float* dw, float* db,
                       int n_tokens, int d, int n_heads, int accumulate_dx, int relu_gate, rlt_stream_t stream);
 /* BiCut's nn.Softmax(dim=2) over the two classes: logit planes z [2, T] <-> probabilities o [T, 2]. */
-int rlt_pair_softmax_fwd(const float* z, float* o, size_t n_tokens, rlt_stream_t stream);
-int rlt_pair_softmax_bwd(const float* o, const float* d_o, float* dz, size_t n_tokens, rlt_stream_t stream);
+int rlt_pair_softmax_fwd(const float* z, float* o, size_t n_tokens, float dropout_p, uint64_t dropout_seed,
+                         rlt_stream_t stream);
+int rlt_pair_softmax_bwd(const float* o, const float* d_o, float* dz, size_t n_tokens, float dropout_p,
+                         uint64_t dropout_seed, rlt_stream_t stream);
 
 /* softmax over the L positions of every list (nn.Softmax(dim=1) of the cut heads) and its backward */
 int rlt_softmax_lists(const float* z, float* p, int n_lists, int seq_len, rlt_stream_t stream);

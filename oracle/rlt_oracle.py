@@ -312,8 +312,13 @@ def layer_norm(x: Tensor, g: Tensor, b: Tensor, eps: float = 1e-5) -> Tensor:
     return (x - mu) / torch.sqrt(var + eps) * g + b
 
 
-def encoder_layer(x: Tensor, sd: Dict[str, Tensor], prefix: str, n_head: int, attend: str = "lists") -> Tensor:
-    """nn.TransformerEncoderLayer (post-norm, ReLU, dim_feedforward=2048, eps=1e-5) in eval / p=0 mode.
+def encoder_layer(x: Tensor, sd: Dict[str, Tensor], prefix: str, n_head: int, attend: str = "lists",
+                  masks: Dict[str, Tensor] = None) -> Tensor:
+    """nn.TransformerEncoderLayer (post-norm, ReLU, dim_feedforward=2048, eps=1e-5).  Eval / p=0 mode by default;
+    `masks` (train mode) holds the keep-and-scale factors (0 or 1/(1-p)) of torch's four dropout sites
+    (torch/nn/modules/transformer.py::_sa_block/_ff_block, functional.multi_head_attention_forward):
+    'attn' [L, n_head, B, B] on the attention probabilities, 'after_attn' [B, L, d] (dropout1), 'ffn' [B, L, d_ff]
+    inside the feed-forward block, 'after_ffn' [B, L, d] (dropout2).
     The reference builds it WITHOUT batch_first and feeds [B, L, d] (models/Choopy.py:11,21 etc.), so the
     attention runs over dim 0 — across the B lists of the call — independently per position and head
     (attend='lists').  attend='positions' is the batch_first behaviour (attention within a list)."""
@@ -329,12 +334,20 @@ def encoder_layer(x: Tensor, sd: Dict[str, Tensor], prefix: str, n_head: int, at
 
     qh, kh, vh = heads(q), heads(k), heads(v)
     att = torch.softmax(qh @ kh.transpose(-1, -2) / math.sqrt(dh), dim=-1)
+    if masks is not None and "attn" in masks:
+        att = att * masks["attn"]
     oh = att @ vh
     o = (oh.permute(2, 0, 1, 3) if attend == "lists" else oh.permute(0, 2, 1, 3)).reshape(B, L, d)
     o = o @ sd[prefix + "self_attn.out_proj.weight"].t() + sd[prefix + "self_attn.out_proj.bias"]
+    if masks is not None and "after_attn" in masks:
+        o = o * masks["after_attn"]
     y = layer_norm(x + o, sd[prefix + "norm1.weight"], sd[prefix + "norm1.bias"])
     hdn = torch.relu(y @ sd[prefix + "linear1.weight"].t() + sd[prefix + "linear1.bias"])
+    if masks is not None and "ffn" in masks:
+        hdn = hdn * masks["ffn"]
     f = hdn @ sd[prefix + "linear2.weight"].t() + sd[prefix + "linear2.bias"]
+    if masks is not None and "after_ffn" in masks:
+        f = f * masks["after_ffn"]
     return layer_norm(y + f, sd[prefix + "norm2.weight"], sd[prefix + "norm2.bias"])
 
 

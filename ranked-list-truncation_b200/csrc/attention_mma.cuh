@@ -10,6 +10,7 @@
 // Backward recomputes P from the saved log-sum-exp (no S x S tensor in HBM): phase A per query tile (dQ),
 // phase B per key tile with the transposed products (dK, dV); no atomics.
 #pragma once
+#include "dropout.cuh"
 #include "sm100.cuh"
 
 namespace rlt {
@@ -333,7 +334,7 @@ __device__ __forceinline__ AttnItem attn_item(long long i, int S, int L, int n_h
 template <int DH, int NT>
 __global__ void __launch_bounds__(128) attn_lists_fwd_pipe_kernel(const float* __restrict__ qkv, float* __restrict__ o,
                                                                   float* __restrict__ lse, int S, int L, int d, int n_head,
-                                                                  float scale, long long n_items) {
+                                                                  float scale, long long n_items, DropCfg drop) {
   constexpr int P = DH + 4;
   constexpr int ROWS = NT * 8;
   constexpr int BUF = 3 * ROWS * P;
@@ -389,12 +390,21 @@ __global__ void __launch_bounds__(128) attn_lists_fwd_pipe_kernel(const float* _
       }
       s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
       s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      const int ra = r0 + gq, rb = r0 + gq + 8;
+      if (drop.thr) {   // dropout on the attention probabilities (the row sums above stay undropped)
+        const uint64_t ea = (uint64_t(item) * S + ra) * S, eb = (uint64_t(item) * S + rb) * S;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const uint64_t ba = drop_bits(drop.seed, DROP_ATTN, ea + j * 8 + 2 * t), bb = drop_bits(drop.seed, DROP_ATTN, eb + j * 8 + 2 * t);
+          acc[j][0] *= drop_factor(ba, 0, drop.thr, drop.scale); acc[j][1] *= drop_factor(ba, 1, drop.thr, drop.scale);
+          acc[j][2] *= drop_factor(bb, 0, drop.thr, drop.scale); acc[j][3] *= drop_factor(bb, 1, drop.thr, drop.scale);
+        }
+      }
       float oacc[DH / 8][4];
 #pragma unroll
       for (int n = 0; n < DH / 8; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
       tile_pB<DH, NT>(acc, sV, oacc, lane);
       const float i0 = 1.f / s0, i1 = 1.f / s1;
-      const int ra = r0 + gq, rb = r0 + gq + 8;
       if (ra < S) {
         float* op = o + (it.tok0 + size_t(ra) * L) * d + it.h * DH;
 #pragma unroll
@@ -420,7 +430,7 @@ template <int DH, int NT>
 __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* __restrict__ qkv, const float* __restrict__ lse,
                                                                   const float* __restrict__ d_o, float* __restrict__ dqkv,
                                                                   int S, int L, int d, int n_head, float scale,
-                                                                  long long n_items) {
+                                                                  long long n_items, DropCfg drop) {
   constexpr int P = DH + 4;
   constexpr int ROWS = NT * 8;
   constexpr int BUF = 4 * ROWS * P + ROWS;      // q, k, v, dO rows + lse
@@ -469,6 +479,15 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
       }
       tile_abT<DH, NT, true>(sQ, r0, sK, p, lane);
       tile_abT<DH, NT, false>(sG, r0, sV, dp, lane);
+      if (drop.thr) {   // d(attn) = mask/(1-p) * d(dropped attn)
+        const uint64_t ea = (uint64_t(item) * S + r0 + gq) * S, eb = (uint64_t(item) * S + r0 + gq + 8) * S;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const uint64_t ba = drop_bits(drop.seed, DROP_ATTN, ea + j * 8 + 2 * t), bb = drop_bits(drop.seed, DROP_ATTN, eb + j * 8 + 2 * t);
+          dp[j][0] *= drop_factor(ba, 0, drop.thr, drop.scale); dp[j][1] *= drop_factor(ba, 1, drop.thr, drop.scale);
+          dp[j][2] *= drop_factor(bb, 0, drop.thr, drop.scale); dp[j][3] *= drop_factor(bb, 1, drop.thr, drop.scale);
+        }
+      }
       const float la = sL[r0 + gq] * kLog2e, lb = sL[r0 + gq + 8] * kLog2e;
       float da = 0.f, db = 0.f;
 #pragma unroll
@@ -525,9 +544,18 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
         const float l0 = sL[i] * kLog2e, l1 = sL[i + 1] * kLog2e, d0 = sD[i], d1 = sD[i + 1];
         const float p0 = exp2f(fmaf(p[j][0], sc, -l0)), p1 = exp2f(fmaf(p[j][1], sc, -l1));
         const float p2 = exp2f(fmaf(p[j][2], sc, -l0)), p3 = exp2f(fmaf(p[j][3], sc, -l1));
-        p[j][0] = p0; p[j][1] = p1; p[j][2] = p2; p[j][3] = p3;              // P^T  (0 for padded queries: lse = +inf)
-        dp[j][0] = p0 * (dp[j][0] - d0); dp[j][1] = p1 * (dp[j][1] - d1);    // dS^T
-        dp[j][2] = p2 * (dp[j][2] - d0); dp[j][3] = p3 * (dp[j][3] - d1);
+        float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;   // dropout factors of (query i / i+1, key c0+gq / +8)
+        if (drop.thr) {
+          const int ka_ = c0 + gq, kb_ = c0 + gq + 8;
+          const uint64_t q0 = (uint64_t(item) * S + i) * S, q1 = (uint64_t(item) * S + i + 1) * S;
+          m0 = drop_factor(drop_bits(drop.seed, DROP_ATTN, q0 + (ka_ & ~1)), ka_ & 1, drop.thr, drop.scale);
+          m1 = drop_factor(drop_bits(drop.seed, DROP_ATTN, q1 + (ka_ & ~1)), ka_ & 1, drop.thr, drop.scale);
+          m2 = drop_factor(drop_bits(drop.seed, DROP_ATTN, q0 + (kb_ & ~1)), kb_ & 1, drop.thr, drop.scale);
+          m3 = drop_factor(drop_bits(drop.seed, DROP_ATTN, q1 + (kb_ & ~1)), kb_ & 1, drop.thr, drop.scale);
+        }
+        p[j][0] = p0 * m0; p[j][1] = p1 * m1; p[j][2] = p2 * m2; p[j][3] = p3 * m3;   // (dropped P)^T; 0 for padded queries
+        dp[j][0] = p0 * (dp[j][0] * m0 - d0); dp[j][1] = p1 * (dp[j][1] * m1 - d1);     // dS^T
+        dp[j][2] = p2 * (dp[j][2] * m2 - d0); dp[j][3] = p3 * (dp[j][3] * m3 - d1);
       }
       float ak[DH / 8][4], av[DH / 8][4];
 #pragma unroll

@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include "../../include/rlt_b200.h"
+#include "dropout.cuh"
 
 namespace rlt {
 
@@ -67,7 +68,10 @@ int gemm_tn_h(const __half* A, int lda, const __half* B, int ldb, int M, int N, 
 int gemm_dw_h(const __half* A, int lda, const __half* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
               const float* alpha_ptr, cudaStream_t stream, int tag = 0);
 // dst = half(src * scale[0]) (scale may be null); dst[c, r] = half(src[r, c])
-int convert_f16(const float* src, __half* dst, size_t n, const float* scale, cudaStream_t stream);
+int convert_f16(const float* src, __half* dst, size_t n, const float* scale, cudaStream_t stream,
+                DropCfg drop = DropCfg{0, 0, 1.f}, uint32_t site = 0);
+// dst = src * keep-and-scale factor of dropout site `site` (element index = linear index)
+int dropout_apply(const float* src, float* dst, size_t n, DropCfg drop, uint32_t site, cudaStream_t stream);
 int transpose_f16(const float* src, __half* dst, int rows, int cols, cudaStream_t stream);
 // scale = {2^k, 2^-k} with max|x| * 2^k in [2^(target-1), 2^target); amax_scratch: one device word
 int grad_scale(const float* x, size_t n, unsigned int* amax_scratch, float* scale, int target, cudaStream_t stream);

@@ -145,13 +145,18 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 
 // out[c] += sum_t src[t, c]   (C a multiple of 4)
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ src, float* __restrict__ out, int T,
-                                                     int C) {
+                                                     int C, DropCfg drop, uint32_t site) {
   // thread -> one float4 column group; rows strided over (blockIdx.y, threadIdx.y)
   const int c4 = blockIdx.x * 32 + threadIdx.x;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c4 * 4 < C) {
     for (int t = blockIdx.y * blockDim.y + threadIdx.y; t < T; t += gridDim.y * blockDim.y) {
-      const float4 v = *reinterpret_cast<const float4*>(src + size_t(t) * C + c4 * 4);
+      float4 v = *reinterpret_cast<const float4*>(src + size_t(t) * C + c4 * 4);
+      if (drop.thr) {   // column sums of the dropout-masked tensor (bias gradient of a Linear that sits inside a dropout)
+        const uint64_t bits = drop_bits(drop.seed, site, (size_t(t) * C + c4 * 4) >> 2);
+        v.x *= drop_factor(bits, 0, drop.thr, drop.scale); v.y *= drop_factor(bits, 1, drop.thr, drop.scale);
+        v.z *= drop_factor(bits, 2, drop.thr, drop.scale); v.w *= drop_factor(bits, 3, drop.thr, drop.scale);
+      }
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
@@ -168,13 +173,23 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ s
   }
 }
 
+int colsum_masked(const float* src, float* out, int T, int C, DropCfg drop, uint32_t site, cudaStream_t stream) {
+  RLT_REQUIRE(C % 4 == 0, RLT_UNSUPPORTED_SHAPE, "colsum: C=%d must be a multiple of 4", C);
+  int gy = (T + 8 * 64 - 1) / (8 * 64);
+  if (gy < 1) gy = 1;
+  const int maxy = num_sms() * 4;
+  if (gy > maxy) gy = maxy;
+  colsum_kernel<<<dim3((C / 4 + 31) / 32, gy), dim3(32, 8), 0, stream>>>(src, out, T, C, drop, site);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
 int colsum(const float* src, float* out, int T, int C, cudaStream_t stream) {
   RLT_REQUIRE(C % 4 == 0, RLT_UNSUPPORTED_SHAPE, "colsum: C=%d must be a multiple of 4", C);
   int gy = (T + 8 * 64 - 1) / (8 * 64);
   if (gy < 1) gy = 1;
   const int maxy = num_sms() * 4;
   if (gy > maxy) gy = maxy;
-  colsum_kernel<<<dim3((C / 4 + 31) / 32, gy), dim3(32, 8), 0, stream>>>(src, out, T, C);
+  colsum_kernel<<<dim3((C / 4 + 31) / 32, gy), dim3(32, 8), 0, stream>>>(src, out, T, C, DropCfg{0, 0, 1.f}, 0);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }
@@ -381,7 +396,7 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_kernel(const float* __rest
 // persistent pipelined kernels: as many CTAs as are co-resident (occupancy API), each walking items with stride gridDim.x
 template <int DH, int NT>
 static int attention_fwd_mma(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head, float scale,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, DropCfg drop) {
   const size_t smem = size_t(2) * 3 * NT * 8 * (DH + 4) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
@@ -397,14 +412,14 @@ static int attention_fwd_mma(const float* qkv, float* o, float* lse, int G, int 
   long long grid = (long long)num_sms() * per_sm;
   if (grid > n_items) grid = n_items;
   time_begin(TAG_ATTN_FWD, stream);
-  attn_lists_fwd_pipe_kernel<DH, NT><<<int(grid), 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, n_items);
+  attn_lists_fwd_pipe_kernel<DH, NT><<<int(grid), 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, n_items, drop);
   time_end(TAG_ATTN_FWD, stream);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }
 template <int DH, int NT>
 static int attention_bwd_mma(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int G,
-                             int S, int L, int d, int n_head, float scale, cudaStream_t stream) {
+                             int S, int L, int d, int n_head, float scale, cudaStream_t stream, DropCfg drop) {
   (void)o;   // D = rowsum(P * dP) is recomputed from the fragments; the attention output is not needed
   const size_t smem = (size_t(2) * (4 * NT * 8 * (DH + 4) + NT * 8) + NT * 8) * sizeof(float);
   static bool attr_set = false;
@@ -421,7 +436,7 @@ static int attention_bwd_mma(const float* qkv, const float* o, const float* lse,
   long long grid = (long long)num_sms() * per_sm;
   if (grid > n_items) grid = n_items;
   time_begin(TAG_ATTN_BWD, stream);
-  attn_lists_bwd_pipe_kernel<DH, NT><<<int(grid), 128, smem, stream>>>(qkv, lse, d_o, dqkv, S, L, d, n_head, scale, n_items);
+  attn_lists_bwd_pipe_kernel<DH, NT><<<int(grid), 128, smem, stream>>>(qkv, lse, d_o, dqkv, S, L, d, n_head, scale, n_items, drop);
   time_end(TAG_ATTN_BWD, stream);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
@@ -430,18 +445,19 @@ static int attention_bwd_mma(const float* qkv, const float* o, const float* lse,
 static bool attention_mma_ok(int S, int dh) { return gemm_backend() == 0 && S <= 128 && (dh == 16 || dh == 32 || dh == 64); }
 
 static int attention_fwd(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, DropCfg drop) {
   const int dh = d / n_head;
   const float scale = 1.0f / sqrtf(float(dh));
   if (attention_mma_ok(S, dh)) {
 #define RLT_AF(DH_)                                                                                            \
-  return S <= 64 ? attention_fwd_mma<DH_, 8>(qkv, o, lse, G, S, L, d, n_head, scale, stream)                  \
-                 : attention_fwd_mma<DH_, 16>(qkv, o, lse, G, S, L, d, n_head, scale, stream)
+  return S <= 64 ? attention_fwd_mma<DH_, 8>(qkv, o, lse, G, S, L, d, n_head, scale, stream, drop)            \
+                 : attention_fwd_mma<DH_, 16>(qkv, o, lse, G, S, L, d, n_head, scale, stream, drop)
     if (dh == 16) RLT_AF(16);
     if (dh == 32) RLT_AF(32);
     RLT_AF(64);
 #undef RLT_AF
   }
+  RLT_REQUIRE(drop.thr == 0, RLT_UNSUPPORTED_SHAPE, "attention: dropout needs the tensor-core path (S <= 128, head dim 16/32/64)");
   const dim3 grid(L, G, n_head);
   const size_t smem = size_t(2) * S * (dh + 1) * sizeof(float);
   RLT_REQUIRE(smem <= 200 * 1024, RLT_UNSUPPORTED_SHAPE, "attention: group of %d lists does not fit in shared memory", S);
@@ -464,13 +480,13 @@ static int attention_fwd(const float* qkv, float* o, float* lse, int G, int S, i
 }
 
 static int attention_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int G,
-                         int S, int L, int d, int n_head, cudaStream_t stream) {
+                         int S, int L, int d, int n_head, cudaStream_t stream, DropCfg drop) {
   const int dh = d / n_head;
   const float scale = 1.0f / sqrtf(float(dh));
   if (attention_mma_ok(S, dh)) {
 #define RLT_AB(DH_)                                                                                                  \
-  return S <= 64 ? attention_bwd_mma<DH_, 8>(qkv, o, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream)             \
-                 : attention_bwd_mma<DH_, 16>(qkv, o, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream)
+  return S <= 64 ? attention_bwd_mma<DH_, 8>(qkv, o, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream, drop)       \
+                 : attention_bwd_mma<DH_, 16>(qkv, o, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream, drop)
     if (dh == 16) RLT_AB(16);
     if (dh == 32) RLT_AB(32);
     RLT_AB(64);
@@ -566,7 +582,9 @@ static int check_desc(const rlt_encoder_desc* e) {
   RLT_REQUIRE(e->d_ff > 0 && e->d_ff % 32 == 0, RLT_UNSUPPORTED_SHAPE, "encoder: d_ff %d must be a multiple of 32", e->d_ff);
   RLT_REQUIRE(e->attend_axis == 0, RLT_UNSUPPORTED_SHAPE,
               "encoder: attend_axis=1 (attention within a list) is not implemented; the reference attends across lists");
-  RLT_REQUIRE(e->dropout_p == 0.f, RLT_UNSUPPORTED_SHAPE, "encoder: dropout_p > 0 is not implemented yet");
+  RLT_REQUIRE(e->dropout_p >= 0.f && e->dropout_p < 1.f, RLT_INVALID_ARG, "encoder: dropout_p %f outside [0, 1)", e->dropout_p);
+  RLT_REQUIRE(e->dropout_p == 0.f || (gemm_backend() == 0 && e->d_ff % 128 == 0 && e->d_model % 128 == 0), RLT_UNSUPPORTED_SHAPE,
+              "encoder: train-mode dropout runs on the tensor-core backend only (the validation kernels have no dropout)");
   RLT_REQUIRE(size_t(e->n_groups) * e->group_size * e->seq_len < (size_t(1) << 31), RLT_UNSUPPORTED_SHAPE,
               "encoder: token count overflows int32");
   return RLT_OK;
@@ -607,15 +625,19 @@ int rlt_encoder_layer_fwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   float* sv = static_cast<float*>(saved);
   const int T = e->n_groups * e->group_size * e->seq_len, d = e->d_model, f = e->d_ff;
 
+  // train-mode dropout (torch: attention probabilities, dropout1 after the attention block, dropout inside the FFN,
+  // dropout2 after it); the masks are functions of (seed, site, element) and are regenerated in the backward
+  const DropCfg drop = e->dropout_p > 0.f ? make_drop(e->dropout_p, e->dropout_seed) : DropCfg{0, 0, 1.f};
   EpiParams ep{};
   ep.alpha = 1.f;
   // qkv = x Win^T + b_in
   ep.out = sv + sl.qkv; ep.ldo = 3 * d; ep.bias = w->in_proj_b; ep.tag = TAG_QKV;
   RLT_TRY(gemm_tn(x, d, w->in_proj_w, d, T, 3 * d, d, ep, stream));
   RLT_TRY(attention_fwd(sv + sl.qkv, sv + sl.o, sv + sl.lse, e->n_groups, e->group_size, e->seq_len, d, e->n_head,
-                        stream));
-  // u1 = x + o Wo^T + b_o ; y = LN1(u1)
+                        stream, drop));
+  // u1 = x + drop(o Wo^T + b_o) ; y = LN1(u1)
   ep = EpiParams{}; ep.alpha = 1.f; ep.out = sv + sl.u1; ep.ldo = d; ep.bias = w->out_proj_b; ep.residual = x; ep.tag = TAG_OUT_PROJ;
+  ep.drop = drop; ep.drop_site = DROP_AFTER_ATTN;
   RLT_TRY(gemm_tn(sv + sl.o, d, w->out_proj_w, d, T, d, d, ep, stream));
   const bool h16 = hidden_f16(*e);
   __half* y16 = reinterpret_cast<__half*>(sv + sl.y16);
@@ -628,6 +650,7 @@ int rlt_encoder_layer_fwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   __half* w2th = w1h + size_t(d) * f;
   // h = relu(y W1^T + b1)
   ep = EpiParams{}; ep.alpha = 1.f; ep.ldo = f; ep.bias = w->lin1_b; ep.relu = 1; ep.tag = TAG_FFN1;
+  ep.drop = drop; ep.drop_site = DROP_FFN;       // the stored hidden is the DROPPED one (its sign pattern gates the backward)
   if (h16) {
     // fp16 operands (y16 is written by LN1, W1 is copied once per call): half the shared-memory operand traffic of
     // the TF32 form - the store-bound K = 128 GEMM is limited by the SM's shared-memory pipe, not by the tensor core
@@ -641,6 +664,7 @@ int rlt_encoder_layer_fwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   }
   // u2 = y + h W2^T + b2 ; out = LN2(u2)
   ep = EpiParams{}; ep.alpha = 1.f; ep.out = sv + sl.u2; ep.ldo = d; ep.bias = w->lin2_b; ep.residual = sv + sl.y; ep.tag = TAG_FFN2;
+  ep.drop = drop; ep.drop_site = DROP_AFTER_FFN;
   if (h16) {
     RLT_TRY(convert_f16(w->lin2_w, w2h, size_t(d) * f, nullptr, stream));      // [d, f] as stored
     RLT_TRY(transpose_f16(w->lin1_w, w1th, f, d, stream));                     // [f, d] -> [d, f] (backward dY)
@@ -663,14 +687,16 @@ int rlt_encoder_layer_bwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   const SavedLayout sl = saved_layout(*e);
   const float* sv = static_cast<const float*>(saved);
   const int T = e->n_groups * e->group_size * e->seq_len, d = e->d_model, f = e->d_ff;
+  const DropCfg drop = e->dropout_p > 0.f ? make_drop(e->dropout_p, e->dropout_seed) : DropCfg{0, 0, 1.f};
   float* ws = static_cast<float*>(workspace);
   float* d_u = ws;                          // [T, d]   dU2, later dU1
   float* d_y = ws + size_t(T) * d;          // [T, d]
   float* wide = ws + size_t(2) * T * d;     // [T, max(dff, 3d)]  dHpre, later dO (first T*d) / dQKV
 
   // LN2 backward: dU2, dgamma2, dbeta2, db2 (= column sums of dU2)
-  RLT_TRY(layer_norm_bwd(d_out, sv + sl.u2, sv + sl.st2, w->norm2_w, d_u, gw->norm2_w, gw->norm2_b, gw->lin2_b, T, d,
-                         stream));
+  RLT_TRY(layer_norm_bwd(d_out, sv + sl.u2, sv + sl.st2, w->norm2_w, d_u, gw->norm2_w, gw->norm2_b,
+                         drop.thr ? nullptr : gw->lin2_b, T, d, stream));
+  if (drop.thr) RLT_TRY(colsum_masked(d_u, gw->lin2_b, T, d, drop, DROP_AFTER_FFN, stream));   // b2 sits inside dropout2
   if (hidden_f16(*e)) {
     const __half* hh = reinterpret_cast<const __half*>(sv + sl.h);
     const __half* y16 = reinterpret_cast<const __half*>(sv + sl.y16);
@@ -681,14 +707,15 @@ int rlt_encoder_layer_bwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
     unsigned int* amax = reinterpret_cast<unsigned int*>(scale + 2);
     // power-of-two scale s: max|dU2| * s in [32, 64) -> dU2, dH = dU2 W2 stay far from fp16's limits on both sides
     RLT_TRY(grad_scale(d_u, size_t(T) * d, amax, scale, 6, stream));
-    RLT_TRY(convert_f16(d_u, du16, size_t(T) * d, scale, stream));
+    // the FFN branch sees dropout2(dU2); the residual branch below keeps the undropped d_u
+    RLT_TRY(convert_f16(d_u, du16, size_t(T) * d, scale, stream, drop, DROP_AFTER_FFN));
     // dW2 += dU2^T h
     RLT_TRY(gemm_dw_h(du16, d, hh, f, T, d, f, gw->lin2_w, f, 1.f, scale + 1, stream, TAG_DW_FFN2));
     // dHpre = ((s dU2) W2) * (h > 0) -> fp16 (the scale rides on the fp16 operand) ; db1 += colsum(dHpre) / s
     const __half* w2th = w1th + 2 * size_t(d) * f;
     EpiParams ep{};
-    ep.alpha = 1.f; ep.out_h = dh16; ep.ldo = f; ep.gate_h = hh; ep.colsum = gw->lin1_b; ep.scale_ptr = scale;
-    ep.scale_mode = 3; ep.tag = TAG_D_FFN2;
+    ep.alpha = drop.scale; ep.out_h = dh16; ep.ldo = f; ep.gate_h = hh; ep.colsum = gw->lin1_b; ep.scale_ptr = scale;
+    ep.scale_mode = 3; ep.tag = TAG_D_FFN2;     // h is the dropped hidden: [h > 0] is relu-mask AND keep-mask; 1/(1-p) via alpha
     RLT_TRY(gemm_tn_h(du16, d, w2th, d, T, f, d, ep, stream));
     // dW1 += dHpre^T y
     RLT_TRY(gemm_dw_h(dh16, f, y16, d, T, f, d, gw->lin1_w, d, 1.f, scale + 1, stream, TAG_DW_FFN1));
@@ -711,17 +738,24 @@ int rlt_encoder_layer_bwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   }
   EpiParams ep{};
   // LN1 backward: dU1 (into d_u), dgamma1, dbeta1, db_o
-  RLT_TRY(layer_norm_bwd(d_y, sv + sl.u1, sv + sl.st1, w->norm1_w, d_u, gw->norm1_w, gw->norm1_b, gw->out_proj_b, T, d,
-                         stream));
-  // dWo += dU1^T o ; dO = dU1 Wo
-  RLT_TRY(gemm_dw(d_u, d, sv + sl.o, d, T, d, d, gw->out_proj_w, d, 1.f, stream));
+  RLT_TRY(layer_norm_bwd(d_y, sv + sl.u1, sv + sl.st1, w->norm1_w, d_u, gw->norm1_w, gw->norm1_b,
+                         drop.thr ? nullptr : gw->out_proj_b, T, d, stream));
+  if (drop.thr) RLT_TRY(colsum_masked(d_u, gw->out_proj_b, T, d, drop, DROP_AFTER_ATTN, stream));   // b_o sits inside dropout1
+  // dWo += dU1m^T o ; dO = dU1m Wo with dU1m = dropout1 mask applied to dU1 (the residual branch keeps d_u itself);
+  // `wide` is free here (dH / dU16 are dead, dQKV is written after the last use of the masked copy)
+  const float* d_um = d_u;
+  if (drop.thr) {
+    RLT_TRY(dropout_apply(d_u, wide, size_t(T) * d, drop, DROP_AFTER_ATTN, stream));
+    d_um = wide;
+  }
+  RLT_TRY(gemm_dw(d_um, d, sv + sl.o, d, T, d, d, gw->out_proj_w, d, 1.f, stream));
   float* d_o = d_y;  // dY is dead
   ep = EpiParams{}; ep.alpha = 1.f; ep.out = d_o; ep.ldo = d;
-  RLT_TRY(gemm_nn(d_u, d, w->out_proj_w, d, T, d, d, ep, stream));
+  RLT_TRY(gemm_nn(d_um, d, w->out_proj_w, d, T, d, d, ep, stream));
   // attention backward -> dQKV
   float* d_qkv = wide;
   RLT_TRY(attention_bwd(sv + sl.qkv, sv + sl.o, sv + sl.lse, d_o, d_qkv, e->n_groups, e->group_size, e->seq_len, d,
-                        e->n_head, stream));
+                        e->n_head, stream, drop));
   // db_in += colsum(dQKV) ; dWin += dQKV^T x ; dX = dU1 + dQKV Win
   RLT_TRY(colsum(d_qkv, gw->in_proj_b, T, 3 * d, stream));
   RLT_TRY(gemm_dw(d_qkv, 3 * d, x, d, T, 3 * d, d, gw->in_proj_w, d, 1.f, stream));

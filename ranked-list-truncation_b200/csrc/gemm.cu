@@ -163,6 +163,7 @@ __global__ void gemm_tn_simt_kernel(const float* __restrict__ A, int lda, const 
       if (ep.bias) v += ep.bias[c];
       if (ep.relu) v = fmaxf(v, 0.f);
       const size_t off = size_t(r) * ep.ldo + c;
+      if (ep.drop.thr) v *= drop_factor(drop_bits(ep.drop.seed, ep.drop_site, off >> 2), int(off & 3), ep.drop.thr, ep.drop.scale);
       if (ep.gate_src) v = ep.gate_src[off] > 0.f ? v : 0.f;
       if (ep.gate_h) v = __half2float(ep.gate_h[off]) > 0.f ? v : 0.f;
       if (ep.residual) v += ep.residual[off];
@@ -249,6 +250,8 @@ static int launch_tn(const void* A, int lda, const void* B, int ldb, int M, int 
       RLT_EF_CASE(EF_BIAS | EF_RELU | EF_OUT_H);                    // FFN1 -> fp16 hidden
       RLT_EF_CASE(EF_GATE_H | EF_COLSUM | EF_OUT_H | EF_SCALE);     // dH = s (dU W2) [h > 0] -> fp16
       RLT_EF_CASE(EF_RES | EF_SCALE);                               // dY = dU + (dH W1) / s
+      RLT_EF_CASE(EF_BIAS | EF_RELU | EF_OUT_H | EF_DROP);          // train-mode dropout variants
+      RLT_EF_CASE(EF_BIAS | EF_RES | EF_DROP);
 #undef RLT_EF_CASE
       default: break;
     }
@@ -363,25 +366,65 @@ int gemm_dw_h(const __half* A, int lda, const __half* B, int ldb, int T, int M, 
 // ------------------------------------------------------------------------------------------
 // fp16 operand copies
 // ------------------------------------------------------------------------------------------
-// dst = half(src * (scale ? scale[0] : 1)), n a multiple of 4
+// dst = half(src * (scale ? scale[0] : 1) * dropout factor), n a multiple of 4
 __global__ void __launch_bounds__(256) convert_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n4,
-                                                          const float* __restrict__ scale) {
+                                                          const float* __restrict__ scale, DropCfg drop, uint32_t site) {
   const float s = scale != nullptr ? scale[0] : 1.f;
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    float4 v = reinterpret_cast<const float4*>(src)[i];
+    if (drop.thr) {
+      const uint64_t bits = drop_bits(drop.seed, site, i);
+      v.x *= drop_factor(bits, 0, drop.thr, drop.scale); v.y *= drop_factor(bits, 1, drop.thr, drop.scale);
+      v.z *= drop_factor(bits, 2, drop.thr, drop.scale); v.w *= drop_factor(bits, 3, drop.thr, drop.scale);
+    }
     const __half2 lo = __floats2half2_rn(v.x * s, v.y * s), hi = __floats2half2_rn(v.z * s, v.w * s);
     reinterpret_cast<uint2*>(dst)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
   }
 }
-int convert_f16(const float* src, __half* dst, size_t n, const float* scale, cudaStream_t stream) {
+int convert_f16(const float* src, __half* dst, size_t n, const float* scale, cudaStream_t stream, DropCfg drop,
+                uint32_t site) {
   RLT_REQUIRE(n % 4 == 0, RLT_INVALID_ARG, "convert_f16: n must be a multiple of 4");
   size_t blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > size_t(num_sms()) * 16) blocks = size_t(num_sms()) * 16;
-  convert_f16_kernel<<<unsigned(blocks), 256, 0, stream>>>(src, dst, n / 4, scale);
+  convert_f16_kernel<<<unsigned(blocks), 256, 0, stream>>>(src, dst, n / 4, scale, drop, site);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
+}
+// dst = src * dropout factor (fp32; the masked copy of a gradient that feeds the GEMMs of a dropped branch)
+__global__ void __launch_bounds__(256) dropout_apply_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n4,
+                                                            DropCfg drop, uint32_t site) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = reinterpret_cast<const float4*>(src)[i];
+    const uint64_t bits = drop_bits(drop.seed, site, i);
+    v.x *= drop_factor(bits, 0, drop.thr, drop.scale); v.y *= drop_factor(bits, 1, drop.thr, drop.scale);
+    v.z *= drop_factor(bits, 2, drop.thr, drop.scale); v.w *= drop_factor(bits, 3, drop.thr, drop.scale);
+    reinterpret_cast<float4*>(dst)[i] = v;
+  }
+}
+int dropout_apply(const float* src, float* dst, size_t n, DropCfg drop, uint32_t site, cudaStream_t stream) {
+  RLT_REQUIRE(n % 4 == 0, RLT_INVALID_ARG, "dropout_apply: n must be a multiple of 4");
+  size_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > size_t(num_sms()) * 16) blocks = size_t(num_sms()) * 16;
+  dropout_apply_kernel<<<unsigned(blocks), 256, 0, stream>>>(src, dst, n / 4, drop, site);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+// Test hook: out[i] = keep-and-scale factor of element i of a linear site (groups of 4), or, for the attention site,
+// out[(item * S + query) * S + key] with the pair indexing of the attention kernels.
+__global__ void dropout_mask_kernel(float* __restrict__ out, size_t n, DropCfg drop, uint32_t site, int S) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (site == DROP_ATTN) {
+      const size_t key = i % S;
+      out[i] = drop_factor(drop_bits(drop.seed, site, i - (key & 1)), int(key & 1), drop.thr, drop.scale);
+    } else {
+      out[i] = drop_factor(drop_bits(drop.seed, site, i >> 2), int(i & 3), drop.thr, drop.scale);
+    }
+  }
 }
 // dst[c, r] = half(src[r, c])   ([rows, cols] -> [cols, rows])
 __global__ void transpose_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int rows, int cols) {
@@ -616,6 +659,15 @@ int rlt_grad_weight(const float* A, const float* B, float* C, int T, int M, int 
 int rlt_convert_f16(const float* src, void* dst, size_t n, const float* scale, rlt_stream_t stream) {
   RLT_REQUIRE(src && dst, RLT_INVALID_ARG, "rlt_convert_f16: null pointer");
   return convert_f16(src, static_cast<__half*>(dst), n, scale, static_cast<cudaStream_t>(stream));
+}
+
+int rlt_dropout_mask(uint64_t seed, int site, float p, size_t n, int group_size, float* out, rlt_stream_t stream) {
+  RLT_REQUIRE(out && n > 0 && site >= 1 && site <= 5 && p >= 0.f && p < 1.f, RLT_INVALID_ARG, "rlt_dropout_mask: bad arguments");
+  RLT_REQUIRE(site != DROP_ATTN || group_size > 0, RLT_INVALID_ARG, "rlt_dropout_mask: the attention site needs group_size");
+  dropout_mask_kernel<<<num_sms() * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, make_drop(p, seed), uint32_t(site),
+                                                                                  group_size);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
 }
 
 int rlt_linear_f16(const void* A, const void* B, const float* bias, float* C, int M, int N, int K, float alpha, int relu,

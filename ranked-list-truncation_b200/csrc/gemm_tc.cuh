@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include "dropout.cuh"
 #include "sm100.cuh"
 
 namespace rlt {
@@ -39,6 +40,10 @@ struct EpiParams {
   //   scale_mode 3: the result is left as it is (an operand already carries s); column sums are multiplied by 1/s
   const float* scale_ptr;
   int scale_mode;
+  // ---- train-mode dropout applied to (alpha acc + bias) after the ReLU and BEFORE the residual is added; the element
+  //      index of the hash is row * ldo + col (dropout.cuh); drop.thr == 0 disables it
+  DropCfg drop;
+  uint32_t drop_site;
 };
 
 // Sum v[j] over the 32 lanes of a warp for 32 different j: on return lane j holds the column-j
@@ -92,11 +97,11 @@ struct GemmTnCfg {
 // epilogue warps thrash the instruction cache: measured +30-45% on the store-bound GEMMs); EF_RUNTIME keeps every
 // branch and tests the EpiParams fields at run time.
 enum : int { EF_BIAS = 1, EF_RELU = 2, EF_GATE = 4, EF_RES = 8, EF_COLSUM = 16, EF_ACC = 32, EF_RUNTIME = 64,
-              EF_OUT_H = 128, EF_GATE_H = 256, EF_SCALE = 512 };
+              EF_OUT_H = 128, EF_GATE_H = 256, EF_SCALE = 512, EF_DROP = 1024 };
 __host__ __device__ inline int epi_mask(const EpiParams& ep) {
   return (ep.bias ? EF_BIAS : 0) | (ep.relu ? EF_RELU : 0) | (ep.gate_src ? EF_GATE : 0) | (ep.residual ? EF_RES : 0) |
          (ep.colsum ? EF_COLSUM : 0) | (ep.accumulate ? EF_ACC : 0) | (ep.out_h ? EF_OUT_H : 0) |
-         (ep.gate_h ? EF_GATE_H : 0) | (ep.scale_mode ? EF_SCALE : 0);
+         (ep.gate_h ? EF_GATE_H : 0) | (ep.scale_mode ? EF_SCALE : 0) | (ep.drop.thr ? EF_DROP : 0);
 }
 template <int EF> __device__ __forceinline__ bool ef_bias(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.bias != nullptr : (EF & EF_BIAS) != 0; }
 template <int EF> __device__ __forceinline__ bool ef_relu(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.relu != 0 : (EF & EF_RELU) != 0; }
@@ -106,6 +111,7 @@ template <int EF> __device__ __forceinline__ bool ef_colsum(const EpiParams& ep)
 template <int EF> __device__ __forceinline__ bool ef_acc(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.accumulate != 0 : (EF & EF_ACC) != 0; }
 template <int EF> __device__ __forceinline__ bool ef_out_h(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.out_h != nullptr : (EF & EF_OUT_H) != 0; }
 template <int EF> __device__ __forceinline__ bool ef_gate_h(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.gate_h != nullptr : (EF & EF_GATE_H) != 0; }
+template <int EF> __device__ __forceinline__ bool ef_drop(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.drop.thr != 0 : (EF & EF_DROP) != 0; }
 template <int EF> __device__ __forceinline__ bool ef_scale(const EpiParams& ep) { return EF == EF_RUNTIME ? ep.scale_mode != 0 : (EF & EF_SCALE) != 0; }
 
 // Operand of the epilogue that comes from global memory, fetched for a whole 32x32 chunk BEFORE the accumulator is
@@ -178,6 +184,11 @@ __device__ __forceinline__ void epilogue_store_chunk(const EpiParams& ep, float 
       x.z = fmaf(x.z, alpha, bias.z); x.w = fmaf(x.w, alpha, bias.w);
       if (ef_relu<EF>(ep)) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
       const size_t off = size_t(row) * ep.ldo + col;
+      if (ef_drop<EF>(ep)) {
+        const uint64_t bits = drop_bits(ep.drop.seed, ep.drop_site, off >> 2);
+        x.x *= drop_factor(bits, 0, ep.drop.thr, ep.drop.scale); x.y *= drop_factor(bits, 1, ep.drop.thr, ep.drop.scale);
+        x.z *= drop_factor(bits, 2, ep.drop.thr, ep.drop.scale); x.w *= drop_factor(bits, 3, ep.drop.thr, ep.drop.scale);
+      }
       if (ef_gate_h<EF>(ep)) {
         // fp16 values are >= +0 after the ReLU: "> 0" is "any bit set" of the 16-bit pattern
         const uint32_t g0 = __float_as_uint(aux.a[it].x), g1 = __float_as_uint(aux.a[it].y);

@@ -705,10 +705,15 @@ __global__ void __launch_bounds__(128) choopy_embed_bwd_kernel(const float* __re
 }
 
 // BiCut output head (models/Bicut.py:11-16): 2-class softmax of the logit planes z[0,:], z[1,:] -> o[t, 0:2]
-__global__ void pair_softmax_fwd_kernel(const float* __restrict__ z, float* __restrict__ o, size_t T) {
+// Train mode: nn.Dropout(p) acts on the two logits BEFORE the softmax (models/Bicut.py:14); element index = c * T + t.
+__global__ void pair_softmax_fwd_kernel(const float* __restrict__ z, float* __restrict__ o, size_t T, DropCfg drop) {
   const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  const float a = z[t], b = z[T + t];
+  float a = z[t], b = z[T + t];
+  if (drop.thr) {
+    a *= drop_factor(drop_bits(drop.seed, DROP_LOGITS, t >> 2), int(t & 3), drop.thr, drop.scale);
+    b *= drop_factor(drop_bits(drop.seed, DROP_LOGITS, (T + t) >> 2), int((T + t) & 3), drop.thr, drop.scale);
+  }
   const float m = fmaxf(a, b);
   const float ea = __expf(a - m), eb = __expf(b - m);
   const float inv = 1.f / (ea + eb);
@@ -716,13 +721,18 @@ __global__ void pair_softmax_fwd_kernel(const float* __restrict__ z, float* __re
 }
 // dz[c, t] = o_c (do_c - <o, do>)
 __global__ void pair_softmax_bwd_kernel(const float* __restrict__ o, const float* __restrict__ d_o, float* __restrict__ dz,
-                                        size_t T) {
+                                        size_t T, DropCfg drop) {
   const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const float2 p = reinterpret_cast<const float2*>(o)[t], g = reinterpret_cast<const float2*>(d_o)[t];
   const float dot = p.x * g.x + p.y * g.y;
-  dz[t] = p.x * (g.x - dot);
-  dz[T + t] = p.y * (g.y - dot);
+  float da = p.x * (g.x - dot), db = p.y * (g.y - dot);
+  if (drop.thr) {
+    da *= drop_factor(drop_bits(drop.seed, DROP_LOGITS, t >> 2), int(t & 3), drop.thr, drop.scale);
+    db *= drop_factor(drop_bits(drop.seed, DROP_LOGITS, (T + t) >> 2), int((T + t) & 3), drop.thr, drop.scale);
+  }
+  dz[t] = da;
+  dz[T + t] = db;
 }
 
 template <typename F>
@@ -884,15 +894,19 @@ int rlt_head_dots_bwd(const float* x, const float* w, const float* dz, float* dx
   return RLT_OK;
 }
 
-int rlt_pair_softmax_fwd(const float* z, float* o, size_t n_tokens, rlt_stream_t stream_) {
-  RLT_REQUIRE(z && o && n_tokens > 0, RLT_INVALID_ARG, "rlt_pair_softmax_fwd: bad arguments");
-  pair_softmax_fwd_kernel<<<unsigned((n_tokens + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(z, o, n_tokens);
+int rlt_pair_softmax_fwd(const float* z, float* o, size_t n_tokens, float dropout_p, uint64_t dropout_seed,
+                         rlt_stream_t stream_) {
+  RLT_REQUIRE(z && o && n_tokens > 0 && dropout_p >= 0.f && dropout_p < 1.f, RLT_INVALID_ARG, "rlt_pair_softmax_fwd: bad arguments");
+  const DropCfg drop = dropout_p > 0.f ? make_drop(dropout_p, dropout_seed) : DropCfg{0, 0, 1.f};
+  pair_softmax_fwd_kernel<<<unsigned((n_tokens + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(z, o, n_tokens, drop);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }
-int rlt_pair_softmax_bwd(const float* o, const float* d_o, float* dz, size_t n_tokens, rlt_stream_t stream_) {
-  RLT_REQUIRE(o && d_o && dz && n_tokens > 0, RLT_INVALID_ARG, "rlt_pair_softmax_bwd: bad arguments");
-  pair_softmax_bwd_kernel<<<unsigned((n_tokens + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(o, d_o, dz, n_tokens);
+int rlt_pair_softmax_bwd(const float* o, const float* d_o, float* dz, size_t n_tokens, float dropout_p,
+                         uint64_t dropout_seed, rlt_stream_t stream_) {
+  RLT_REQUIRE(o && d_o && dz && n_tokens > 0 && dropout_p >= 0.f && dropout_p < 1.f, RLT_INVALID_ARG, "rlt_pair_softmax_bwd: bad arguments");
+  const DropCfg drop = dropout_p > 0.f ? make_drop(dropout_p, dropout_seed) : DropCfg{0, 0, 1.f};
+  pair_softmax_bwd_kernel<<<unsigned((n_tokens + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(o, d_o, dz, n_tokens, drop);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }

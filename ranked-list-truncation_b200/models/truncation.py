@@ -6,8 +6,8 @@ parameter names (checkpoints interchange both ways, run.py:208-220), identical s
 the same torch seed — identical initial values.  `forward` never calls them; it hands their
 parameters to the CUDA kernels through rlt_b200.autograd.
 
-Train-mode dropout (p > 0) is not implemented yet: modules raise in train() mode unless dropout == 0
-(parity tests and benchmarks use dropout = 0; eval() always works).
+Train-mode dropout follows torch's placement (four sites per encoder layer, the two logits of BiCut) with masks from
+a counter hash instead of torch's Philox stream (csrc/dropout.cuh): same distribution, different bits.
 """
 from __future__ import annotations
 
@@ -51,14 +51,15 @@ class _Base(nn.Module):
     _dropout_p = 0.0
 
     def _check_mode(self):
-        if self.training and self._dropout_p > 0:
-            raise NotImplementedError(
-                f"{type(self).__name__}: train-mode dropout (p={self._dropout_p}) is not implemented on the rlt_b200 "
-                "path yet; construct the model with dropout=0 or call .eval()")
+        """Kept for the callers: every mode is supported (train-mode dropout included)."""
+
+    def _p(self) -> float:
+        """Dropout probability in effect: the constructor's value in train(), 0 in eval()."""
+        return float(self._dropout_p) if self.training else 0.0
 
     def _encode(self, x, enc: nn.TransformerEncoder):
         layer0 = enc.layers[0]
-        return F.EncoderStack.apply(x, layer0.self_attn.num_heads, 1, layer0.norm1.eps, *_encoder_params(enc))
+        return F.EncoderStack.apply(x, layer0.self_attn.num_heads, 1, layer0.norm1.eps, self._p(), *_encoder_params(enc))
 
     @staticmethod
     def _heads(h, linears):
@@ -134,7 +135,7 @@ class BiCut(_Base):
     def forward(self, x):
         self._check_mode()
         h = F.BiLstm.apply(x, self.bilstm.hidden_size, self.bilstm.num_layers, *self.bilstm._flat_weights)
-        return F.BicutHead.apply(h, self.fc.weight, self.fc.bias, self.softmax[1].weight, self.softmax[1].bias)
+        return F.BicutHead.apply(h, self.fc.weight, self.fc.bias, self.softmax[1].weight, self.softmax[1].bias, self._p())
 
 
 class AttnCut(_Base):

@@ -14,6 +14,12 @@ def _buf(nbytes: int, device) -> torch.Tensor:
     return torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
 
 
+def fresh_seed() -> int:
+    """Seed of one forward call's dropout masks, drawn from torch's default (host) generator so that
+    torch.manual_seed() makes runs repeatable.  The same seed is handed to the backward kernels."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
 def _c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise RuntimeError("rlt_b200 computes in float32 only (the reference's parameters and inputs are float32); "
@@ -29,7 +35,7 @@ class EncoderStack(torch.autograd.Function):
     attention group, as in the reference (no batch_first)."""
 
     @staticmethod
-    def forward(ctx, x, n_head, n_groups, ln_eps, *params):
+    def forward(ctx, x, n_head, n_groups, ln_eps, dropout_p, *params):
         x = _c(x)
         B, L, d = x.shape
         n_layers = len(params) // 12
@@ -37,7 +43,10 @@ class EncoderStack(torch.autograd.Function):
         d_ff = params[4].shape[0]
         if B % n_groups:
             raise RuntimeError(f"batch of {B} lists is not divisible into {n_groups} attention groups")
-        desc = ops.encoder_desc(n_groups, B // n_groups, L, d, n_head, d_ff, ln_eps)
+        dropout_p = float(dropout_p)
+        descs = [ops.encoder_desc(n_groups, B // n_groups, L, d, n_head, d_ff, ln_eps, dropout_p,
+                                  fresh_seed() if dropout_p > 0 else 0) for _ in range(n_layers)]   # one mask set per layer
+        desc = descs[0]
         need_grad = any(ctx.needs_input_grad)
         saved_bytes = ops.encoder_saved_bytes(desc)
         if saved_bytes == 0:
@@ -54,12 +63,13 @@ class EncoderStack(torch.autograd.Function):
                 if scratch is None:
                     scratch = _buf(saved_bytes, x.device)
                 sv = scratch
-            ops.encoder_layer_fwd(desc, w, cur, out, sv)
+            ops.encoder_layer_fwd(descs[i], w, cur, out, sv)
             if need_grad:
                 saved.append(sv)
                 inputs.append(cur)
             cur = out
         ctx.desc = desc
+        ctx.descs = descs
         ctx.n_layers = n_layers
         ctx.params = params
         ctx.saved_bufs = saved
@@ -77,10 +87,10 @@ class EncoderStack(torch.autograd.Function):
             w = ops.encoder_ptrs(params[12 * i:12 * i + 12])
             g = ops.encoder_ptrs(grads[12 * i:12 * i + 12])
             d_x = torch.empty_like(d_out)
-            ops.encoder_layer_bwd(desc, w, g, ctx.layer_inputs[i], ctx.saved_bufs[i], cur, d_x, ws)
+            ops.encoder_layer_bwd(ctx.descs[i], w, g, ctx.layer_inputs[i], ctx.saved_bufs[i], cur, d_x, ws)
             cur = d_x
         ctx.saved_bufs = ctx.layer_inputs = None
-        return (cur, None, None, None, *grads)
+        return (cur, None, None, None, None, *grads)
 
 
 class BiLstm(torch.autograd.Function):
@@ -112,10 +122,10 @@ class BiLstm(torch.autograd.Function):
 
 
 class BicutHead(torch.autograd.Function):
-    """softmax_2( Linear(256,2)( relu( Linear(256,256)(h) ) ) ) of models/Bicut.py:10-16,20-21 (dropout p = 0)."""
+    """softmax_2( dropout_p( Linear(256,2)( relu( Linear(256,256)(h) ) ) ) ) of models/Bicut.py:10-16,20-21."""
 
     @staticmethod
-    def forward(ctx, h, w1, b1, w2, b2):
+    def forward(ctx, h, w1, b1, w2, b2, dropout_p=0.0):
         h, w1, b1, w2, b2 = _c(h), _c(w1.detach()), _c(b1.detach()), _c(w2.detach()), _c(b2.detach())
         B, L, d = h.shape
         T = B * L
@@ -124,7 +134,9 @@ class BicutHead(torch.autograd.Function):
         z = torch.empty(2, T, dtype=torch.float32, device=h.device)
         ops.head_dots_fwd(a, w2, b2, z, T, w1.shape[0], 2)
         o = torch.empty(B, L, 2, dtype=torch.float32, device=h.device)
-        ops.pair_softmax_fwd(z, o, T)
+        ctx.dropout_p = float(dropout_p)
+        ctx.seed = fresh_seed() if ctx.dropout_p > 0 else 0
+        ops.pair_softmax_fwd(z, o, T, ctx.dropout_p, ctx.seed)
         ctx.save_for_backward(h, w1, w2, a, o)
         return o
 
@@ -136,7 +148,7 @@ class BicutHead(torch.autograd.Function):
         T = B * L
         f = w1.shape[0]
         dz = torch.empty(2, T, dtype=torch.float32, device=h.device)
-        ops.pair_softmax_bwd(o, d_o, dz, T)
+        ops.pair_softmax_bwd(o, d_o, dz, T, ctx.dropout_p, ctx.seed)
         da = torch.empty_like(a)
         dw2 = torch.zeros_like(w2)
         db2 = torch.zeros(2, dtype=torch.float32, device=h.device)
@@ -147,7 +159,7 @@ class BicutHead(torch.autograd.Function):
         ops.colsum(da, db1)
         dh = torch.empty_like(h)
         ops.linear_nn(da, w1, dh.view(T, d))
-        return dh, dw1, db1, dw2, db2
+        return dh, dw1, db1, dw2, db2, None
 
 
 class MoeGateMix(torch.autograd.Function):

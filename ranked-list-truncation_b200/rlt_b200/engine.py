@@ -46,12 +46,26 @@ class _EncStack:
         sb = (ops.encoder_saved_bytes(self.desc) + 3) // 4
         self.saved = [torch.empty(sb, **f32) for _ in range(self.n if eng.training else 1)]
         self.training = eng.training
+        # train-mode dropout: the model's probability while stepping, one fresh mask seed per layer and step
+        self.p = float(l0.dropout.p) if eng.training else 0.0
+        self.seeds = [0] * self.n
 
-    def forward(self, x):
+    def _set_drop(self, desc, i):
+        desc.dropout_p = self.p
+        desc.dropout_seed = self.seeds[i]
+
+    def forward(self, x, train=True):
+        from .autograd import fresh_seed
         cur = x
+        p_saved = self.p
+        if not train:
+            self.p = 0.0
         for i in range(self.n):
+            self.seeds[i] = fresh_seed() if self.p > 0 else 0
+            self._set_drop(self.desc, i)
             ops.encoder_layer_fwd(self.desc, self.w[i], cur, self.outs[i], self.saved[i if self.training else 0])
             cur = self.outs[i]
+        self.p = p_saved
         return cur
 
     def backward(self, x, d_out, d_x, scratch, ws):
@@ -63,6 +77,7 @@ class _EncStack:
                 dst, desc = d_x, self.desc_first
             else:
                 dst, desc = (scratch[0] if cur is not scratch[0] else scratch[1]), self.desc
+            self._set_drop(desc, i)
             ops.encoder_layer_bwd(desc, self.w[i], self.g[i], inp, self.saved[i], cur, dst, ws)
             cur = dst
 
@@ -198,7 +213,8 @@ class Engine:
                     self.w_gates[t].copy_(p)
 
     # ------------------------------------------------------------------------------------------
-    def _forward(self, x):
+    def _forward(self, x, train=False):
+        from .autograd import fresh_seed
         k = self.kind
         if self.lstm is None:
             ops.choopy_embed_fwd(x, self.pe.detach(), self.front)
@@ -207,9 +223,11 @@ class Engine:
         if k == "bicut":
             ops.linear(self.front, self.fc_w.detach(), self.fc_b.detach(), self.fc_out, relu=True)
             ops.head_dots_fwd(self.fc_out, self.head_w, self.head_b, self.z, self.T, self.d_head, 2)
-            ops.pair_softmax_fwd(self.z, self.probs2, self.T)
+            self.bicut_p = float(self.model._dropout_p) if train else 0.0
+            self.bicut_seed = fresh_seed() if self.bicut_p > 0 else 0
+            ops.pair_softmax_fwd(self.z, self.probs2, self.T, self.bicut_p, self.bicut_seed)
             return self.fc_out
-        tops = [st.forward(self.front) for st in self.stacks]
+        tops = [st.forward(self.front, train) for st in self.stacks]
         if k == "mmoecut":
             ops.moe_heads_fwd(self.moe_desc, self.front, self.w_gates, tops, self.head_w, self.head_b, self.gates, self.z)
         else:
@@ -224,7 +242,7 @@ class Engine:
         if k == "bicut":
             ops.bicut_loss(self.probs2, y, input_kind=1, metric_nci=False, grad=self.dprobs2,
                            loss_per_list=self.loss_per_list, loss_out=self.loss, grad_scale=1.0 / B, loss_scale=1.0 / B)
-            ops.pair_softmax_bwd(self.probs2, self.dprobs2, self.dz, self.T)
+            ops.pair_softmax_bwd(self.probs2, self.dprobs2, self.dz, self.T, self.bicut_p, self.bicut_seed)
             return
         if k == "choopy":
             ops.cut_loss(self.z[cut], y, loss_kind="choopy", metric=self.metric, tau=1.0, input_kind=0, grad=self.dz[cut],
@@ -249,7 +267,7 @@ class Engine:
         self.grad_bucket.zero_()
         self.head_dw.zero_()
         self.head_db.zero_()
-        top = self._forward(x)
+        top = self._forward(x, train=True)
         self._criterion(y)
         d_front = self.dact[2]
         if k == "bicut":

@@ -153,12 +153,23 @@ def head_dots_bwd(x, w, dz, dx, dw, db, n_tokens, d, n_heads, accumulate_dx=Fals
                                   int(accumulate_dx), int(relu_gate), stream_ptr()), "rlt_head_dots_bwd")
 
 
-def pair_softmax_fwd(z, o, n_tokens):
-    check(lib().rlt_pair_softmax_fwd(ptr(z), ptr(o), C.c_size_t(n_tokens), stream_ptr()), "rlt_pair_softmax_fwd")
+def pair_softmax_fwd(z, o, n_tokens, dropout_p=0.0, seed=0):
+    check(lib().rlt_pair_softmax_fwd(ptr(z), ptr(o), C.c_size_t(n_tokens), C.c_float(dropout_p), C.c_uint64(seed),
+                                     stream_ptr()), "rlt_pair_softmax_fwd")
 
 
-def pair_softmax_bwd(o, d_o, dz, n_tokens):
-    check(lib().rlt_pair_softmax_bwd(ptr(o), ptr(d_o), ptr(dz), C.c_size_t(n_tokens), stream_ptr()), "rlt_pair_softmax_bwd")
+def pair_softmax_bwd(o, d_o, dz, n_tokens, dropout_p=0.0, seed=0):
+    check(lib().rlt_pair_softmax_bwd(ptr(o), ptr(d_o), ptr(dz), C.c_size_t(n_tokens), C.c_float(dropout_p), C.c_uint64(seed),
+                                     stream_ptr()), "rlt_pair_softmax_bwd")
+
+
+def dropout_mask(seed, site, p, n, group_size=0, device="cuda"):
+    """Test hook: the keep-and-scale factors (0 or 1/(1-p)) the kernels apply at dropout site `site`."""
+    import torch
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    check(lib().rlt_dropout_mask(C.c_uint64(seed), int(site), C.c_float(p), C.c_size_t(n), int(group_size), ptr(out),
+                                 stream_ptr()), "rlt_dropout_mask")
+    return out
 
 
 def linear(a, w, bias, out, relu=False):

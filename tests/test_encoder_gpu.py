@@ -44,7 +44,7 @@ def test_encoder_layer_fwd_bwd_vs_oracle(backend, d, n_head, S, L, G):
         (out64 * dy.double()).sum().backward()
         params = [sd[n].cuda().requires_grad_(True) for n in ops.ENCODER_PARAM_ORDER]
         xc = x.cuda().requires_grad_(True)
-        out = EncoderStack.apply(xc, n_head, G, 1e-5, *params)
+        out = EncoderStack.apply(xc, n_head, G, 1e-5, 0.0, *params)
         (out * dy.cuda()).sum().backward()
         # backend 1 (exact fp32 FMA) pins the kernel logic at 2e-5.  backend 0 (TF32 tensor cores): outputs at
         # 1e-3; for gradients this synthetic test (random upstream gradient, a few hundred tokens) only asserts a
