@@ -331,7 +331,8 @@ __device__ __forceinline__ AttnItem attn_item(long long i, int S, int L, int n_h
   return it;
 }
 
-template <int DH, int NT>
+// kDrop: train-mode dropout on the attention probabilities (a separate instantiation: the hash code costs registers)
+template <int DH, int NT, bool kDrop>
 __global__ void __launch_bounds__(128) attn_lists_fwd_pipe_kernel(const float* __restrict__ qkv, float* __restrict__ o,
                                                                   float* __restrict__ lse, int S, int L, int d, int n_head,
                                                                   float scale, long long n_items, DropCfg drop) {
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(128) attn_lists_fwd_pipe_kernel(const float* _
       s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
       s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
       const int ra = r0 + gq, rb = r0 + gq + 8;
-      if (drop.thr) {   // dropout on the attention probabilities (the row sums above stay undropped)
+      if (kDrop) {   // dropout on the attention probabilities (the row sums above stay undropped)
         const uint64_t ea = (uint64_t(item) * S + ra) * S, eb = (uint64_t(item) * S + rb) * S;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(128) attn_lists_fwd_pipe_kernel(const float* _
 
 // Backward.  D_i = sum_j P_ij dP_ij (= dO_i . O_i) is taken from the phase-A fragments, so the attention output is not
 // read at all.
-template <int DH, int NT>
+template <int DH, int NT, bool kDrop>
 __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* __restrict__ qkv, const float* __restrict__ lse,
                                                                   const float* __restrict__ d_o, float* __restrict__ dqkv,
                                                                   int S, int L, int d, int n_head, float scale,
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
       }
       tile_abT<DH, NT, true>(sQ, r0, sK, p, lane);
       tile_abT<DH, NT, false>(sG, r0, sV, dp, lane);
-      if (drop.thr) {   // d(attn) = mask/(1-p) * d(dropped attn)
+      if (kDrop) {   // d(attn) = mask/(1-p) * d(dropped attn)
         const uint64_t ea = (uint64_t(item) * S + r0 + gq) * S, eb = (uint64_t(item) * S + r0 + gq + 8) * S;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
@@ -545,7 +546,7 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
         const float p0 = exp2f(fmaf(p[j][0], sc, -l0)), p1 = exp2f(fmaf(p[j][1], sc, -l1));
         const float p2 = exp2f(fmaf(p[j][2], sc, -l0)), p3 = exp2f(fmaf(p[j][3], sc, -l1));
         float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;   // dropout factors of (query i / i+1, key c0+gq / +8)
-        if (drop.thr) {
+        if (kDrop) {
           const int ka_ = c0 + gq, kb_ = c0 + gq + 8;
           const uint64_t q0 = (uint64_t(item) * S + i) * S, q1 = (uint64_t(item) * S + i + 1) * S;
           m0 = drop_factor(drop_bits(drop.seed, DROP_ATTN, q0 + (ka_ & ~1)), ka_ & 1, drop.thr, drop.scale);

@@ -394,26 +394,51 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_kernel(const float* __rest
 }
 
 // persistent pipelined kernels: as many CTAs as are co-resident (occupancy API), each walking items with stride gridDim.x
-template <int DH, int NT>
-static int attention_fwd_mma(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head, float scale,
-                             cudaStream_t stream, DropCfg drop) {
+template <int DH, int NT, bool kDrop>
+static int attention_fwd_launch(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head, float scale,
+                                cudaStream_t stream, DropCfg drop) {
   const size_t smem = size_t(2) * 3 * NT * 8 * (DH + 4) * sizeof(float);
   static bool attr_set = false;
+  static int per_sm = 0;
   if (!attr_set) {
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_pipe_kernel<DH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_pipe_kernel<DH, NT, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_fwd_pipe_kernel<DH, NT, kDrop>, 128, smem));
+    if (per_sm < 1) per_sm = 1;
     attr_set = true;
   }
   const long long n_items = (long long)G * L * n_head;
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_fwd_pipe_kernel<DH, NT>, 128, smem));
-    if (per_sm < 1) per_sm = 1;
-  }
   long long grid = (long long)num_sms() * per_sm;
   if (grid > n_items) grid = n_items;
   time_begin(TAG_ATTN_FWD, stream);
-  attn_lists_fwd_pipe_kernel<DH, NT><<<int(grid), 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, n_items, drop);
+  attn_lists_fwd_pipe_kernel<DH, NT, kDrop><<<int(grid), 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, n_items, drop);
   time_end(TAG_ATTN_FWD, stream);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+template <int DH, int NT>
+static int attention_fwd_mma(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head, float scale,
+                             cudaStream_t stream, DropCfg drop) {
+  return drop.thr ? attention_fwd_launch<DH, NT, true>(qkv, o, lse, G, S, L, d, n_head, scale, stream, drop)
+                  : attention_fwd_launch<DH, NT, false>(qkv, o, lse, G, S, L, d, n_head, scale, stream, drop);
+}
+template <int DH, int NT, bool kDrop>
+static int attention_bwd_launch(const float* qkv, const float* lse, const float* d_o, float* dqkv, int G, int S, int L, int d,
+                                int n_head, float scale, cudaStream_t stream, DropCfg drop) {
+  const size_t smem = (size_t(2) * (4 * NT * 8 * (DH + 4) + NT * 8) + NT * 8) * sizeof(float);
+  static bool attr_set = false;
+  static int per_sm = 0;
+  if (!attr_set) {
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_pipe_kernel<DH, NT, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_bwd_pipe_kernel<DH, NT, kDrop>, 128, smem));
+    if (per_sm < 1) per_sm = 1;
+    attr_set = true;
+  }
+  const long long n_items = (long long)G * L * n_head;
+  long long grid = (long long)num_sms() * per_sm;
+  if (grid > n_items) grid = n_items;
+  time_begin(TAG_ATTN_BWD, stream);
+  attn_lists_bwd_pipe_kernel<DH, NT, kDrop><<<int(grid), 128, smem, stream>>>(qkv, lse, d_o, dqkv, S, L, d, n_head, scale, n_items, drop);
+  time_end(TAG_ATTN_BWD, stream);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }
@@ -421,25 +446,8 @@ template <int DH, int NT>
 static int attention_bwd_mma(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int G,
                              int S, int L, int d, int n_head, float scale, cudaStream_t stream, DropCfg drop) {
   (void)o;   // D = rowsum(P * dP) is recomputed from the fragments; the attention output is not needed
-  const size_t smem = (size_t(2) * (4 * NT * 8 * (DH + 4) + NT * 8) + NT * 8) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_pipe_kernel<DH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    attr_set = true;
-  }
-  const long long n_items = (long long)G * L * n_head;
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_bwd_pipe_kernel<DH, NT>, 128, smem));
-    if (per_sm < 1) per_sm = 1;
-  }
-  long long grid = (long long)num_sms() * per_sm;
-  if (grid > n_items) grid = n_items;
-  time_begin(TAG_ATTN_BWD, stream);
-  attn_lists_bwd_pipe_kernel<DH, NT><<<int(grid), 128, smem, stream>>>(qkv, lse, d_o, dqkv, S, L, d, n_head, scale, n_items, drop);
-  time_end(TAG_ATTN_BWD, stream);
-  RLT_CHECK_LAUNCH();
-  return RLT_OK;
+  return drop.thr ? attention_bwd_launch<DH, NT, true>(qkv, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream, drop)
+                  : attention_bwd_launch<DH, NT, false>(qkv, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream, drop);
 }
 // tensor-core path available for S <= 128 and dh in {16, 32, 64}
 static bool attention_mma_ok(int S, int dh) { return gemm_backend() == 0 && S <= 128 && (dh == 16 || dh == 32 || dh == 64); }
