@@ -279,29 +279,63 @@ int rlt_bilstm_fwd(const rlt_bilstm_desc* d, const rlt_bilstm_weights* w, const 
   float* WT = y0_scratch + size_t(T) * 2 * H;
   float* bias_scratch = WT + 4 * size_t(H) * G4;
   float* y0 = saved ? saved + sl.y0 : y0_scratch;
-  for (int l = 0; l < 2; ++l)
-    for (int dir = 0; dir < 2; ++dir) {
-      transpose_whh_kernel<<<(G4 * H + 255) / 256, 256, 0, stream>>>(w->w_hh[l][dir], WT + (l * 2 + dir) * size_t(H) * G4);
-      RLT_CHECK_LAUNCH();
-    }
+  const bool tc = lstm_backend() == 0;
+  if (!tc) {
+    for (int l = 0; l < 2; ++l)
+      for (int dir = 0; dir < 2; ++dir) {
+        transpose_whh_kernel<<<(G4 * H + 255) / 256, 256, 0, stream>>>(w->w_hh[l][dir], WT + (l * 2 + dir) * size_t(H) * G4);
+        RLT_CHECK_LAUNCH();
+      }
+  }
   for (int l = 0; l < 2; ++l) {
     const float* in = l == 0 ? x : y0;
     const int K = l == 0 ? F : 2 * H;
-    for (int dir = 0; dir < 2; ++dir)
-      RLT_TRY(input_projection(in, K, w->w_ih[l][dir], w->b_ih[l][dir], w->b_hh[l][dir], P + dir * G4, bias_scratch + dir * G4,
-                               T, stream));
+    const bool fused_in = tc && l == 0 && F <= 4;      // projection evaluated inside the recurrence: no P tensor
+    if (fused_in) {
+      // nothing to launch
+    } else if (tc && !small_k(K)) {
+      // both directions in ONE GEMM: [W_ih_fwd ; W_ih_rev] (1024 x K) and the summed biases are gathered into the
+      // workspace (the transposed-W_hh region is unused on this backend), so the input is read once
+      float* wcat = WT;
+      RLT_REQUIRE(size_t(2) * G4 * K <= 4 * size_t(H) * G4, RLT_UNSUPPORTED_SHAPE, "bilstm: input width %d too large", K);
+      for (int dir = 0; dir < 2; ++dir) {
+        RLT_CHECK_CUDA(cudaMemcpyAsync(wcat + size_t(dir) * G4 * K, w->w_ih[l][dir], size_t(G4) * K * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, stream));
+        RLT_CHECK_CUDA(cudaMemcpyAsync(bias_scratch + dir * G4, w->b_ih[l][dir], G4 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        copy_add_kernel<<<(G4 + 255) / 256, 256, 0, stream>>>(w->b_hh[l][dir], bias_scratch + dir * G4, G4);
+        RLT_CHECK_LAUNCH();
+      }
+      EpiParams ep{};
+      ep.alpha = 1.f; ep.out = P; ep.ldo = 2 * G4; ep.bias = bias_scratch;
+      RLT_TRY(gemm_tn(in, K, wcat, K, T, 2 * G4, K, ep, stream));
+    } else {
+      for (int dir = 0; dir < 2; ++dir)
+        RLT_TRY(input_projection(in, K, w->w_ih[l][dir], w->b_ih[l][dir], w->b_hh[l][dir], P + dir * G4, bias_scratch + dir * G4,
+                                 T, stream));
+    }
     float* out = l == 0 ? y0 : y;
     float* sv = saved ? saved + (l == 0 ? sl.s0 : sl.s1) : nullptr;
     time_begin(TAG_LSTM, stream);
-    if (lstm_backend() == 0) {
+    if (tc) {
       static bool attr = false;
       if (!attr) {
-        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            int(LstmUmFwdSmem::TOTAL)));
+        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             int(LstmUmFwdSmem::TOTAL)));
         attr = true;
       }
-      lstm_um_fwd_kernel<<<dim3((B + U_TILE - 1) / U_TILE, 2), U_THREADS, LstmUmFwdSmem::TOTAL, stream>>>(
-          P, w->w_hh[l][0], w->w_hh[l][1], out, sv, B, L);
+      LstmInProj inp{};
+      const dim3 grid((B + U_TILE - 1) / U_TILE, 2);
+      if (fused_in) {
+        inp.x = x; inp.F = F;
+        for (int dir = 0; dir < 2; ++dir) { inp.w_ih[dir] = w->w_ih[0][dir]; inp.b_ih[dir] = w->b_ih[0][dir]; inp.b_hh[dir] = w->b_hh[0][dir]; }
+        lstm_um_fwd_kernel<true><<<grid, U_THREADS, LstmUmFwdSmem::TOTAL, stream>>>(nullptr, inp, w->w_hh[l][0], w->w_hh[l][1],
+                                                                                   out, sv, B, L);
+      } else {
+        lstm_um_fwd_kernel<false><<<grid, U_THREADS, LstmUmFwdSmem::TOTAL, stream>>>(P, inp, w->w_hh[l][0], w->w_hh[l][1], out,
+                                                                                    sv, B, L);
+      }
     } else {
       lstm_rec_fwd_kernel<<<dim3(B, 2), H, 0, stream>>>(P, WT + (l * 2) * size_t(H) * G4, WT + (l * 2 + 1) * size_t(H) * G4,
                                                         out, sv, L);
@@ -335,11 +369,9 @@ int rlt_bilstm_bwd(const rlt_bilstm_desc* d, const rlt_bilstm_weights* w, const 
       // power-of-two scale that brings the incoming gradient into fp16's normal range (unscaled on read-back)
       unsigned int* amax = reinterpret_cast<unsigned int*>(colsum_scratch + 2 * G4);
       float* scale = colsum_scratch + 2 * G4 + 4;
-      RLT_CHECK_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), stream));
-      amax_abs_kernel<<<num_sms() * 4, 256, 0, stream>>>(dout, size_t(T) * 2 * H, amax);
-      RLT_CHECK_LAUNCH();
-      grad_scale_kernel<<<1, 1, 0, stream>>>(amax, scale);
-      RLT_CHECK_LAUNCH();
+      RLT_TRY(grad_scale(dout, size_t(T) * 2 * H, amax, scale, 6, stream));
+      // bias gradients (column sums of dA) are accumulated by the recurrence itself
+      RLT_CHECK_CUDA(cudaMemsetAsync(colsum_scratch, 0, 2 * G4 * sizeof(float), stream));
       static bool attr = false;
       if (!attr) {
         RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -347,15 +379,17 @@ int rlt_bilstm_bwd(const rlt_bilstm_desc* d, const rlt_bilstm_weights* w, const 
         attr = true;
       }
       lstm_um_bwd_kernel<<<dim3((B + U_TILE - 1) / U_TILE, 2), U_THREADS, LstmUmBwdSmem::TOTAL, stream>>>(
-          dout, sv, w->w_hh[l][0], w->w_hh[l][1], scale, dA, B, L);
+          dout, sv, w->w_hh[l][0], w->w_hh[l][1], scale, dA, colsum_scratch, B, L);
     } else {
       lstm_rec_bwd_kernel<<<dim3(B, 2), H, 0, stream>>>(dout, sv, w->w_hh[l][0], w->w_hh[l][1], dA, L);
     }
     time_end(TAG_LSTM, stream);
     RLT_CHECK_LAUNCH();
     // biases: db_ih = db_hh = column sums of dA
-    RLT_CHECK_CUDA(cudaMemsetAsync(colsum_scratch, 0, 2 * G4 * sizeof(float), stream));
-    RLT_TRY(colsum(dA, colsum_scratch, T, 2 * G4, stream));
+    if (lstm_backend() != 0) {
+      RLT_CHECK_CUDA(cudaMemsetAsync(colsum_scratch, 0, 2 * G4 * sizeof(float), stream));
+      RLT_TRY(colsum(dA, colsum_scratch, T, 2 * G4, stream));
+    }
     for (int dir = 0; dir < 2; ++dir) {
       copy_add_kernel<<<(G4 + 255) / 256, 256, 0, stream>>>(colsum_scratch + dir * G4, g->b_ih[l][dir], G4);
       RLT_CHECK_LAUNCH();

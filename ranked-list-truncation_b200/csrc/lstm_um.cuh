@@ -74,28 +74,6 @@ __device__ __forceinline__ unsigned short f32_to_f16_bits(float x) {
   return r;
 }
 
-// amax |x| over n floats -> *out (uint bits of a non-negative float; zero-initialised by the caller)
-__global__ void __launch_bounds__(256) amax_abs_kernel(const float* __restrict__ x, size_t n, unsigned int* __restrict__ out) {
-  float m = 0.f;
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(x[i]));
-#pragma unroll
-  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
-}
-// scale[0] = 2^k with amax * 2^k in [32, 64]; scale[1] = 2^-k   (1, 1 when amax is 0 or not finite)
-__global__ void grad_scale_kernel(const unsigned int* __restrict__ amax_bits, float* __restrict__ scale) {
-  const float a = __uint_as_float(*amax_bits);
-  float s = 1.f;
-  if (a > 0.f && a < 3.0e38f) {
-    int e;
-    frexpf(a, &e);              // a = m * 2^e, m in [0.5, 1)
-    s = ldexpf(1.f, 6 - e);     // a * s in [32, 64)
-  }
-  scale[0] = s;
-  scale[1] = 1.f / s;
-}
-
 struct LstmUmFwdSmem {
   static constexpr int W_BYTES = 2 * UG4 * 128;            // two k-blocks of [512 rows x 128 B]
   static constexpr int H_BYTES = 2 * U_HALF * 128;         // per half: two k-blocks of [32 rows x 128 B]
@@ -103,9 +81,21 @@ struct LstmUmFwdSmem {
   static constexpr size_t TOTAL = 1024 + W_BYTES + 2 * H_BYTES + C_BYTES + 256;
 };
 
+// Layer-0 input projection fused into the recurrence (kFusedIn): with F <= 4 input features (robust04: 3) the
+// pre-activation P_t = x_t W_ih^T + b_ih + b_hh is 12 FMAs per cell on values the thread keeps in registers, so the
+// [T, 1024] fp32 tensor P (4 KB per token written by a projection kernel and read back here) does not exist at all.
+struct LstmInProj {
+  const float* x;          // [B, L, F]
+  int F;                   // 1..4
+  const float* w_ih[2];    // [512, F] per direction
+  const float* b_ih[2];    // [512]
+  const float* b_hh[2];
+};
+
+template <bool kFusedIn>
 __global__ void __launch_bounds__(U_THREADS, 1)
-lstm_um_fwd_kernel(const float* __restrict__ P, const float* __restrict__ whh_f, const float* __restrict__ whh_r,
-                   float* __restrict__ y, float* __restrict__ saved, int B, int L) {
+lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __restrict__ whh_f,
+                   const float* __restrict__ whh_r, float* __restrict__ y, float* __restrict__ saved, int B, int L) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sW = smem;
@@ -180,7 +170,7 @@ lstm_um_fwd_kernel(const float* __restrict__ P, const float* __restrict__ whh_f,
     // pull the P rows (2 KB per list and step, contiguous) of the step that is kAhead ahead into L2, paced by the
     // accumulator barrier of the second half (own warp: never more than one phase behind)
     constexpr int kAhead = 2;
-    for (int step = 0; step < L; ++step) {
+    for (int step = 0; step < L && !kFusedIn; ++step) {
       if (step >= kAhead) mbar_wait(&bar_acc[1], (step - kAhead) & 1);
       const int t = dir ? (L - 1 - step) : step;
       for (int r = lane; r < U_TILE; r += 32) {
@@ -205,20 +195,44 @@ lstm_um_fwd_kernel(const float* __restrict__ P, const float* __restrict__ whh_f,
     const size_t p_list = size_t(L) * (2 * UG4);          // P stride between lists
     const size_t y_list = size_t(L) * (2 * UH);
     const size_t s_list = size_t(L) * (2 * USAVE * UH);
+    // fused input projection: this unit's four W_ih rows (F <= 4 columns, zero padded) and summed biases
+    float wi[4][4], bsum[4];
+    if (kFusedIn) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        bsum[q] = inp.b_ih[dir][q * UH + u] + inp.b_hh[dir][q * UH + u];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) wi[q][f] = f < inp.F ? inp.w_ih[dir][size_t(q * UH + u) * inp.F + f] : 0.f;
+      }
+    }
+    // pre-activations of U_CHUNK lists starting at cell c0: from P, or from x (the same 3 floats for every lane: broadcast)
+    auto load_pre = [&](float (&dst)[4][U_CHUNK], int c0, int t) {
+#pragma unroll
+      for (int li = 0; li < U_CHUNK; ++li) {
+        const bool live = list0 + c0 + li < B;
+        if (kFusedIn) {
+          const float* xr = inp.x + (size_t(live ? list0 + c0 + li : 0) * L + t) * inp.F;
+          float xv[4];
+#pragma unroll
+          for (int f = 0; f < 4; ++f) xv[f] = (live && f < inp.F) ? __ldg(xr + f) : 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q][li] = fmaf(xv[3], wi[q][3], fmaf(xv[2], wi[q][2], fmaf(xv[1], wi[q][1], fmaf(xv[0], wi[q][0], bsum[q]))));
+        } else {
+          const float* p0 = P + (size_t(list0) * L + t) * (2 * UG4) + dir * UG4 + u;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q][li] = live ? __ldg(p0 + (c0 + li) * p_list + q * UH) : 0.f;
+        }
+      }
+    };
 
     for (int step = 0; step < L; ++step) {
       const int t = dir ? (L - 1 - step) : step;
       const int tn = dir ? (t - 1) : (t + 1);            // time index of the next step (for its h_{t-1} plane)
-      const float* p0 = P + (size_t(list0) * L + t) * (2 * UG4) + dir * UG4 + u;
       float* y0 = y + (size_t(list0) * L + t) * (2 * UH) + dir * UH + u;
       float* s0 = saved ? saved + ((size_t(list0) * L + t) * 2 + dir) * (USAVE * UH) + u : nullptr;
       float pc[4][U_CHUNK];
-#pragma unroll
-      for (int li = 0; li < U_CHUNK; ++li) {
-        const bool live = list0 + li < B;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) pc[q][li] = live ? __ldg(p0 + li * p_list + q * UH) : 0.f;
-      }
+      load_pre(pc, 0, t);
       mbar_wait(&bar_acc[hf], step & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -227,14 +241,7 @@ lstm_um_fwd_kernel(const float* __restrict__ P, const float* __restrict__ whh_f,
 #pragma unroll
         for (int q = 0; q < 4; ++q) tmem_ld4(t_lane + q * U_HALF + ch * U_CHUNK, a[q]);
         float pn[4][U_CHUNK];
-        if (ch + 1 < U_CELLS / U_CHUNK) {
-#pragma unroll
-          for (int li = 0; li < U_CHUNK; ++li) {
-            const bool live = list0 + (ch + 1) * U_CHUNK + li < B;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) pn[q][li] = live ? __ldg(p0 + ((ch + 1) * U_CHUNK + li) * p_list + q * UH) : 0.f;
-          }
-        }
+        if (ch + 1 < U_CELLS / U_CHUNK) load_pre(pn, (ch + 1) * U_CHUNK, t);
 #pragma unroll
         for (int li = 0; li < U_CHUNK; ++li) {
           const int cell = ch * U_CHUNK + li;
@@ -291,8 +298,8 @@ struct LstmUmBwdSmem {
 
 __global__ void __launch_bounds__(U_THREADS, 1)
 lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved, const float* __restrict__ whh_f,
-                   const float* __restrict__ whh_r, const float* __restrict__ scale_ptr, float* __restrict__ dA, int B,
-                   int L) {
+                   const float* __restrict__ whh_r, const float* __restrict__ scale_ptr, float* __restrict__ dA,
+                   float* __restrict__ db /* [2][512] += column sums of dA (bias gradients) */, int B, int L) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sW = smem;
@@ -393,6 +400,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
     const size_t s_list = size_t(L) * (2 * USAVE * UH);
     const size_t y_list = size_t(L) * (2 * UH);
     const size_t a_list = size_t(L) * (2 * UG4);
+    float dbs[4] = {0.f, 0.f, 0.f, 0.f};                // this unit's share of db = sum over (list, t) of da
 
     for (int it = 0; it < L; ++it) {
       const int step = L - 1 - it;                      // forward step index being differentiated
@@ -454,6 +462,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
           if (live) {
             float* o = da0 + cell * a_list;
             o[0 * UH] = dai; o[1 * UH] = daf; o[2 * UH] = dag; o[3 * UH] = dao;
+            dbs[0] += dai; dbs[1] += daf; dbs[2] += dag; dbs[3] += dao;
           }
           const int r = row0 + cell;
           uint8_t* dst = dabase + (r >> 3) * 1024 + (r & 7) * 128 + (((dunit ^ r) & 7) << 4);
@@ -470,6 +479,10 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&bar_da[hf]);
+    }
+    if (db != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) atomicAdd(db + dir * UG4 + q * UH + u, dbs[q]);
     }
   }
   tc_fence_before();
