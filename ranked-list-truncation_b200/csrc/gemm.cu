@@ -12,6 +12,7 @@
 
 #include "common.h"
 #include "gemm_tc.cuh"
+#include "gemm_f16out.cuh"
 
 namespace rlt {
 
@@ -38,7 +39,8 @@ static int g_gemm_backend = env_int("RLT_GEMM_BACKEND", 0);
 // exact ties), so operands stay exact fp32 in HBM and no rounded copies are materialised.  Without it the
 // tensor core would truncate the low 13 mantissa bits (a systematic -2^-11 relative bias per operand).
 static int g_tma_round = env_int("RLT_TMA_ROUND", 1);
-static int g_b_resident = env_int("RLT_B_RESIDENT", 1);   // gemm_tn: keep the CTA's B slice in shared memory when it fits
+static int g_b_resident = env_int("RLT_B_RESIDENT", 1);
+static int g_f16out_tma = env_int("RLT_F16OUT_TMA", 1);     // copy-engine epilogue kernel for the fp16-output GEMMs   // gemm_tn: keep the CTA's B slice in shared memory when it fits
 
 static std::atomic<unsigned long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -97,7 +99,8 @@ static EncodeTiledFn encode_fn() {
 // 2-D row-major matrix [rows, cols] with leading dimension ld (elements); box = box_rows x (128 bytes of columns:
 // 32 fp32 or 64 fp16), SWIZZLE_128B (or the 32-byte-atom variant for MN-major fp32 operands), zero fill outside.
 static int make_tmap_any(CUtensorMap* out, const void* base, int elem_bytes, CUtensorMapDataType dtype, uint64_t rows,
-                         uint64_t cols, uint64_t ld, uint32_t box_rows, bool atom32) {
+                         uint64_t cols, uint64_t ld, uint32_t box_rows, bool atom32, uint32_t box_cols = 0,
+                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   RLT_REQUIRE(fn != nullptr, RLT_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from the driver");
   RLT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * elem_bytes) % 16 == 0, RLT_INVALID_ARG,
@@ -105,10 +108,10 @@ static int make_tmap_any(CUtensorMap* out, const void* base, int elem_bytes, CUt
               "(ptr=%p ld=%llu)", base, (unsigned long long)ld);
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {ld * elem_bytes};
-  const cuuint32_t box[2] = {cuuint32_t(128 / elem_bytes), box_rows};
+  const cuuint32_t box[2] = {box_cols ? box_cols : cuuint32_t(128 / elem_bytes), box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
   const CUresult r = fn(out, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RLT_REQUIRE(r == CUDA_SUCCESS, RLT_CUDA_ERROR, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
   return RLT_OK;
@@ -292,10 +295,49 @@ int gemm_nn(const float* A, int lda, const float* B, int ldb, int M, int N, int 
   if (gemm_backend() == 1) return gemm_simt(A, lda, B, ldb, M, N, K, ep, stream, 1);
   return gemm_any<OP_TF32_N>(A, lda, B, ldb, M, N, K, ep, stream);
 }
+// fp16 operands AND fp16 output, K <= 128, N % 256 == 0: the copy-engine epilogue kernel (gemm_f16out.cuh)
+template <int EF>
+static int launch_f16out(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const EpiParams& ep,
+                         cudaStream_t stream) {
+  using Cfg = GemmF16OutCfg;
+  CUtensorMap tmA, tmB, tmOut, tmGate;
+  RLT_TRY(make_tmap_h(&tmA, A, M, K, lda, Cfg::BM));
+  RLT_TRY(make_tmap_h(&tmB, B, N, K, ldb, Cfg::BN));
+  RLT_TRY(make_tmap_any(&tmOut, ep.out_h, 2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, ep.ldo, 32, false, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  tmGate = tmOut;
+  if (ep.gate_h != nullptr)
+    RLT_TRY(make_tmap_any(&tmGate, ep.gate_h, 2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, ep.ldo, 32, false, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16out_kernel<EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
+    attr_set = true;
+  }
+  const int tiles_m = (M + Cfg::BM - 1) / Cfg::BM, tiles_n = N / Cfg::BN;
+  RLT_REQUIRE(tiles_n <= num_sms(), RLT_UNSUPPORTED_SHAPE, "gemm: N=%d needs more column blocks than there are SMs", N);
+  int walkers = num_sms() / tiles_n;
+  if (walkers > tiles_m) walkers = tiles_m;
+  time_begin(ep.tag, stream);
+  gemm_f16out_kernel<EF><<<walkers * tiles_n, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmGate, M, N, K, ep);
+  time_end(ep.tag, stream);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+
 int gemm_tn_h(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const EpiParams& ep,
               cudaStream_t stream) {
   RLT_REQUIRE(gemm_backend() == 0, RLT_INVALID_ARG, "gemm_tn_h: fp16 operands exist only on the tensor-core backend");
   RLT_REQUIRE(K % 8 == 0, RLT_UNSUPPORTED_SHAPE, "gemm_tn_h: K=%d must be a multiple of 8", K);
+  if (g_f16out_tma != 0 && ep.out_h != nullptr && K <= 128 && N % 256 == 0 && ep.ldo % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(ep.out_h) & 15) == 0) {
+    switch (epi_mask(ep)) {
+      case (EF_BIAS | EF_RELU | EF_OUT_H): return launch_f16out<EF_BIAS | EF_RELU | EF_OUT_H>(A, lda, B, ldb, M, N, K, ep, stream);
+      case (EF_BIAS | EF_RELU | EF_OUT_H | EF_DROP):
+        return launch_f16out<EF_BIAS | EF_RELU | EF_OUT_H | EF_DROP>(A, lda, B, ldb, M, N, K, ep, stream);
+      case (EF_GATE_H | EF_COLSUM | EF_OUT_H | EF_SCALE):
+        return launch_f16out<EF_GATE_H | EF_COLSUM | EF_OUT_H | EF_SCALE>(A, lda, B, ldb, M, N, K, ep, stream);
+      default: break;
+    }
+  }
   return gemm_any<OP_F16_K>(A, lda, B, ldb, M, N, K, ep, stream);
 }
 
@@ -596,6 +638,7 @@ int rlt_set_option(const char* key, int value) {
   if (strcmp(key, "gemm_backend") == 0) { g_gemm_backend = value; return RLT_OK; }
   if (strcmp(key, "tma_round") == 0) { g_tma_round = value; return RLT_OK; }
   if (strcmp(key, "b_resident") == 0) { g_b_resident = value; return RLT_OK; }
+  if (strcmp(key, "f16out_tma") == 0) { g_f16out_tma = value; return RLT_OK; }
   return set_error(RLT_INVALID_ARG, "rlt_set_option: unknown option '%s'", key);
 }
 int rlt_get_option(const char* key) {
@@ -603,6 +646,7 @@ int rlt_get_option(const char* key) {
   if (strcmp(key, "gemm_backend") == 0) return g_gemm_backend;
   if (strcmp(key, "tma_round") == 0) return g_tma_round;
   if (strcmp(key, "b_resident") == 0) return g_b_resident;
+  if (strcmp(key, "f16out_tma") == 0) return g_f16out_tma;
   if (strcmp(key, "time_tag") == 0) return g_time_tag;
   if (strcmp(key, "lstm_backend") == 0) return lstm_backend();
   return set_error(RLT_INVALID_ARG, "rlt_get_option: unknown option '%s'", key);
