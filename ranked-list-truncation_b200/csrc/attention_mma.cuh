@@ -77,6 +77,27 @@ __device__ __forceinline__ void tile_pB(const float (&p)[NT][4], const float* __
   }
 }
 
+// acc[n] (16 x 8 tiles over the head dim) += T[0 : 8*NT, c0 : c0+16]^T * B[0 : 8*NT, 0:DH]: the A operand is read
+// TRANSPOSED from a [rows][PP] shared-memory matrix (PP % 16 == 4: conflict-free), B rows with pitch DH + 4.  The
+// contraction index is permuted (slot t <-> row 8ks+2t, slot t+4 <-> row 8ks+2t+1) so that both loads are conflict-free.
+template <int DH, int NT>
+__device__ __forceinline__ void tile_tAB(const float* __restrict__ sT, int PP, int c0, const float* __restrict__ sB,
+                                         float (&acc)[DH / 8][4], int lane) {
+  constexpr int P = DH + 4;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < NT; ++ks) {
+    const float* r0 = sT + (ks * 8 + 2 * t) * PP + c0 + g;
+    const uint32_t a0 = tf32_bits(r0[0]), a1 = tf32_bits(r0[8]), a2 = tf32_bits(r0[PP]), a3 = tf32_bits(r0[PP + 8]);
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      const uint32_t b0 = tf32_bits(sB[(ks * 8 + 2 * t) * P + n * 8 + g]);
+      const uint32_t b1 = tf32_bits(sB[(ks * 8 + 2 * t + 1) * P + n * 8 + g]);
+      mma_tf32(acc[n], a0, a1, a2, a3, b0, b1);
+    }
+  }
+}
+
 // cooperative load of one head's rows of a [T, ld] matrix into shared memory [rows_pad][DH+4]; rows >= S are zero
 template <int DH>
 __device__ __forceinline__ void load_head_rows(float* __restrict__ dst, const float* __restrict__ src, size_t tok0, int L,
@@ -426,7 +447,8 @@ __global__ void __launch_bounds__(128) attn_lists_fwd_pipe_kernel(const float* _
 }
 
 // Backward.  D_i = sum_j P_ij dP_ij (= dO_i . O_i) is taken from the phase-A fragments, so the attention output is not
-// read at all.
+// read at all.  Phase A leaves P (dropped) and dS in shared memory; phase B contracts them TRANSPOSED with Q / dO for
+// dK / dV instead of recomputing the scores a second time (the kernel is instruction-issue bound).
 template <int DH, int NT, bool kDrop>
 __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* __restrict__ qkv, const float* __restrict__ lse,
                                                                   const float* __restrict__ d_o, float* __restrict__ dqkv,
@@ -435,10 +457,12 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
   constexpr int P = DH + 4;
   constexpr int ROWS = NT * 8;
   constexpr int BUF = 4 * ROWS * P + ROWS;      // q, k, v, dO rows + lse
+  constexpr int PP = ROWS + 4;                  // pitch of the probability / dS matrices (== 4 mod 16)
   extern __shared__ float sm[];
-  float* sD = sm + 2 * BUF;                     // [ROWS], shared by both buffers (rewritten per item)
+  float* sPm = sm + 2 * BUF;                    // [ROWS][PP] (dropped) probabilities of the current item
+  float* sS = sPm + ROWS * PP;                  // [ROWS][PP] dS of the current item
   const int ld = 3 * d;
-  for (int i = threadIdx.x; i < 2 * BUF; i += blockDim.x) sm[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * BUF + 2 * ROWS * PP; i += blockDim.x) sm[i] = 0.f;   // padded rows stay zero
   __syncthreads();
   for (int b = 0; b < 2; ++b)
     for (int s_ = S + threadIdx.x; s_ < ROWS; s_ += blockDim.x) sm[b * BUF + 4 * ROWS * P + s_] = INFINITY;  // padded queries: P = 0
@@ -470,7 +494,7 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
     const float* sV = sK + ROWS * P;
     const float* sG = sV + ROWS * P;
     const float* sL = sG + ROWS * P;            // natural-log lse
-    // ---------------- phase A: query tiles -> D, dQ
+    // ---------------- phase A: query tiles -> P, dS (kept in shared memory for phase B), dQ
     for (int r0 = warp * 16; r0 < S; r0 += 64) {
       float p[NT][4], dp[NT][4];
 #pragma unroll
@@ -480,17 +504,10 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
       }
       tile_abT<DH, NT, true>(sQ, r0, sK, p, lane);
       tile_abT<DH, NT, false>(sG, r0, sV, dp, lane);
-      if (kDrop) {   // d(attn) = mask/(1-p) * d(dropped attn)
-        const uint64_t ea = (uint64_t(item) * S + r0 + gq) * S, eb = (uint64_t(item) * S + r0 + gq + 8) * S;
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          const uint64_t ba = drop_bits(drop.seed, DROP_ATTN, ea + j * 8 + 2 * t), bb = drop_bits(drop.seed, DROP_ATTN, eb + j * 8 + 2 * t);
-          dp[j][0] *= drop_factor(ba, 0, drop.thr, drop.scale); dp[j][1] *= drop_factor(ba, 1, drop.thr, drop.scale);
-          dp[j][2] *= drop_factor(bb, 0, drop.thr, drop.scale); dp[j][3] *= drop_factor(bb, 1, drop.thr, drop.scale);
-        }
-      }
       const float la = sL[r0 + gq] * kLog2e, lb = sL[r0 + gq + 8] * kLog2e;
       float da = 0.f, db = 0.f;
+      float* pa_row = sPm + (r0 + gq) * PP + 2 * t;
+      float* pb_row = pa_row + 8 * PP;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         const int c = j * 8 + 2 * t;
@@ -499,16 +516,29 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
         p[j][1] = ok1 ? exp2f(fmaf(p[j][1], sc, -la)) : 0.f;
         p[j][2] = ok0 ? exp2f(fmaf(p[j][2], sc, -lb)) : 0.f;
         p[j][3] = ok1 ? exp2f(fmaf(p[j][3], sc, -lb)) : 0.f;
+        float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;
+        if (kDrop) {   // d(attn) = mask/(1-p) * d(dropped attn); dV sees the dropped probabilities
+          const uint64_t ba = drop_bits(drop.seed, DROP_ATTN, (uint64_t(item) * S + r0 + gq) * S + c);
+          const uint64_t bb = drop_bits(drop.seed, DROP_ATTN, (uint64_t(item) * S + r0 + gq + 8) * S + c);
+          m0 = drop_factor(ba, 0, drop.thr, drop.scale); m1 = drop_factor(ba, 1, drop.thr, drop.scale);
+          m2 = drop_factor(bb, 0, drop.thr, drop.scale); m3 = drop_factor(bb, 1, drop.thr, drop.scale);
+          dp[j][0] *= m0; dp[j][1] *= m1; dp[j][2] *= m2; dp[j][3] *= m3;
+        }
+        *reinterpret_cast<float2*>(pa_row + j * 8) = make_float2(p[j][0] * m0, p[j][1] * m1);
+        *reinterpret_cast<float2*>(pb_row + j * 8) = make_float2(p[j][2] * m2, p[j][3] * m3);
         da = fmaf(p[j][0], dp[j][0], fmaf(p[j][1], dp[j][1], da));
         db = fmaf(p[j][2], dp[j][2], fmaf(p[j][3], dp[j][3], db));
       }
       da += __shfl_xor_sync(0xffffffffu, da, 1); da += __shfl_xor_sync(0xffffffffu, da, 2);
       db += __shfl_xor_sync(0xffffffffu, db, 1); db += __shfl_xor_sync(0xffffffffu, db, 2);
-      if (t == 0) { sD[r0 + gq] = da; sD[r0 + gq + 8] = db; }
+      float* sa_row = sS + (r0 + gq) * PP + 2 * t;
+      float* sb_row = sa_row + 8 * PP;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         p[j][0] *= dp[j][0] - da; p[j][1] *= dp[j][1] - da;
         p[j][2] *= dp[j][2] - db; p[j][3] *= dp[j][3] - db;
+        *reinterpret_cast<float2*>(sa_row + j * 8) = make_float2(p[j][0], p[j][1]);
+        *reinterpret_cast<float2*>(sb_row + j * 8) = make_float2(p[j][2], p[j][3]);
       }
       float acc[DH / 8][4];
 #pragma unroll
@@ -528,44 +558,17 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
           *reinterpret_cast<float2*>(out + n * 8 + 2 * t) = make_float2(acc[n][2] * scale, acc[n][3] * scale);
       }
     }
-    __syncthreads();   // sD complete
-    // ---------------- phase B: key tiles (transposed products) -> dK, dV
+    __syncthreads();   // P and dS complete
+    // ---------------- phase B: key tiles -> dK = dS^T Q, dV = (dropped P)^T dO, operands read transposed from smem
     for (int c0 = warp * 16; c0 < S; c0 += 64) {
-      float p[NT][4], dp[NT][4];
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        p[j][0] = p[j][1] = p[j][2] = p[j][3] = 0.f;
-        dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
-      }
-      tile_abT<DH, NT, true>(sK, c0, sQ, p, lane);     // [key, query] raw scores
-      tile_abT<DH, NT, false>(sV, c0, sG, dp, lane);   // [key, query] dP^T
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const int i = j * 8 + 2 * t;                    // query index of columns 0/2 ; i+1 for columns 1/3
-        const float l0 = sL[i] * kLog2e, l1 = sL[i + 1] * kLog2e, d0 = sD[i], d1 = sD[i + 1];
-        const float p0 = exp2f(fmaf(p[j][0], sc, -l0)), p1 = exp2f(fmaf(p[j][1], sc, -l1));
-        const float p2 = exp2f(fmaf(p[j][2], sc, -l0)), p3 = exp2f(fmaf(p[j][3], sc, -l1));
-        float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;   // dropout factors of (query i / i+1, key c0+gq / +8)
-        if (kDrop) {
-          const int ka_ = c0 + gq, kb_ = c0 + gq + 8;
-          const uint64_t q0 = (uint64_t(item) * S + i) * S, q1 = (uint64_t(item) * S + i + 1) * S;
-          m0 = drop_factor(drop_bits(drop.seed, DROP_ATTN, q0 + (ka_ & ~1)), ka_ & 1, drop.thr, drop.scale);
-          m1 = drop_factor(drop_bits(drop.seed, DROP_ATTN, q1 + (ka_ & ~1)), ka_ & 1, drop.thr, drop.scale);
-          m2 = drop_factor(drop_bits(drop.seed, DROP_ATTN, q0 + (kb_ & ~1)), kb_ & 1, drop.thr, drop.scale);
-          m3 = drop_factor(drop_bits(drop.seed, DROP_ATTN, q1 + (kb_ & ~1)), kb_ & 1, drop.thr, drop.scale);
-        }
-        p[j][0] = p0 * m0; p[j][1] = p1 * m1; p[j][2] = p2 * m2; p[j][3] = p3 * m3;   // (dropped P)^T; 0 for padded queries
-        dp[j][0] = p0 * (dp[j][0] * m0 - d0); dp[j][1] = p1 * (dp[j][1] * m1 - d1);     // dS^T
-        dp[j][2] = p2 * (dp[j][2] * m2 - d0); dp[j][3] = p3 * (dp[j][3] * m3 - d1);
-      }
       float ak[DH / 8][4], av[DH / 8][4];
 #pragma unroll
       for (int n = 0; n < DH / 8; ++n) {
         ak[n][0] = ak[n][1] = ak[n][2] = ak[n][3] = 0.f;
         av[n][0] = av[n][1] = av[n][2] = av[n][3] = 0.f;
       }
-      tile_pB<DH, NT>(dp, sQ, ak, lane);
-      tile_pB<DH, NT>(p, sG, av, lane);
+      tile_tAB<DH, NT>(sS, PP, c0, sQ, ak, lane);
+      tile_tAB<DH, NT>(sPm, PP, c0, sG, av, lane);
       const int ka = c0 + gq, kb = c0 + gq + 8;
       if (ka < S) {
         float* outk = dqkv + (it.tok0 + size_t(ka) * L) * ld + d + it.h * DH;

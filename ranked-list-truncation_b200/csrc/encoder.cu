@@ -424,7 +424,7 @@ static int attention_fwd_mma(const float* qkv, float* o, float* lse, int G, int 
 template <int DH, int NT, bool kDrop>
 static int attention_bwd_launch(const float* qkv, const float* lse, const float* d_o, float* dqkv, int G, int S, int L, int d,
                                 int n_head, float scale, cudaStream_t stream, DropCfg drop) {
-  const size_t smem = (size_t(2) * (4 * NT * 8 * (DH + 4) + NT * 8) + NT * 8) * sizeof(float);
+  const size_t smem = (size_t(2) * (4 * NT * 8 * (DH + 4) + NT * 8) + size_t(2) * NT * 8 * (NT * 8 + 4)) * sizeof(float);
   static bool attr_set = false;
   static int per_sm = 0;
   if (!attr_set) {
