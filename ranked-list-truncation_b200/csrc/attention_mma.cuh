@@ -449,7 +449,9 @@ __global__ void __launch_bounds__(128) attn_lists_fwd_pipe_kernel(const float* _
 // Backward.  D_i = sum_j P_ij dP_ij (= dO_i . O_i) is taken from the phase-A fragments, so the attention output is not
 // read at all.  Phase A leaves P (dropped) and dS in shared memory; phase B contracts them TRANSPOSED with Q / dO for
 // dK / dV instead of recomputing the scores a second time (the kernel is instruction-issue bound).
-template <int DH, int NT, bool kDrop>
+// kBufs: 2 = cp.async double buffer over items; 1 = single staging buffer (large head dims: two buffers would leave room
+// for ONE CTA per SM; a second resident CTA hides the staging latency instead)
+template <int DH, int NT, bool kDrop, int kBufs>
 __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* __restrict__ qkv, const float* __restrict__ lse,
                                                                   const float* __restrict__ d_o, float* __restrict__ dqkv,
                                                                   int S, int L, int d, int n_head, float scale,
@@ -459,12 +461,12 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
   constexpr int BUF = 4 * ROWS * P + ROWS;      // q, k, v, dO rows + lse
   constexpr int PP = ROWS + 4;                  // pitch of the probability / dS matrices (== 4 mod 16)
   extern __shared__ float sm[];
-  float* sPm = sm + 2 * BUF;                    // [ROWS][PP] (dropped) probabilities of the current item
+  float* sPm = sm + kBufs * BUF;                // [ROWS][PP] (dropped) probabilities of the current item
   float* sS = sPm + ROWS * PP;                  // [ROWS][PP] dS of the current item
   const int ld = 3 * d;
-  for (int i = threadIdx.x; i < 2 * BUF + 2 * ROWS * PP; i += blockDim.x) sm[i] = 0.f;   // padded rows stay zero
+  for (int i = threadIdx.x; i < kBufs * BUF + 2 * ROWS * PP; i += blockDim.x) sm[i] = 0.f;   // padded rows stay zero
   __syncthreads();
-  for (int b = 0; b < 2; ++b)
+  for (int b = 0; b < kBufs; ++b)
     for (int s_ = S + threadIdx.x; s_ < ROWS; s_ += blockDim.x) sm[b * BUF + 4 * ROWS * P + s_] = INFINITY;  // padded queries: P = 0
   __syncthreads();
   auto stage = [&](long long item, int b) {
@@ -482,11 +484,16 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
   const int gq = lane >> 2, t = lane & 3;
   const float sc = scale * kLog2e;
   long long item = blockIdx.x;
-  if (item < n_items) stage(item, 0);
+  if (kBufs == 2 && item < n_items) stage(item, 0);
   int b = 0;
-  for (; item < n_items; item += gridDim.x, b ^= 1) {
-    const long long nxt = item + gridDim.x;
-    if (nxt < n_items) { stage(nxt, b ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+  for (; item < n_items; item += gridDim.x, b ^= (kBufs - 1)) {
+    if (kBufs == 2) {
+      const long long nxt = item + gridDim.x;
+      if (nxt < n_items) { stage(nxt, b ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    } else {
+      stage(item, 0);
+      cp_async_wait<0>();
+    }
     __syncthreads();
     const AttnItem it = attn_item(item, S, L, n_head);
     const float* sQ = sm + b * BUF;

@@ -424,12 +424,16 @@ static int attention_fwd_mma(const float* qkv, float* o, float* lse, int G, int 
 template <int DH, int NT, bool kDrop>
 static int attention_bwd_launch(const float* qkv, const float* lse, const float* d_o, float* dqkv, int G, int S, int L, int d,
                                 int n_head, float scale, cudaStream_t stream, DropCfg drop) {
-  const size_t smem = (size_t(2) * (4 * NT * 8 * (DH + 4) + NT * 8) + size_t(2) * NT * 8 * (NT * 8 + 4)) * sizeof(float);
+  // double-buffered staging when two buffers still leave room for two CTAs per SM, else one buffer
+  constexpr size_t kBuf = (4 * NT * 8 * (DH + 4) + NT * 8) * sizeof(float);
+  constexpr size_t kPS = size_t(2) * NT * 8 * (NT * 8 + 4) * sizeof(float);
+  constexpr int kBufs = (2 * kBuf + kPS <= 110 * 1024) ? 2 : 1;
+  constexpr size_t smem = kBufs * kBuf + kPS;
   static bool attr_set = false;
   static int per_sm = 0;
   if (!attr_set) {
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_pipe_kernel<DH, NT, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_bwd_pipe_kernel<DH, NT, kDrop>, 128, smem));
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_pipe_kernel<DH, NT, kDrop, kBufs>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_bwd_pipe_kernel<DH, NT, kDrop, kBufs>, 128, smem));
     if (per_sm < 1) per_sm = 1;
     attr_set = true;
   }
@@ -437,7 +441,7 @@ static int attention_bwd_launch(const float* qkv, const float* lse, const float*
   long long grid = (long long)num_sms() * per_sm;
   if (grid > n_items) grid = n_items;
   time_begin(TAG_ATTN_BWD, stream);
-  attn_lists_bwd_pipe_kernel<DH, NT, kDrop><<<int(grid), 128, smem, stream>>>(qkv, lse, d_o, dqkv, S, L, d, n_head, scale, n_items, drop);
+  attn_lists_bwd_pipe_kernel<DH, NT, kDrop, kBufs><<<int(grid), 128, smem, stream>>>(qkv, lse, d_o, dqkv, S, L, d, n_head, scale, n_items, drop);
   time_end(TAG_ATTN_BWD, stream);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
