@@ -250,6 +250,7 @@ static int launch_tn(const void* A, int lda, const void* B, int ldb, int M, int 
       RLT_EF_CASE(EF_GATE | EF_COLSUM);
       RLT_EF_CASE(EF_RES);
       RLT_EF_CASE(EF_ACC);
+      RLT_EF_CASE(EF_RES | EF_ACC);                                 // dX of an expert that shares its input (MMOECut)
       RLT_EF_CASE(EF_BIAS | EF_RELU | EF_OUT_H);                    // FFN1 -> fp16 hidden
       RLT_EF_CASE(EF_GATE_H | EF_COLSUM | EF_OUT_H | EF_SCALE);     // dH = s (dU W2) [h > 0] -> fp16
       RLT_EF_CASE(EF_RES | EF_SCALE);                               // dY = dU + (dH W1) / s
@@ -296,10 +297,10 @@ int gemm_nn(const float* A, int lda, const float* B, int ldb, int M, int N, int 
   return gemm_any<OP_TF32_N>(A, lda, B, ldb, M, N, K, ep, stream);
 }
 // fp16 operands AND fp16 output, K <= 128, N % 256 == 0: the copy-engine epilogue kernel (gemm_f16out.cuh)
-template <int EF>
+template <int BN, int EF>
 static int launch_f16out(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const EpiParams& ep,
                          cudaStream_t stream) {
-  using Cfg = GemmF16OutCfg;
+  using Cfg = GemmF16OutCfg<BN>;
   CUtensorMap tmA, tmB, tmOut, tmGate;
   RLT_TRY(make_tmap_h(&tmA, A, M, K, lda, Cfg::BM));
   RLT_TRY(make_tmap_h(&tmB, B, N, K, ldb, Cfg::BN));
@@ -309,7 +310,7 @@ static int launch_f16out(const __half* A, int lda, const __half* B, int ldb, int
     RLT_TRY(make_tmap_any(&tmGate, ep.gate_h, 2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, ep.ldo, 32, false, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   static bool attr_set = false;
   if (!attr_set) {
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16out_kernel<EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16out_kernel<BN, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
     attr_set = true;
   }
   const int tiles_m = (M + Cfg::BM - 1) / Cfg::BM, tiles_n = N / Cfg::BN;
@@ -317,7 +318,7 @@ static int launch_f16out(const __half* A, int lda, const __half* B, int ldb, int
   int walkers = num_sms() / tiles_n;
   if (walkers > tiles_m) walkers = tiles_m;
   time_begin(ep.tag, stream);
-  gemm_f16out_kernel<EF><<<walkers * tiles_n, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmGate, M, N, K, ep);
+  gemm_f16out_kernel<BN, EF><<<walkers * tiles_n, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmGate, M, N, K, ep);
   time_end(ep.tag, stream);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
@@ -327,16 +328,23 @@ int gemm_tn_h(const __half* A, int lda, const __half* B, int ldb, int M, int N, 
               cudaStream_t stream) {
   RLT_REQUIRE(gemm_backend() == 0, RLT_INVALID_ARG, "gemm_tn_h: fp16 operands exist only on the tensor-core backend");
   RLT_REQUIRE(K % 8 == 0, RLT_UNSUPPORTED_SHAPE, "gemm_tn_h: K=%d must be a multiple of 8", K);
-  if (g_f16out_tma != 0 && ep.out_h != nullptr && K <= 128 && N % 256 == 0 && ep.ldo % 8 == 0 &&
+  if (g_f16out_tma != 0 && ep.out_h != nullptr && K <= 256 && N % 256 == 0 && ep.ldo % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(ep.out_h) & 15) == 0) {
-    switch (epi_mask(ep)) {
-      case (EF_BIAS | EF_RELU | EF_OUT_H): return launch_f16out<EF_BIAS | EF_RELU | EF_OUT_H>(A, lda, B, ldb, M, N, K, ep, stream);
-      case (EF_BIAS | EF_RELU | EF_OUT_H | EF_DROP):
-        return launch_f16out<EF_BIAS | EF_RELU | EF_OUT_H | EF_DROP>(A, lda, B, ldb, M, N, K, ep, stream);
-      case (EF_GATE_H | EF_COLSUM | EF_OUT_H | EF_SCALE):
-        return launch_f16out<EF_GATE_H | EF_COLSUM | EF_OUT_H | EF_SCALE>(A, lda, B, ldb, M, N, K, ep, stream);
+#define RLT_F16OUT(mask)                                                                                    \
+  case (mask):                                                                                              \
+    return K <= 128 ? launch_f16out<256, (mask)>(A, lda, B, ldb, M, N, K, ep, stream)                       \
+                    : launch_f16out<128, (mask)>(A, lda, B, ldb, M, N, K, ep, stream)
+    // measured at d_model 256 (K = 256, BN = 128 tiles): the gated dH GEMM gains (3.36 -> 2.63 ms), the plain FFN1 store
+    // does not (1.75 -> 2.13 ms: 32 KB tiles, per-tile overheads) and stays on gemm_tn_kernel<256>
+    const int mask = epi_mask(ep);
+    const bool plain = (mask & EF_GATE_H) == 0;
+    switch ((plain && K > 128) ? -1 : mask) {
+      RLT_F16OUT(EF_BIAS | EF_RELU | EF_OUT_H);
+      RLT_F16OUT(EF_BIAS | EF_RELU | EF_OUT_H | EF_DROP);
+      RLT_F16OUT(EF_GATE_H | EF_COLSUM | EF_OUT_H | EF_SCALE);
       default: break;
     }
+#undef RLT_F16OUT
   }
   return gemm_any<OP_F16_K>(A, lda, B, ldb, M, N, K, ep, stream);
 }

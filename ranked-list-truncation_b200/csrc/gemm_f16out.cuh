@@ -16,11 +16,13 @@
 
 namespace rlt {
 
+// BN = 256 for K <= 128 (d_model 128), BN = 128 for K <= 256 (d_model 256): the resident B slice is 64 KB either way.
+template <int BN_>
 struct GemmF16OutCfg {
-  static constexpr int BM = 128, BN = 256, BKE = 64;
+  static constexpr int BM = 128, BN = BN_, BKE = 64;
   static constexpr int A_BYTES = BM * 128;                 // one k-block: 128 rows x 128 B
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int MAX_KB = 2;                         // K <= 128
+  static constexpr int MAX_KB = 64 * 1024 / B_BYTES;       // 2 (K <= 128) or 4 (K <= 256)
   static constexpr int A_STAGES = 3;
   static constexpr int EPI_WARPS = 16;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
@@ -36,12 +38,12 @@ struct GemmF16OutCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <int EF>
-__global__ void __launch_bounds__(GemmF16OutCfg::THREADS, 1)
+template <int BN_, int EF>
+__global__ void __launch_bounds__(GemmF16OutCfg<BN_>::THREADS, 1)
 gemm_f16out_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmGate, int M, int N,
                    int K, EpiParams ep) {
-  using Cfg = GemmF16OutCfg;
+  using Cfg = GemmF16OutCfg<BN_>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* a_ring = smem + Cfg::OFF_A;
@@ -77,7 +79,7 @@ gemm_f16out_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc<512>(tmem_slot);
+    tmem_alloc<2 * Cfg::BN>(tmem_slot);
   }
   for (int j = threadIdx.x; j < Cfg::BN; j += blockDim.x) {
     s_colsum[j] = 0.f;
@@ -246,7 +248,7 @@ gemm_f16out_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem_base);
+  if (warp == 0) tmem_dealloc<2 * Cfg::BN>(tmem_base);
 }
 
 }  // namespace rlt
