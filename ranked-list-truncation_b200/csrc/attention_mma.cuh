@@ -15,11 +15,13 @@
 
 namespace rlt {
 
-__device__ __forceinline__ uint32_t tf32_bits(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// fp32 -> tf32 operand bits, round to nearest (ties away): the tensor core ignores the low 13 mantissa bits, so adding
+// half a tf32 ulp to the bit pattern and letting the MMA truncate IS cvt.rna.tf32.f32 (except for inf / NaN inputs) -
+// in ONE integer add.  (ncu: `cvt.rna.tf32.f32` is emulated on sm_100a with an FSETP / IMAD / LOP3 / SEL sequence; at
+// ~500 conversions per warp and item it was more than half of the attention kernels' instructions.)
+__device__ __forceinline__ uint32_t tf32_bits(float x) { return __float_as_uint(x) + 0x1000u; }
+// the same value with the low bits cleared, for the hi / lo split of the 3xTF32 products (lo = x - hi must be exact)
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
   asm volatile(
@@ -39,7 +41,8 @@ __device__ __forceinline__ void tile_abT(const float* __restrict__ sA, int r0, c
   for (int ks = 0; ks < DH / 8; ++ks) {
     const float fa0 = sA[(r0 + g) * P + ks * 8 + t], fa1 = sA[(r0 + g + 8) * P + ks * 8 + t];
     const float fa2 = sA[(r0 + g) * P + ks * 8 + t + 4], fa3 = sA[(r0 + g + 8) * P + ks * 8 + t + 4];
-    const uint32_t a0 = tf32_bits(fa0), a1 = tf32_bits(fa1), a2 = tf32_bits(fa2), a3 = tf32_bits(fa3);
+    const uint32_t a0 = X3 ? tf32_hi(fa0) : tf32_bits(fa0), a1 = X3 ? tf32_hi(fa1) : tf32_bits(fa1);
+    const uint32_t a2 = X3 ? tf32_hi(fa2) : tf32_bits(fa2), a3 = X3 ? tf32_hi(fa3) : tf32_bits(fa3);
     uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0;
     if (X3) {
       l0 = tf32_bits(fa0 - __uint_as_float(a0)); l1 = tf32_bits(fa1 - __uint_as_float(a1));
@@ -48,7 +51,7 @@ __device__ __forceinline__ void tile_abT(const float* __restrict__ sA, int r0, c
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const float fb0 = sB[(j * 8 + g) * P + ks * 8 + t], fb1 = sB[(j * 8 + g) * P + ks * 8 + t + 4];
-      const uint32_t b0 = tf32_bits(fb0), b1 = tf32_bits(fb1);
+      const uint32_t b0 = X3 ? tf32_hi(fb0) : tf32_bits(fb0), b1 = X3 ? tf32_hi(fb1) : tf32_bits(fb1);
       if (X3) {
         const uint32_t m0 = tf32_bits(fb0 - __uint_as_float(b0)), m1 = tf32_bits(fb1 - __uint_as_float(b1));
         mma_tf32(acc[j], l0, l1, l2, l3, b0, b1);   // small terms first
