@@ -22,6 +22,13 @@ namespace rlt {
 __device__ __forceinline__ uint32_t tf32_bits(float x) { return __float_as_uint(x) + 0x1000u; }
 // the same value with the low bits cleared, for the hi / lo split of the 3xTF32 products (lo = x - hi must be exact)
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+// 2^x on the SFU (ex2.approx.ftz: ~2 ulp; arguments here are <= 0, results in [0, 1]); exp2f() adds a denormal-range
+// rescaling sequence (FSETP / FMUL) per call that the softmax does not need
+__device__ __forceinline__ float ex2_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
   asm volatile(
@@ -159,8 +166,8 @@ __global__ void __launch_bounds__(128) attn_lists_fwd_mma_kernel(const float* __
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      acc[j][0] = exp2f(acc[j][0] - m0); acc[j][1] = exp2f(acc[j][1] - m0);
-      acc[j][2] = exp2f(acc[j][2] - m1); acc[j][3] = exp2f(acc[j][3] - m1);
+      acc[j][0] = ex2_fast(acc[j][0] - m0); acc[j][1] = ex2_fast(acc[j][1] - m0);
+      acc[j][2] = ex2_fast(acc[j][2] - m1); acc[j][3] = ex2_fast(acc[j][3] - m1);
       s0 += acc[j][0] + acc[j][1];
       s1 += acc[j][2] + acc[j][3];
     }
@@ -408,8 +415,8 @@ __global__ void __launch_bounds__(128) attn_lists_fwd_pipe_kernel(const float* _
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        acc[j][0] = exp2f(acc[j][0] - m0); acc[j][1] = exp2f(acc[j][1] - m0);
-        acc[j][2] = exp2f(acc[j][2] - m1); acc[j][3] = exp2f(acc[j][3] - m1);
+        acc[j][0] = ex2_fast(acc[j][0] - m0); acc[j][1] = ex2_fast(acc[j][1] - m0);
+        acc[j][2] = ex2_fast(acc[j][2] - m1); acc[j][3] = ex2_fast(acc[j][3] - m1);
         s0 += acc[j][0] + acc[j][1];
         s1 += acc[j][2] + acc[j][3];
       }
@@ -522,10 +529,10 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
       for (int j = 0; j < NT; ++j) {
         const int c = j * 8 + 2 * t;
         const bool ok0 = c < S, ok1 = c + 1 < S;
-        p[j][0] = ok0 ? exp2f(fmaf(p[j][0], sc, -la)) : 0.f;
-        p[j][1] = ok1 ? exp2f(fmaf(p[j][1], sc, -la)) : 0.f;
-        p[j][2] = ok0 ? exp2f(fmaf(p[j][2], sc, -lb)) : 0.f;
-        p[j][3] = ok1 ? exp2f(fmaf(p[j][3], sc, -lb)) : 0.f;
+        p[j][0] = ok0 ? ex2_fast(fmaf(p[j][0], sc, -la)) : 0.f;
+        p[j][1] = ok1 ? ex2_fast(fmaf(p[j][1], sc, -la)) : 0.f;
+        p[j][2] = ok0 ? ex2_fast(fmaf(p[j][2], sc, -lb)) : 0.f;
+        p[j][3] = ok1 ? ex2_fast(fmaf(p[j][3], sc, -lb)) : 0.f;
         float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;
         if (kDrop) {   // d(attn) = mask/(1-p) * d(dropped attn); dV sees the dropped probabilities
           const uint64_t ba = drop_bits(drop.seed, DROP_ATTN, (uint64_t(item) * S + r0 + gq) * S + c);
