@@ -275,7 +275,9 @@ def main():
         8: ("dW1 += dH^T y (gemm_dw, kind::f16, MN-major operands)", T * (d + dff) * 2),
         9: ("cross-list attention forward (mma.sync TF32, cp.async pipeline)", T * (3 * d + d + nh) * 4),
         10: ("cross-list attention backward (mma.sync TF32, cp.async pipeline)", T * (3 * d + d + nh + 3 * d) * 4),
-        12: ("BiLSTM recurrence (tcgen05 kind::f16, unit-major)", T * (1024 + 2 * 6 * 128 + 256) * 4),
+        # mean over the 4 launches of a step: layer-0 forward has no P tensor (fused projection): saved 6 KB + y 1 KB;
+        # layer-1 forward adds P 4 KB; each backward reads saved 6 KB + dy 1 KB and writes dA 4 KB
+        12: ("BiLSTM recurrence (tcgen05 kind::f16, unit-major; mean of 2 forward + 2 backward launches)", T * 10240),
     }
     roof, kernels = None, {}
     if args.time_tag == -1:
@@ -293,6 +295,14 @@ def main():
                             "share_of_step": tot_ms.value / ms,
                             "gbs": site_bytes[top][1] / (tot_ms.value / cnt.value * 1e-3) / 1e9}
     lib.rlt_timing_reset()
+    # all tagged GEMM sites together (the HBM-bound part of the step): sum of algorithmic bytes / sum of device time
+    gemm_sites = [t for t in kernels if t in (1, 2, 3, 4, 5, 6, 7, 8)]
+    gemm_family = None
+    if gemm_sites:
+        tot_s = sum(kernels[t]["avg_launch_ms"] * kernels[t]["launches"] for t in gemm_sites) * 1e-3
+        tot_b = sum(site_bytes[t][1] * kernels[t]["launches"] for t in gemm_sites)
+        gemm_family = {"what": "all tagged tcgen05 GEMM call sites of the encoder layers", "share_of_step": tot_s * 1e3 / ms,
+                       "achieved": tot_b / tot_s / 1e9, "unit": "GB/s", "peak": hbm, "frac": tot_b / tot_s / 1e9 / hbm}
     if top is not None:
         k = kernels[top]
         traffic = None
@@ -329,6 +339,7 @@ def main():
             "e2e": {"value": e2e_lps, "unit": "lists/s", "h2d_bytes_per_step": int(hx.numel() * 4 + hy.numel() * 4),
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "loss": loss_val, "clocks": sampler.summary(), "roofline": roof,
+            "roofline_gemm_family": gemm_family,
             "kernels": {str(k): {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()}
                         for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["share_of_step"])},
             "cpu_baseline": cpu}
