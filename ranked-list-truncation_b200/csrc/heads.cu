@@ -46,12 +46,13 @@ __device__ double g_dcg_term64[1024];
 //                input_kind 1: `in` holds probabilities p (the reference API boundary, grad = dL/dp)
 // loss_kind 0 ChoopyLoss | 1 AttnCutLoss (RAML) | 2 DivLoss kl | 3 DivLoss js
 // ------------------------------------------------------------------------------------------
-template <int NI>
+// The three configuration words are template parameters: every criterion of the reference gets its own small kernel
+// (the run-time-switched kernel spent 15 % of its samples on instruction fetch, profiles/r01_ncu_k3.txt).
+template <int NI, int input_kind, int loss_kind, int metric_dcg>
 __global__ void __launch_bounds__(128) cut_loss_kernel(const float* __restrict__ in, const float* __restrict__ labels,
                                                        float* __restrict__ probs_out, float* __restrict__ grad,
                                                        float* __restrict__ loss_per_list,
-                                                       float* __restrict__ rewards_out, int B, int L,
-                                                       int input_kind, int loss_kind, int metric_dcg, float tau,
+                                                       float* __restrict__ rewards_out, int B, int L, float tau,
                                                        float gscale) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(128) eval_cut_kernel(const float* __restrict__
                                                        const int32_t* __restrict__ pyint_in, int B, int L, int mode, int32_t* __restrict__ k_out,
                                                        int32_t* __restrict__ count_out, int32_t* __restrict__ nrel_out,
                                                        double* __restrict__ f1_out, double* __restrict__ dcg_out) {
-  __shared__ uint32_t s_bits[4][32][32];  // [warp][list in warp][word]
+  __shared__ uint32_t s_bits[4][32][33];  // [warp][list in warp][word]; 33: phase 2 reads one ROW per lane, conflict-free
   __shared__ int s_k[4][32];
   __shared__ int s_pyint[4][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -773,10 +774,21 @@ __global__ void pair_softmax_bwd_kernel(const float* __restrict__ o, const float
   dz[T + t] = db;
 }
 
+// one cut_loss_kernel instantiation per (input kind, loss kind, metric)
+#define RLT_K3(IK, LK, MD)                                                                                             \
+  case (IK) * 8 + (LK) * 2 + (MD):                                                                                     \
+    cut_loss_kernel<NI, IK, LK, MD><<<grid, 128, 0, stream>>>(in, labels, probs_out, grad, loss_per_list, nullptr, B, L, \
+                                                              tau, gscale);                                            \
+    break;
+#define RLT_K3_CASES                                                                                                  \
+  RLT_K3(0, 0, 0) RLT_K3(0, 0, 1) RLT_K3(0, 1, 0) RLT_K3(0, 1, 1) RLT_K3(0, 2, 0) RLT_K3(0, 2, 1) RLT_K3(0, 3, 0) RLT_K3(0, 3, 1) \
+  RLT_K3(1, 0, 0) RLT_K3(1, 0, 1) RLT_K3(1, 1, 0) RLT_K3(1, 1, 1) RLT_K3(1, 2, 0) RLT_K3(1, 2, 1) RLT_K3(1, 3, 0) RLT_K3(1, 3, 1)
+
 template <typename F>
 static int dispatch_ni(int L, F&& f) {
   if (L <= 64) return f(std::integral_constant<int, 2>{});
   if (L <= 320) return f(std::integral_constant<int, 10>{});
+  if (L <= 512) return f(std::integral_constant<int, 16>{});
   if (L <= 1024) return f(std::integral_constant<int, 32>{});
   return set_error(RLT_UNSUPPORTED_SHAPE, "list length %d exceeds 1024", L);
 }
@@ -827,12 +839,19 @@ int rlt_cut_loss(const rlt_cut_loss_desc* c, const float* in, const float* label
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int B = c->n_lists, L = c->seq_len;
   const int grid = (B + 3) / 4;
-  RLT_TRY(dispatch_ni(L, [&](auto ni) {
-    cut_loss_kernel<decltype(ni)::value><<<grid, 128, 0, stream>>>(in, labels, probs_out, grad, loss_per_list, nullptr, B, L,
-                                                                   c->input_kind, c->loss_kind, c->metric_dcg, c->tau,
-                                                                   c->grad_scale);
+  RLT_REQUIRE(c->input_kind >= 0 && c->input_kind <= 1 && c->loss_kind >= 0 && c->loss_kind <= 3, RLT_INVALID_ARG,
+              "rlt_cut_loss: input_kind %d / loss_kind %d out of range", c->input_kind, c->loss_kind);
+  const int cfg = c->input_kind * 8 + c->loss_kind * 2 + (c->metric_dcg ? 1 : 0);
+  const float tau = c->tau, gscale = c->grad_scale;
+  auto launch = [&](auto ni) {
+    constexpr int NI = decltype(ni)::value;
+    switch (cfg) {
+      RLT_K3_CASES
+      default: break;
+    }
     return RLT_OK;
-  }));
+  };
+  RLT_TRY(dispatch_ni(L, launch));
   RLT_CHECK_LAUNCH();
   if (loss_out != nullptr) {
     reduce_scale_kernel<<<1, 256, 0, stream>>>(loss_per_list, B, c->loss_scale, loss_out, c->accumulate_loss);
@@ -845,8 +864,12 @@ int rlt_reward_matrix(const float* labels, float* rewards, int n_lists, int seq_
   RLT_REQUIRE(labels && rewards && n_lists > 0 && seq_len > 0, RLT_INVALID_ARG, "rlt_reward_matrix: bad arguments");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RLT_TRY(dispatch_ni(seq_len, [&](auto ni) {
-    cut_loss_kernel<decltype(ni)::value><<<(n_lists + 3) / 4, 128, 0, stream>>>(
-        nullptr, labels, nullptr, nullptr, nullptr, rewards, n_lists, seq_len, 1, 0, metric_dcg, 1.f, 1.f);
+    if (metric_dcg)
+      cut_loss_kernel<decltype(ni)::value, 1, 0, 1><<<(n_lists + 3) / 4, 128, 0, stream>>>(nullptr, labels, nullptr, nullptr, nullptr,
+                                                                                         rewards, n_lists, seq_len, 1.f, 1.f);
+    else
+      cut_loss_kernel<decltype(ni)::value, 1, 0, 0><<<(n_lists + 3) / 4, 128, 0, stream>>>(nullptr, labels, nullptr, nullptr, nullptr,
+                                                                                         rewards, n_lists, seq_len, 1.f, 1.f);
     return RLT_OK;
   }));
   RLT_CHECK_LAUNCH();
