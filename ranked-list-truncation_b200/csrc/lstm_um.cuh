@@ -48,15 +48,16 @@ __device__ __forceinline__ float tanh_2mufu(float x) {
   // 2 / (1 + e^(-2x)) - 1 ; saturates correctly when the exponential overflows / underflows
   return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.f * 1.4426950408889634f * x)), -1.f);
 }
-// sigmoid(ai), sigmoid(af), tanh(ag), sigmoid(ao) with one shared reciprocal.  Pre-activations are clamped so that
-// the product of the four denominators stays finite: sigmoid(+-20) and tanh(+-10) are exact to 2e-9.
+// sigmoid(ai), sigmoid(af), tanh(ag), sigmoid(ao) with one shared reciprocal.  Pre-activations are clamped from below so
+// that the product of the four denominators stays finite: sigmoid(-20) and tanh(-10) are exact to 2e-9.
 __device__ __forceinline__ void lstm_gate_values(float ai, float af, float ag, float ao, float& gi, float& gf, float& gg,
                                                  float& go) {
   constexpr float kL = 1.4426950408889634f;
-  ai = fminf(fmaxf(ai, -20.f), 20.f);
-  af = fminf(fmaxf(af, -20.f), 20.f);
-  ao = fminf(fmaxf(ao, -20.f), 20.f);
-  ag = fminf(fmaxf(ag, -10.f), 10.f);
+  // only the negative side can overflow (e^{-x} for x -> -inf); for x -> +inf the exponential underflows to 0
+  ai = fmaxf(ai, -20.f);
+  af = fmaxf(af, -20.f);
+  ao = fmaxf(ao, -20.f);
+  ag = fmaxf(ag, -10.f);
   const float di = 1.f + ex2_approx(-kL * ai), df = 1.f + ex2_approx(-kL * af);
   const float dg = 1.f + ex2_approx(-2.f * kL * ag), dO = 1.f + ex2_approx(-kL * ao);
   const float pa = di * df, pb = dg * dO;
@@ -105,6 +106,7 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
   uint64_t* bar_h = bars;          // [2] h of the half complete in smem (count 256)
   uint64_t* bar_acc = bars + 2;    // [2] accumulator of the half ready (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  volatile int* s_progress = reinterpret_cast<volatile int*>(tmem_slot + 1);   // steps finished by the gate warps (prefetch pacing)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, dir = blockIdx.y;
@@ -127,6 +129,7 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
   if (warp == 0) {
     if (lane == 0) {
       for (int h = 0; h < 2; ++h) { mbar_init(&bar_h[h], 256); mbar_init(&bar_acc[h], 1); }
+      *s_progress = 0;
       fence_mbar_init();
     }
     __syncwarp();
@@ -167,11 +170,12 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
       }
     }
   } else if (warp == 17) {
-    // pull the P rows (2 KB per list and step, contiguous) of the step that is kAhead ahead into L2, paced by the
-    // accumulator barrier of the second half (own warp: never more than one phase behind)
+    // pull the P rows (2 KB per list and step, contiguous) of the step that is kAhead ahead into L2, paced by a step
+    // counter the gate warps publish (an mbarrier parity wait aliases when the waiter is two phases behind: the
+    // backward version of this loop dead-locked on its last iterations)
     constexpr int kAhead = 2;
     for (int step = 0; step < L && !kFusedIn; ++step) {
-      if (step >= kAhead) mbar_wait(&bar_acc[1], (step - kAhead) & 1);
+      while (*s_progress < step - kAhead) __nanosleep(200);
       const int t = dir ? (L - 1 - step) : step;
       for (int r = lane; r < U_TILE; r += 32) {
         const int bb = tile * U_TILE + r;
@@ -192,9 +196,12 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
     // this thread's 2-byte slot inside a list's h row: k-block u/64, 16-byte unit (u%64)/8
     uint8_t* hbase = sH + hf * LstmUmFwdSmem::H_BYTES + (u >> 6) * (U_HALF * 128) + (u & 7) * 2;
     const int hunit = (u & 63) >> 3;
-    const size_t p_list = size_t(L) * (2 * UG4);          // P stride between lists
-    const size_t y_list = size_t(L) * (2 * UH);
-    const size_t s_list = size_t(L) * (2 * USAVE * UH);
+    // All global addressing below uses 32-bit ELEMENT offsets from the tensor bases (token count * 1536 < 2^32 is
+    // checked by the host): one IMAD + one IMAD.WIDE per access instead of the 64-bit multiply chains the size_t
+    // form compiled to (ncu: 22 % of the kernel's instructions were IMAD, 36 per cell).
+    const uint32_t Lu = uint32_t(L);
+    const uint32_t tok_list0 = uint32_t(list0) * Lu;      // token index of (list0, t = 0)
+    const uint32_t cP = uint32_t(dir * UG4 + u), cY = uint32_t(dir * UH + u), cS = uint32_t(dir * (USAVE * UH) + u);
     // fused input projection: this unit's four W_ih rows (F <= 4 columns, zero padded) and summed biases
     float wi[4][4], bsum[4];
     if (kFusedIn) {
@@ -205,13 +212,15 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
         for (int f = 0; f < 4; ++f) wi[q][f] = f < inp.F ? inp.w_ih[dir][size_t(q * UH + u) * inp.F + f] : 0.f;
       }
     }
-    // pre-activations of U_CHUNK lists starting at cell c0: from P, or from x (the same 3 floats for every lane: broadcast)
-    auto load_pre = [&](float (&dst)[4][U_CHUNK], int c0, int t) {
+    // pre-activations of U_CHUNK lists whose first token index is tok: from P, or from x (the same 3 floats for every
+    // lane: broadcast loads)
+    auto load_pre = [&](float (&dst)[4][U_CHUNK], uint32_t tok, int c0) {
 #pragma unroll
       for (int li = 0; li < U_CHUNK; ++li) {
         const bool live = list0 + c0 + li < B;
+        const uint32_t tk = tok + uint32_t(li) * Lu;
         if (kFusedIn) {
-          const float* xr = inp.x + (size_t(live ? list0 + c0 + li : 0) * L + t) * inp.F;
+          const float* xr = inp.x + size_t(tk) * inp.F;
           float xv[4];
 #pragma unroll
           for (int f = 0; f < 4; ++f) xv[f] = (live && f < inp.F) ? __ldg(xr + f) : 0.f;
@@ -219,33 +228,36 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
           for (int q = 0; q < 4; ++q)
             dst[q][li] = fmaf(xv[3], wi[q][3], fmaf(xv[2], wi[q][2], fmaf(xv[1], wi[q][1], fmaf(xv[0], wi[q][0], bsum[q]))));
         } else {
-          const float* p0 = P + (size_t(list0) * L + t) * (2 * UG4) + dir * UG4 + u;
+          const float* pr = P + (tk * uint32_t(2 * UG4) + cP);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q][li] = live ? __ldg(p0 + (c0 + li) * p_list + q * UH) : 0.f;
+          for (int q = 0; q < 4; ++q) dst[q][li] = live ? __ldg(pr + q * UH) : 0.f;
         }
       }
     };
 
     for (int step = 0; step < L; ++step) {
       const int t = dir ? (L - 1 - step) : step;
-      const int tn = dir ? (t - 1) : (t + 1);            // time index of the next step (for its h_{t-1} plane)
-      float* y0 = y + (size_t(list0) * L + t) * (2 * UH) + dir * UH + u;
-      float* s0 = saved ? saved + ((size_t(list0) * L + t) * 2 + dir) * (USAVE * UH) + u : nullptr;
+      const uint32_t tokb = tok_list0 + uint32_t(t);       // token of this thread's first list at this step
+      // h_t is the "previous h" plane of the NEXT step's record: +-1 token, plane 5
+      const uint32_t dnext = (dir ? 0u - uint32_t(2 * USAVE * UH) : uint32_t(2 * USAVE * UH)) + uint32_t(5 * UH);
+      const bool has_next = step + 1 < L;
       float pc[4][U_CHUNK];
-      load_pre(pc, 0, t);
+      load_pre(pc, tokb, 0);
       mbar_wait(&bar_acc[hf], step & 1);
       tc_fence_after();
+      uint32_t tok_ch = tokb;                              // token of the first list of the current chunk
 #pragma unroll 1
-      for (int ch = 0; ch < U_CELLS / U_CHUNK; ++ch) {
+      for (int ch = 0; ch < U_CELLS / U_CHUNK; ++ch, tok_ch += U_CHUNK * Lu) {
         float a[4][U_CHUNK];
 #pragma unroll
         for (int q = 0; q < 4; ++q) tmem_ld4(t_lane + q * U_HALF + ch * U_CHUNK, a[q]);
         float pn[4][U_CHUNK];
-        if (ch + 1 < U_CELLS / U_CHUNK) load_pre(pn, (ch + 1) * U_CHUNK, t);
+        if (ch + 1 < U_CELLS / U_CHUNK) load_pre(pn, tok_ch + U_CHUNK * Lu, (ch + 1) * U_CHUNK);
 #pragma unroll
         for (int li = 0; li < U_CHUNK; ++li) {
           const int cell = ch * U_CHUNK + li;
           const bool live = list0 + cell < B;
+          const uint32_t tk = tok_ch + uint32_t(li) * Lu;
           float gi, gf, gg, go;
           lstm_gate_values(a[0][li] + pc[0][li], a[1][li] + pc[1][li], a[2][li] + pc[2][li], a[3][li] + pc[3][li], gi, gf,
                            gg, go);
@@ -253,14 +265,14 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
           sC[cell * 512 + gt] = cn;
           const float hv = go * tanh_2mufu(cn);
           if (live) {
-            if (s0 != nullptr) {
-              float* sv = s0 + cell * s_list;
+            if (saved != nullptr) {
+              const uint32_t so = tk * uint32_t(2 * USAVE * UH) + cS;
+              float* sv = saved + so;
               sv[0 * UH] = gi; sv[1 * UH] = gf; sv[2 * UH] = gg; sv[3 * UH] = go; sv[4 * UH] = cn;
               if (step == 0) sv[5 * UH] = 0.f;
-              // h_t is the "previous h" of the next step's record
-              if (step + 1 < L) saved[((size_t(list0 + cell) * L + tn) * 2 + dir) * (USAVE * UH) + 5 * UH + u] = hv;
+              if (has_next) saved[so + dnext] = hv;
             }
-            y0[cell * y_list] = hv;
+            y[tk * uint32_t(2 * UH) + cY] = hv;
           }
           const int r = row0 + cell;
           *reinterpret_cast<unsigned short*>(hbase + (r >> 3) * 1024 + (r & 7) * 128 + (((hunit ^ r) & 7) << 4)) =
@@ -274,6 +286,7 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&bar_h[hf]);
+      if (gt == 511) *s_progress = step + 1;     // last gate thread of the second half
     }
   }
   tc_fence_before();
@@ -309,6 +322,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
   uint64_t* bar_da = bars;         // [2] da of the half complete in smem (count 256)
   uint64_t* bar_d = bars + 2;      // [2] dh_rec of the half ready (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  volatile int* s_progress = reinterpret_cast<volatile int*>(tmem_slot + 1);   // steps finished by the gate warps (prefetch pacing)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, dir = blockIdx.y;
@@ -333,6 +347,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
   if (warp == 0) {
     if (lane == 0) {
       for (int h = 0; h < 2; ++h) { mbar_init(&bar_da[h], 256); mbar_init(&bar_d[h], 1); }
+      *s_progress = 0;
       fence_mbar_init();
     }
     __syncwarp();
@@ -370,7 +385,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
     // L2 prefetch of the saved record (i, f, g, o, c: 2.5 KB) and dy row (512 B) of the step kAhead ahead
     constexpr int kAhead = 2;
     for (int it = 0; it < L; ++it) {
-      if (it >= kAhead) mbar_wait(&bar_d[1], (it - kAhead) & 1);
+      while (*s_progress < it - kAhead) __nanosleep(200);
       const int step = L - 1 - it;
       const int t = dir ? (L - 1 - step) : step;
       for (int r = lane; r < U_TILE; r += 32) {
@@ -397,35 +412,43 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
     // da[list row r][n = q*128 + u]: k-block q*2 + u/64, 16-byte unit (u%64)/8, 2 bytes at (u%8)*2
     uint8_t* dabase = sDA + hf * LstmUmBwdSmem::DA_BYTES + (u >> 6) * LstmUmBwdSmem::DA_KB + (u & 7) * 2;
     const int dunit = (u & 63) >> 3;
-    const size_t s_list = size_t(L) * (2 * USAVE * UH);
-    const size_t y_list = size_t(L) * (2 * UH);
-    const size_t a_list = size_t(L) * (2 * UG4);
+    // 32-bit element offsets from the tensor bases, as in the forward kernel
+    const uint32_t Lu = uint32_t(L);
+    const uint32_t tok_list0 = uint32_t(list0) * Lu;
+    const uint32_t cS = uint32_t(dir * (USAVE * UH) + u), cY = uint32_t(dir * UH + u), cA = uint32_t(dir * UG4 + u);
     float dbs[4] = {0.f, 0.f, 0.f, 0.f};                // this unit's share of db = sum over (list, t) of da
+    // i, f, g, o, c of the step, c of the previous step, dy: U_CHUNK lists whose first token index is tok
+    auto load_rec = [&](float (&dst)[7][U_CHUNK], uint32_t tok, int c0, bool has_prev, uint32_t dprev) {
+#pragma unroll
+      for (int li = 0; li < U_CHUNK; ++li) {
+        const bool live = list0 + c0 + li < B;
+        const uint32_t tk = tok + uint32_t(li) * Lu;
+        const uint32_t so = tk * uint32_t(2 * USAVE * UH) + cS;
+        const float* sr = saved + so;
+#pragma unroll
+        for (int pl = 0; pl < 5; ++pl) dst[pl][li] = live ? __ldg(sr + pl * UH) : 0.f;
+        dst[5][li] = (live && has_prev) ? __ldg(saved + uint32_t(so + dprev)) : 0.f;   // offset sum wraps in 32 bits
+        dst[6][li] = live ? __ldg(dy + (tk * uint32_t(2 * UH) + cY)) : 0.f;
+      }
+    };
 
     for (int it = 0; it < L; ++it) {
       const int step = L - 1 - it;                      // forward step index being differentiated
       const int t = dir ? (L - 1 - step) : step;
-      const int tp = dir ? (t + 1) : (t - 1);           // time index of the previous forward step
-      const float* s0 = saved + ((size_t(list0) * L + t) * 2 + dir) * (USAVE * UH) + u;
-      const float* c0 = saved + ((size_t(list0) * L + tp) * 2 + dir) * (USAVE * UH) + 4 * UH + u;   // c_{t-1} (step > 0)
-      const float* dy0 = dy + (size_t(list0) * L + t) * (2 * UH) + dir * UH + u;
-      float* da0 = dA + (size_t(list0) * L + t) * (2 * UG4) + dir * UG4 + u;
+      const uint32_t tokb = tok_list0 + uint32_t(t);
+      // c_{t-1} lives in the record of the previous forward step: -+1 token, plane 4 (relative to plane 0 of this one)
+      const uint32_t dprev = (dir ? uint32_t(2 * USAVE * UH) : 0u - uint32_t(2 * USAVE * UH)) + uint32_t(4 * UH);
+      const bool has_prev = step > 0;
       // operands of the first chunk: in flight while the tensor core finishes dh_rec
       float vc[7][U_CHUNK];   // i, f, g, o, c, c_prev, dy
-#pragma unroll
-      for (int li = 0; li < U_CHUNK; ++li) {
-        const bool live = list0 + li < B;
-#pragma unroll
-        for (int pl = 0; pl < 5; ++pl) vc[pl][li] = live ? __ldg(s0 + li * s_list + pl * UH) : 0.f;
-        vc[5][li] = (live && step > 0) ? __ldg(c0 + li * s_list) : 0.f;
-        vc[6][li] = live ? __ldg(dy0 + li * y_list) : 0.f;
-      }
+      load_rec(vc, tokb, 0, has_prev, dprev);
       if (it > 0) {
         mbar_wait(&bar_d[hf], (it - 1) & 1);
         tc_fence_after();
       }
+      uint32_t tok_ch = tokb;
 #pragma unroll 1
-      for (int ch = 0; ch < U_CELLS / U_CHUNK; ++ch) {
+      for (int ch = 0; ch < U_CELLS / U_CHUNK; ++ch, tok_ch += U_CHUNK * Lu) {
         float dhr[U_CHUNK];
         if (it > 0) {
           tmem_ld4(t_lane + ch * U_CHUNK, dhr);
@@ -434,17 +457,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
           for (int li = 0; li < U_CHUNK; ++li) dhr[li] = 0.f;
         }
         float vn[7][U_CHUNK];
-        if (ch + 1 < U_CELLS / U_CHUNK) {
-#pragma unroll
-          for (int li = 0; li < U_CHUNK; ++li) {
-            const int cell = (ch + 1) * U_CHUNK + li;
-            const bool live = list0 + cell < B;
-#pragma unroll
-            for (int pl = 0; pl < 5; ++pl) vn[pl][li] = live ? __ldg(s0 + cell * s_list + pl * UH) : 0.f;
-            vn[5][li] = (live && step > 0) ? __ldg(c0 + cell * s_list) : 0.f;
-            vn[6][li] = live ? __ldg(dy0 + cell * y_list) : 0.f;
-          }
-        }
+        if (ch + 1 < U_CELLS / U_CHUNK) load_rec(vn, tok_ch + U_CHUNK * Lu, (ch + 1) * U_CHUNK, has_prev, dprev);
 #pragma unroll
         for (int li = 0; li < U_CHUNK; ++li) {
           const int cell = ch * U_CHUNK + li;
@@ -460,7 +473,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
           const float dag = dc * gi * (1.f - gg * gg);
           const float dao = d_o * go * (1.f - go);
           if (live) {
-            float* o = da0 + cell * a_list;
+            float* o = dA + ((tok_ch + uint32_t(li) * Lu) * uint32_t(2 * UG4) + cA);
             o[0 * UH] = dai; o[1 * UH] = daf; o[2 * UH] = dag; o[3 * UH] = dao;
             dbs[0] += dai; dbs[1] += daf; dbs[2] += dag; dbs[3] += dao;
           }
@@ -479,6 +492,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&bar_da[hf]);
+      if (gt == 511) *s_progress = it + 1;
     }
     if (db != nullptr) {
 #pragma unroll
