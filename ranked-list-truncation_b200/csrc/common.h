@@ -75,6 +75,8 @@ int dropout_apply(const float* src, float* dst, size_t n, DropCfg drop, uint32_t
 int transpose_f16(const float* src, __half* dst, int rows, int cols, cudaStream_t stream);
 // scale = {2^k, 2^-k} with max|x| * 2^k in [2^(target-1), 2^target); amax_scratch: one device word
 int grad_scale(const float* x, size_t n, unsigned int* amax_scratch, float* scale, int target, cudaStream_t stream);
+// the same from an already reduced amax word (float bits)
+int pow2_scale(const unsigned int* amax_bits, float* scale, int target, cudaStream_t stream);
 
 // 0 = tcgen05 tensor-core kernels (default), 1 = plain SIMT kernels (validation backend only)
 int gemm_backend();

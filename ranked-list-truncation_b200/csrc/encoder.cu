@@ -81,9 +81,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      const float* __restrict__ stats,
                                                      const float* __restrict__ gamma, float* __restrict__ du,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                     float* __restrict__ dbias_prev, int T) {
+                                                     float* __restrict__ dbias_prev, int T,
+                                                     unsigned int* __restrict__ amax_out /* optional: max |du| (float bits) */) {
   constexpr int V4 = D / 128;
   __shared__ float red[3][D];
+  float amax = 0.f;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) (&red[0][0])[i] = 0.f;
   __syncthreads();
@@ -123,7 +125,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                    rstd * (dg[i].z - m1 - xh[i].z * m2), rstd * (dg[i].w - m1 - xh[i].w * m2));
       po[lane + 32 * i] = r;
       ad[i].x += r.x; ad[i].y += r.y; ad[i].z += r.z; ad[i].w += r.w;
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w))));
     }
+  }
+  if (amax_out != nullptr) {   // the fp16 scale of the FFN gradient branch comes from max |dU2|: no separate pass over du
+#pragma unroll
+    for (int o = 16; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0 && amax > 0.f) atomicMax(amax_out, __float_as_uint(amax));
   }
 #pragma unroll
   for (int i = 0; i < V4; ++i) {
@@ -537,13 +545,14 @@ static int layer_norm_fwd(const float* u, const float* gamma, const float* beta,
 }
 
 static int layer_norm_bwd(const float* dy, const float* u, const float* stats, const float* gamma, float* du,
-                          float* dgamma, float* dbeta, float* dbias_prev, int T, int d, cudaStream_t stream) {
+                          float* dgamma, float* dbeta, float* dbias_prev, int T, int d, cudaStream_t stream,
+                          unsigned int* amax_out = nullptr) {
   int grid = (T + 63) / 64;
   const int cap = num_sms() * 4;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  if (d == 128) ln_bwd_kernel<128><<<grid, 256, 0, stream>>>(dy, u, stats, gamma, du, dgamma, dbeta, dbias_prev, T);
-  else if (d == 256) ln_bwd_kernel<256><<<grid, 256, 0, stream>>>(dy, u, stats, gamma, du, dgamma, dbeta, dbias_prev, T);
+  if (d == 128) ln_bwd_kernel<128><<<grid, 256, 0, stream>>>(dy, u, stats, gamma, du, dgamma, dbeta, dbias_prev, T, amax_out);
+  else if (d == 256) ln_bwd_kernel<256><<<grid, 256, 0, stream>>>(dy, u, stats, gamma, du, dgamma, dbeta, dbias_prev, T, amax_out);
   else return set_error(RLT_UNSUPPORTED_SHAPE, "layer_norm: d_model %d not in {128, 256}", d);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
@@ -706,8 +715,12 @@ int rlt_encoder_layer_bwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   float* wide = ws + size_t(2) * T * d;     // [T, max(dff, 3d)]  dHpre, later dO (first T*d) / dQKV
 
   // LN2 backward: dU2, dgamma2, dbeta2, db2 (= column sums of dU2)
+  // fp16 path: max |dU2| (for the power-of-two gradient scale) is reduced inside the LayerNorm backward
+  float* scale = ws + size_t(T) * (2 * size_t(d) + (size_t(f) > 3 * size_t(d) ? f : 3 * d));   // {s, 1/s}, then the amax word
+  unsigned int* amax = reinterpret_cast<unsigned int*>(scale + 2);
+  if (hidden_f16(*e)) RLT_CHECK_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), stream));
   RLT_TRY(layer_norm_bwd(d_out, sv + sl.u2, sv + sl.st2, w->norm2_w, d_u, gw->norm2_w, gw->norm2_b,
-                         drop.thr ? nullptr : gw->lin2_b, T, d, stream));
+                         drop.thr ? nullptr : gw->lin2_b, T, d, stream, hidden_f16(*e) ? amax : nullptr));
   if (drop.thr) RLT_TRY(colsum_masked(d_u, gw->lin2_b, T, d, drop, DROP_AFTER_FFN, stream));   // b2 sits inside dropout2
   if (hidden_f16(*e)) {
     const __half* hh = reinterpret_cast<const __half*>(sv + sl.h);
@@ -715,10 +728,8 @@ int rlt_encoder_layer_bwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
     const __half* w1th = reinterpret_cast<const __half*>(sv + sl.wh) + size_t(d) * f;
     __half* dh16 = reinterpret_cast<__half*>(wide);                           // [T, f] fp16, scaled by s
     __half* du16 = reinterpret_cast<__half*>(wide + size_t(T) * f / 2);       // [T, d] fp16, scaled by s
-    float* scale = ws + size_t(T) * (2 * size_t(d) + (size_t(f) > 3 * size_t(d) ? f : 3 * d));   // {s, 1/s}
-    unsigned int* amax = reinterpret_cast<unsigned int*>(scale + 2);
     // power-of-two scale s: max|dU2| * s in [32, 64) -> dU2, dH = dU2 W2 stay far from fp16's limits on both sides
-    RLT_TRY(grad_scale(d_u, size_t(T) * d, amax, scale, 6, stream));
+    RLT_TRY(pow2_scale(amax, scale, 6, stream));
     // the FFN branch sees dropout2(dU2); the residual branch below keeps the undropped d_u
     RLT_TRY(convert_f16(d_u, du16, size_t(T) * d, scale, stream, drop, DROP_AFTER_FFN));
     // dW2 += dU2^T h

@@ -520,6 +520,11 @@ __global__ void pow2_scale_kernel(const unsigned int* __restrict__ amax_bits, fl
   scale[0] = s;
   scale[1] = 1.f / s;
 }
+int pow2_scale(const unsigned int* amax_bits, float* scale, int target, cudaStream_t stream) {
+  pow2_scale_kernel<<<1, 1, 0, stream>>>(amax_bits, scale, target);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
 int grad_scale(const float* x, size_t n, unsigned int* amax_scratch, float* scale, int target, cudaStream_t stream) {
   RLT_REQUIRE(n % 4 == 0, RLT_INVALID_ARG, "grad_scale: n must be a multiple of 4");
   RLT_CHECK_CUDA(cudaMemsetAsync(amax_scratch, 0, sizeof(unsigned int), stream));

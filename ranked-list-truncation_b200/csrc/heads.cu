@@ -728,19 +728,36 @@ __global__ void __launch_bounds__(128) bicut_loss_kernel(const float* __restrict
 // Choopy input (models/Choopy.py:18-20, MtChoopy.py:24-25): X[b, l, :] = [score[b,l] | PE[l, 0:127]]
 // and the gradient of the learned table: dPE[l, c] += sum_b dX[b, l, 1 + c].
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) choopy_embed_kernel(const float* __restrict__ score, const float* __restrict__ pe,
-                                                           float* __restrict__ x, int B, int L) {
-  const size_t t = blockIdx.x;  // token = b*L + l
-  const int l = int(t % L);
-  const int c = threadIdx.x;
-  x[t * 128 + c] = c == 0 ? score[t] : pe[size_t(l) * 127 + c - 1];
+// x[t, 0] = score[t], x[t, 1:128] = PE[l, :]  (models/Choopy.py:19-20).  One thread per 16-byte unit of x, grid-stride:
+// the first version launched one 128-thread CTA per token (1.2 M CTAs, 1 TB/s).
+__global__ void __launch_bounds__(256) choopy_embed_kernel(const float* __restrict__ score, const float* __restrict__ pe,
+                                                           float* __restrict__ x, size_t T, int L) {
+  const size_t n4 = T * 32, stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const size_t t = i >> 5;
+    const int c = int(i & 31) * 4;
+    const float* pr = pe + size_t(t % L) * 127 + c - 1;       // PE column c-1 .. c+2 (rows of 127 floats: unaligned)
+    float4 v;
+    v.x = c == 0 ? __ldg(score + t) : __ldg(pr);
+    v.y = __ldg(pr + 1); v.z = __ldg(pr + 2); v.w = __ldg(pr + 3);
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
 }
+// dPE[l, c-1] += sum over lists of dx[b, l, c]: CTA (l, slice of the lists), 4 independent loads in flight per thread
 __global__ void __launch_bounds__(128) choopy_embed_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dpe,
                                                                int B, int L) {
   const int l = blockIdx.x, c = threadIdx.x;
-  float acc = 0.f;
-  for (int b = blockIdx.y; b < B; b += gridDim.y) acc += dx[(size_t(b) * L + l) * 128 + c];
-  if (c > 0) atomicAdd(dpe + size_t(l) * 127 + c - 1, acc);
+  const size_t pitch = size_t(L) * 128;
+  const float* base = dx + size_t(l) * 128 + c;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int b = blockIdx.y;
+  const int g = gridDim.y;
+  for (; b + 3 * g < B; b += 4 * g) {
+    a0 += __ldg(base + size_t(b) * pitch); a1 += __ldg(base + size_t(b + g) * pitch);
+    a2 += __ldg(base + size_t(b + 2 * g) * pitch); a3 += __ldg(base + size_t(b + 3 * g) * pitch);
+  }
+  for (; b < B; b += g) a0 += __ldg(base + size_t(b) * pitch);
+  if (c > 0) atomicAdd(dpe + size_t(l) * 127 + c - 1, (a0 + a1) + (a2 + a3));
 }
 
 // BiCut output head (models/Bicut.py:11-16): 2-class softmax of the logit planes z[0,:], z[1,:] -> o[t, 0:2]
@@ -813,15 +830,18 @@ int rlt_set_dcg_tables(const float* coef32_host, const double* term64_host, int 
 
 int rlt_choopy_embed_fwd(const float* score, const float* pe, float* x, int n_lists, int seq_len, rlt_stream_t stream_) {
   RLT_REQUIRE(score && pe && x && n_lists > 0 && seq_len > 0, RLT_INVALID_ARG, "rlt_choopy_embed_fwd: bad arguments");
-  choopy_embed_kernel<<<unsigned(size_t(n_lists) * seq_len), 128, 0, static_cast<cudaStream_t>(stream_)>>>(score, pe, x, n_lists, seq_len);
+  const size_t T = size_t(n_lists) * seq_len;
+  size_t blocks = (T * 32 + 255) / 256;
+  if (blocks > size_t(num_sms()) * 16) blocks = size_t(num_sms()) * 16;
+  choopy_embed_kernel<<<unsigned(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(score, pe, x, T, seq_len);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }
 
 int rlt_choopy_embed_bwd(const float* dx, float* dpe, int n_lists, int seq_len, rlt_stream_t stream_) {
   RLT_REQUIRE(dx && dpe && n_lists > 0 && seq_len > 0, RLT_INVALID_ARG, "rlt_choopy_embed_bwd: bad arguments");
-  int gy = (n_lists + 63) / 64;
-  if (gy > 32) gy = 32;
+  int gy = (n_lists + 31) / 32;
+  if (gy > 16) gy = 16;     // seq_len x gy CTAs: 4800 at L = 300, each with 4 x 512 B loads in flight per warp group
   choopy_embed_bwd_kernel<<<dim3(seq_len, gy), 128, 0, static_cast<cudaStream_t>(stream_)>>>(dx, dpe, n_lists, seq_len);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
