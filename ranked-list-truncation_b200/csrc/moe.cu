@@ -21,44 +21,55 @@ __device__ __forceinline__ float wsum(float v) {
 }
 
 // logits[t, b, e] = sum_j flat[b, j] * W[t][j, e]; one CTA per list, 256 threads stride over j.
+constexpr int GATE_LB = 8;   // lists per CTA of the gate kernels: every gate weight fetched from L2 serves 8 lists
+// gates[t, b, :] = softmax_e( flat[b, :] . W_t[:, e] )  in true fp32 (K = 76 800).  One CTA per GATE_LB
+// lists (the first version used one CTA per list and re-read the 2.8 MB of gate weights from L2 for each of them: 0.83 ms
+// for 2048 lists, L2-bandwidth bound).
 __global__ void __launch_bounds__(256) moe_gate_logits_kernel(const float* __restrict__ flat, const float* __restrict__ wg,
                                                               float* __restrict__ gates, int B, int J, int E, int Tk) {
-  const int b = blockIdx.x;
-  float acc[MAX_T * MAX_E];
+  const int b0 = blockIdx.x * GATE_LB;
+  float acc[GATE_LB][MAX_T * MAX_E];
 #pragma unroll
-  for (int i = 0; i < MAX_T * MAX_E; ++i) acc[i] = 0.f;
-  const float* fr = flat + size_t(b) * J;
+  for (int l = 0; l < GATE_LB; ++l)
+#pragma unroll
+    for (int i = 0; i < MAX_T * MAX_E; ++i) acc[l][i] = 0.f;
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
-    const float v = fr[j];
+    float w[MAX_T * MAX_E];
 #pragma unroll
     for (int t = 0; t < MAX_T; ++t)
-      if (t < Tk) {
-        const float* wr = wg + (size_t(t) * J + j) * E;
 #pragma unroll
-        for (int e = 0; e < MAX_E; ++e)
-          if (e < E) acc[t * MAX_E + e] = fmaf(v, __ldg(wr + e), acc[t * MAX_E + e]);
-      }
+      for (int e = 0; e < MAX_E; ++e) w[t * MAX_E + e] = (t < Tk && e < E) ? __ldg(wg + (size_t(t) * J + j) * E + e) : 0.f;
+#pragma unroll
+    for (int l = 0; l < GATE_LB; ++l) {
+      const float v = b0 + l < B ? __ldg(flat + size_t(b0 + l) * J + j) : 0.f;
+#pragma unroll
+      for (int i = 0; i < MAX_T * MAX_E; ++i) acc[l][i] = fmaf(v, w[i], acc[l][i]);
+    }
   }
-  __shared__ float red[8][MAX_T * MAX_E];
+  __shared__ float red[8][GATE_LB][MAX_T * MAX_E];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < MAX_T * MAX_E; ++i) {
-    const float s = wsum(acc[i]);
-    if (lane == 0) red[warp][i] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < Tk) {
-    const int t = threadIdx.x;
-    float lg[MAX_E], m = -INFINITY;
-    for (int e = 0; e < E; ++e) {
-      float s = 0.f;
-      for (int w = 0; w < 8; ++w) s += red[w][t * MAX_E + e];
-      lg[e] = s;
-      m = fmaxf(m, s);
+  for (int l = 0; l < GATE_LB; ++l)
+#pragma unroll
+    for (int i = 0; i < MAX_T * MAX_E; ++i) {
+      const float sacc = wsum(acc[l][i]);
+      if (lane == 0) red[warp][l][i] = sacc;
     }
-    float den = 0.f;
-    for (int e = 0; e < E; ++e) { lg[e] = expf(lg[e] - m); den += lg[e]; }
-    for (int e = 0; e < E; ++e) gates[(size_t(t) * B + b) * E + e] = lg[e] / den;
+  __syncthreads();
+  if (threadIdx.x < GATE_LB * Tk) {
+    const int l = threadIdx.x / Tk, t = threadIdx.x % Tk;
+    if (b0 + l < B) {
+      float lg[MAX_E], m = -INFINITY;
+      for (int e = 0; e < E; ++e) {
+        float sacc = 0.f;
+        for (int wq = 0; wq < 8; ++wq) sacc += red[wq][l][t * MAX_E + e];
+        lg[e] = sacc;
+        m = fmaxf(m, sacc);
+      }
+      float den = 0.f;
+      for (int e = 0; e < E; ++e) { lg[e] = expf(lg[e] - m); den += lg[e]; }
+      for (int e = 0; e < E; ++e) gates[(size_t(t) * B + b0 + l) * E + e] = lg[e] / den;
+    }
   }
 }
 
@@ -185,17 +196,34 @@ __global__ void moe_gate_softmax_bwd_kernel(const float* __restrict__ gates, flo
   for (int e = 0; e < E; ++e) dG[size_t(i) * E + e] = gates[size_t(i) * E + e] * (dG[size_t(i) * E + e] - dot);
 }
 
-// dW[t][j, e] += sum_b flat[b, j] * dlogit[t, b, e]   (one thread per j; loops over all lists: no atomics)
-// dflat[b, j] += sum_{t,e} dlogit[t,b,e] * W[t][j,e]  is done by the kernel below.
+// dW[t][j, e] += sum_b flat[b, j] * dlogit[t, b, e]: thread = gate input j, blockIdx.y = slice of the lists (the first
+// version walked ALL lists in one dependent loop per thread: 1.4 ms for 2048 lists); the dlogit addresses are uniform
+// per warp (broadcast), four independent flat loads are in flight, partial sums go out with one red.add per element.
 __global__ void __launch_bounds__(256) moe_gate_dw_kernel(const float* __restrict__ flat, const float* __restrict__ dlogit,
                                                           float* __restrict__ dwg, int B, int J, int E, int Tk) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= J) return;
+  const int per = (B + gridDim.y - 1) / gridDim.y;
+  const int bs = blockIdx.y * per, be = min(B, bs + per);
   float acc[MAX_T * MAX_E];
 #pragma unroll
   for (int i = 0; i < MAX_T * MAX_E; ++i) acc[i] = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float v = flat[size_t(b) * J + j];
+  int b = bs;
+  for (; b + 3 < be; b += 4) {
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = __ldg(flat + size_t(b + q) * J + j);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int t = 0; t < MAX_T; ++t)
+        if (t < Tk)
+#pragma unroll
+          for (int e = 0; e < MAX_E; ++e)
+            if (e < E) acc[t * MAX_E + e] = fmaf(v[q], __ldg(dlogit + (size_t(t) * B + b + q) * E + e), acc[t * MAX_E + e]);
+  }
+  for (; b < be; ++b) {
+    const float v = __ldg(flat + size_t(b) * J + j);
 #pragma unroll
     for (int t = 0; t < MAX_T; ++t)
       if (t < Tk)
@@ -204,21 +232,35 @@ __global__ void __launch_bounds__(256) moe_gate_dw_kernel(const float* __restric
           if (e < E) acc[t * MAX_E + e] = fmaf(v, __ldg(dlogit + (size_t(t) * B + b) * E + e), acc[t * MAX_E + e]);
   }
   for (int t = 0; t < Tk; ++t)
-    for (int e = 0; e < E; ++e) dwg[(size_t(t) * J + j) * E + e] += acc[t * MAX_E + e];
+    for (int e = 0; e < E; ++e) atomicAdd(dwg + (size_t(t) * J + j) * E + e, acc[t * MAX_E + e]);
 }
 
+// dflat[b, j] (+)= sum_{t,e} dlogit[t,b,e] * W[t][j,e]: thread = gate input j for GATE_LB lists (weights loaded once)
 __global__ void __launch_bounds__(256) moe_gate_dflat_kernel(const float* __restrict__ dlogit, const float* __restrict__ wg,
                                                              float* __restrict__ dflat, int B, int J, int E, int Tk,
                                                              int accumulate) {
-  const int b = blockIdx.y;
+  const int b0 = blockIdx.y * GATE_LB;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= J) return;
-  float acc = 0.f;
-  for (int t = 0; t < Tk; ++t)
-    for (int e = 0; e < E; ++e)
-      acc = fmaf(__ldg(dlogit + (size_t(t) * B + b) * E + e), __ldg(wg + (size_t(t) * J + j) * E + e), acc);
-  float* o = dflat + size_t(b) * J + j;
-  *o = accumulate ? *o + acc : acc;
+  float w[MAX_T * MAX_E];
+#pragma unroll
+  for (int t = 0; t < MAX_T; ++t)
+#pragma unroll
+    for (int e = 0; e < MAX_E; ++e) w[t * MAX_E + e] = (t < Tk && e < E) ? __ldg(wg + (size_t(t) * J + j) * E + e) : 0.f;
+#pragma unroll
+  for (int l = 0; l < GATE_LB; ++l) {
+    const int b = b0 + l;
+    if (b >= B) break;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < MAX_T; ++t)
+      if (t < Tk)
+#pragma unroll
+        for (int e = 0; e < MAX_E; ++e)
+          if (e < E) acc = fmaf(__ldg(dlogit + (size_t(t) * B + b) * E + e), w[t * MAX_E + e], acc);
+    float* o = dflat + size_t(b) * J + j;
+    *o = accumulate ? *o + acc : acc;
+  }
 }
 
 }  // namespace rlt
@@ -235,7 +277,7 @@ int rlt_moe_heads_fwd(const rlt_moe_desc* m, const float* h_lstm, const float* w
   RLT_REQUIRE(m->d_model == 128 || m->d_model == 256, RLT_UNSUPPORTED_SHAPE, "moe: d_model %d", m->d_model);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int B = m->n_lists, L = m->seq_len, J = L * m->d_lstm, E = m->n_experts, Tk = m->n_tasks;
-  moe_gate_logits_kernel<<<B, 256, 0, stream>>>(h_lstm, w_gates, gates, B, J, E, Tk);
+  moe_gate_logits_kernel<<<(B + GATE_LB - 1) / GATE_LB, 256, 0, stream>>>(h_lstm, w_gates, gates, B, J, E, Tk);
   RLT_CHECK_LAUNCH();
   ExpertPtrs xs{};
   for (int e = 0; e < E; ++e) xs.x[e] = experts[e];
@@ -270,9 +312,14 @@ int rlt_moe_heads_bwd(const rlt_moe_desc* m, const float* h_lstm, const float* w
   RLT_CHECK_LAUNCH();
   moe_gate_softmax_bwd_kernel<<<(Tk * B + 127) / 128, 128, 0, stream>>>(gates, dgate_scratch, Tk * B, E);
   RLT_CHECK_LAUNCH();
-  moe_gate_dw_kernel<<<(J + 255) / 256, 256, 0, stream>>>(h_lstm, dgate_scratch, d_w_gates, B, J, E, Tk);
+  {
+    int slices = (B + 127) / 128;      // >= 128 lists per slice; (J / 256) x slices CTAs
+    if (slices > 16) slices = 16;
+    moe_gate_dw_kernel<<<dim3((J + 255) / 256, slices), 256, 0, stream>>>(h_lstm, dgate_scratch, d_w_gates, B, J, E, Tk);
+  }
   RLT_CHECK_LAUNCH();
-  moe_gate_dflat_kernel<<<dim3((J + 255) / 256, B), 256, 0, stream>>>(dgate_scratch, w_gates, d_h_lstm, B, J, E, Tk, accumulate_dh);
+  moe_gate_dflat_kernel<<<dim3((J + 255) / 256, (B + GATE_LB - 1) / GATE_LB), 256, 0, stream>>>(dgate_scratch, w_gates, d_h_lstm, B, J, E,
+                                                                                             Tk, accumulate_dh);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }
