@@ -1,14 +1,14 @@
 // Cross-list attention on the warp-level tensor-core path (mma.sync.m16n8k8 TF32, fp32 accumulate).
 //
-// One CTA per (position l, group g, head h); the problem is S x S x dh with S = lists per group (<= 128) and
-// dh in {16, 32, 64, 128}: far below a 128-row tcgen05 tile, so each warp owns a 16-row tile and keeps
-// everything in registers.  Score products use the 3xTF32 split (a_hi b_hi + a_lo b_hi + a_hi b_lo) so that the
+// One work item per (group g, position l, head h); the problem is S x S x dh with S = lists per group (<= 128) and
+// dh in {16, 32, 64}: far below a 128-row tcgen05 tile, so each warp owns a 16-row tile and keeps everything in
+// registers.  Score products use the 3xTF32 split (a_hi b_hi + a_lo b_hi + a_hi b_lo) so that the
 // softmax sees ~fp32-accurate logits; P V and the gradient contractions use single TF32.
 // The contraction index of the second GEMM is permuted so that accumulator fragments (cols 2t, 2t+1) feed the
 // next MMA's A fragment (cols t, t+4) without any shuffle: key 8j+2t -> k-slot t, key 8j+2t+1 -> k-slot t+4, and
 // the B fragment rows are read from shared memory with the same permutation.
-// Backward recomputes P from the saved log-sum-exp (no S x S tensor in HBM): phase A per query tile (dQ),
-// phase B per key tile with the transposed products (dK, dV); no atomics.
+// Backward recomputes P from the saved log-sum-exp (no S x S tensor in HBM): phase A per query tile (dQ; P and dS stay
+// in shared memory), phase B per key tile contracts them transposed (dK, dV); no atomics.
 #pragma once
 #include "dropout.cuh"
 #include "sm100.cuh"
@@ -108,224 +108,15 @@ __device__ __forceinline__ void tile_tAB(const float* __restrict__ sT, int PP, i
   }
 }
 
-// cooperative load of one head's rows of a [T, ld] matrix into shared memory [rows_pad][DH+4]; rows >= S are zero
-template <int DH>
-__device__ __forceinline__ void load_head_rows(float* __restrict__ dst, const float* __restrict__ src, size_t tok0, int L,
-                                               int ld, int S, int rows_pad, float mul) {
-  constexpr int P = DH + 4;
-  for (int i = threadIdx.x; i < rows_pad * (DH / 4); i += blockDim.x) {
-    const int s = i / (DH / 4), c = (i % (DH / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (s < S) {
-      v = *reinterpret_cast<const float4*>(src + (tok0 + size_t(s) * L) * ld + c);
-      v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
-    }
-    *reinterpret_cast<float4*>(dst + s * P + c) = v;
-  }
-}
-
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-template <int DH, int NT>
-__global__ void __launch_bounds__(128) attn_lists_fwd_mma_kernel(const float* __restrict__ qkv, float* __restrict__ o,
-                                                                 float* __restrict__ lse, int S, int L, int d, int n_head,
-                                                                 float scale) {
-  constexpr int P = DH + 4;
-  constexpr int ROWS = NT * 8;
-  extern __shared__ float sm[];
-  float* sQ = sm;
-  float* sK = sQ + ROWS * P;
-  float* sV = sK + ROWS * P;
-  const int l = blockIdx.x, g_ = blockIdx.y, h = blockIdx.z;
-  const size_t tok0 = (size_t(g_) * S) * L + l;
-  const int ld = 3 * d;
-  // q is pre-multiplied by scale * log2(e): scores come out in the exp2 domain
-  load_head_rows<DH>(sQ, qkv + h * DH, tok0, L, ld, S, ROWS, scale * kLog2e);
-  load_head_rows<DH>(sK, qkv + d + h * DH, tok0, L, ld, S, ROWS, 1.f);
-  load_head_rows<DH>(sV, qkv + 2 * d + h * DH, tok0, L, ld, S, ROWS, 1.f);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gq = lane >> 2, t = lane & 3;
-  for (int r0 = warp * 16; r0 < S; r0 += 64) {
-    float acc[NT][4];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-    tile_abT<DH, NT, true>(sQ, r0, sK, acc, lane);
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const int c = j * 8 + 2 * t;
-      if (c >= S) acc[j][0] = acc[j][2] = -INFINITY;
-      if (c + 1 >= S) acc[j][1] = acc[j][3] = -INFINITY;
-      m0 = fmaxf(m0, fmaxf(acc[j][0], acc[j][1]));
-      m1 = fmaxf(m1, fmaxf(acc[j][2], acc[j][3]));
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      acc[j][0] = ex2_fast(acc[j][0] - m0); acc[j][1] = ex2_fast(acc[j][1] - m0);
-      acc[j][2] = ex2_fast(acc[j][2] - m1); acc[j][3] = ex2_fast(acc[j][3] - m1);
-      s0 += acc[j][0] + acc[j][1];
-      s1 += acc[j][2] + acc[j][3];
-    }
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-    float oacc[DH / 8][4];
-#pragma unroll
-    for (int n = 0; n < DH / 8; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
-    tile_pB<DH, NT>(acc, sV, oacc, lane);
-    const float i0 = 1.f / s0, i1 = 1.f / s1;
-    const int ra = r0 + gq, rb = r0 + gq + 8;
-    if (ra < S) {
-      float* op = o + (tok0 + size_t(ra) * L) * d + h * DH;
-#pragma unroll
-      for (int n = 0; n < DH / 8; ++n)
-        *reinterpret_cast<float2*>(op + n * 8 + 2 * t) = make_float2(oacc[n][0] * i0, oacc[n][1] * i0);
-      if (t == 0 && lse != nullptr) lse[(tok0 + size_t(ra) * L) * n_head + h] = (m0 + log2f(s0)) * kLn2;
-    }
-    if (rb < S) {
-      float* op = o + (tok0 + size_t(rb) * L) * d + h * DH;
-#pragma unroll
-      for (int n = 0; n < DH / 8; ++n)
-        *reinterpret_cast<float2*>(op + n * 8 + 2 * t) = make_float2(oacc[n][2] * i1, oacc[n][3] * i1);
-      if (t == 0 && lse != nullptr) lse[(tok0 + size_t(rb) * L) * n_head + h] = (m1 + log2f(s1)) * kLn2;
-    }
-  }
-}
-
-template <int DH, int NT>
-__global__ void __launch_bounds__(128, 4) attn_lists_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ o,
-                                                                 const float* __restrict__ lse,
-                                                                 const float* __restrict__ d_o, float* __restrict__ dqkv,
-                                                                 int S, int L, int d, int n_head, float scale) {
-  constexpr int P = DH + 4;
-  constexpr int ROWS = NT * 8;
-  extern __shared__ float sm[];
-  float* sQ = sm;                 // q * scale * log2e
-  float* sK = sQ + ROWS * P;
-  float* sV = sK + ROWS * P;
-  float* sG = sV + ROWS * P;      // dO
-  float* sL = sG + ROWS * P;      // lse * log2e ; +inf for padded rows
-  float* sD = sL + ROWS;          // D_i = dO_i . O_i
-  const int l = blockIdx.x, g_ = blockIdx.y, h = blockIdx.z;
-  const size_t tok0 = (size_t(g_) * S) * L + l;
-  const int ld = 3 * d;
-  load_head_rows<DH>(sQ, qkv + h * DH, tok0, L, ld, S, ROWS, scale * kLog2e);
-  load_head_rows<DH>(sK, qkv + d + h * DH, tok0, L, ld, S, ROWS, 1.f);
-  load_head_rows<DH>(sV, qkv + 2 * d + h * DH, tok0, L, ld, S, ROWS, 1.f);
-  load_head_rows<DH>(sG, d_o + h * DH, tok0, L, d, S, ROWS, 1.f);
-  for (int s = threadIdx.x; s < ROWS; s += blockDim.x) {
-    float lv = INFINITY, dv = 0.f;
-    if (s < S) {
-      const size_t tok = tok0 + size_t(s) * L;
-      lv = lse[tok * n_head + h] * kLog2e;
-      const float* po = o + tok * d + h * DH;
-      const float* pg = d_o + tok * d + h * DH;
-      for (int c = 0; c < DH; ++c) dv = fmaf(po[c], pg[c], dv);
-    }
-    sL[s] = lv;
-    sD[s] = dv;
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gq = lane >> 2, t = lane & 3;
-  // q was scaled by scale*log2e for the exp2-domain scores: dQ = scale * dS K ; dK = dS^T (q_scaled) / log2e
-  const float inv_log2e = 1.f / kLog2e;
-  // ---------------- phase A: query tiles -> dQ
-  for (int r0 = warp * 16; r0 < S; r0 += 64) {
-    float p[NT][4], dp[NT][4];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      p[j][0] = p[j][1] = p[j][2] = p[j][3] = 0.f;
-      dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
-    }
-    tile_abT<DH, NT, true>(sQ, r0, sK, p, lane);
-    tile_abT<DH, NT, false>(sG, r0, sV, dp, lane);
-    const float la = sL[r0 + gq], lb = sL[r0 + gq + 8], da = sD[r0 + gq], db = sD[r0 + gq + 8];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const int c = j * 8 + 2 * t;
-      const bool ok0 = c < S, ok1 = c + 1 < S;
-      p[j][0] = ok0 ? exp2f(p[j][0] - la) * (dp[j][0] - da) : 0.f;
-      p[j][1] = ok1 ? exp2f(p[j][1] - la) * (dp[j][1] - da) : 0.f;
-      p[j][2] = ok0 ? exp2f(p[j][2] - lb) * (dp[j][2] - db) : 0.f;
-      p[j][3] = ok1 ? exp2f(p[j][3] - lb) * (dp[j][3] - db) : 0.f;
-    }
-    float acc[DH / 8][4];
-#pragma unroll
-    for (int n = 0; n < DH / 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-    tile_pB<DH, NT>(p, sK, acc, lane);
-    const int ra = r0 + gq, rb = r0 + gq + 8;
-    if (ra < S) {
-      float* out = dqkv + (tok0 + size_t(ra) * L) * ld + h * DH;
-#pragma unroll
-      for (int n = 0; n < DH / 8; ++n)
-        *reinterpret_cast<float2*>(out + n * 8 + 2 * t) = make_float2(acc[n][0] * scale, acc[n][1] * scale);
-    }
-    if (rb < S) {
-      float* out = dqkv + (tok0 + size_t(rb) * L) * ld + h * DH;
-#pragma unroll
-      for (int n = 0; n < DH / 8; ++n)
-        *reinterpret_cast<float2*>(out + n * 8 + 2 * t) = make_float2(acc[n][2] * scale, acc[n][3] * scale);
-    }
-  }
-  // ---------------- phase B: key tiles (transposed products) -> dK, dV
-  for (int c0 = warp * 16; c0 < S; c0 += 64) {
-    float p[NT][4], dp[NT][4];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      p[j][0] = p[j][1] = p[j][2] = p[j][3] = 0.f;
-      dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
-    }
-    tile_abT<DH, NT, true>(sK, c0, sQ, p, lane);     // [key, query] scores (exp2 domain: q carries the scale)
-    tile_abT<DH, NT, false>(sV, c0, sG, dp, lane);   // [key, query] dP^T
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const int i = j * 8 + 2 * t;                    // query index of columns 0/2 ; i+1 for columns 1/3
-      const float l0 = sL[i], l1 = sL[i + 1], d0 = sD[i], d1 = sD[i + 1];
-      const float p0 = exp2f(p[j][0] - l0), p1 = exp2f(p[j][1] - l1), p2 = exp2f(p[j][2] - l0), p3 = exp2f(p[j][3] - l1);
-      p[j][0] = p0; p[j][1] = p1; p[j][2] = p2; p[j][3] = p3;              // P^T  (0 for padded queries: lse = +inf)
-      dp[j][0] = p0 * (dp[j][0] - d0); dp[j][1] = p1 * (dp[j][1] - d1);    // dS^T
-      dp[j][2] = p2 * (dp[j][2] - d0); dp[j][3] = p3 * (dp[j][3] - d1);
-    }
-    float ak[DH / 8][4], av[DH / 8][4];
-#pragma unroll
-    for (int n = 0; n < DH / 8; ++n) {
-      ak[n][0] = ak[n][1] = ak[n][2] = ak[n][3] = 0.f;
-      av[n][0] = av[n][1] = av[n][2] = av[n][3] = 0.f;
-    }
-    tile_pB<DH, NT>(dp, sQ, ak, lane);
-    tile_pB<DH, NT>(p, sG, av, lane);
-    const int ka = c0 + gq, kb = c0 + gq + 8;
-    if (ka < S) {
-      float* outk = dqkv + (tok0 + size_t(ka) * L) * ld + d + h * DH;
-#pragma unroll
-      for (int n = 0; n < DH / 8; ++n) {
-        *reinterpret_cast<float2*>(outk + n * 8 + 2 * t) = make_float2(ak[n][0] * inv_log2e, ak[n][1] * inv_log2e);
-        *reinterpret_cast<float2*>(outk + d + n * 8 + 2 * t) = make_float2(av[n][0], av[n][1]);
-      }
-    }
-    if (kb < S) {
-      float* outk = dqkv + (tok0 + size_t(kb) * L) * ld + d + h * DH;
-#pragma unroll
-      for (int n = 0; n < DH / 8; ++n) {
-        *reinterpret_cast<float2*>(outk + n * 8 + 2 * t) = make_float2(ak[n][2] * inv_log2e, ak[n][3] * inv_log2e);
-        *reinterpret_cast<float2*>(outk + d + n * 8 + 2 * t) = make_float2(av[n][2], av[n][3]);
-      }
-    }
-  }
-}
-
-
 // ------------------------------------------------------------------------------------------------------------
-// Persistent, software-pipelined versions: a CTA walks work items (group, position, head) with the head index
+// Persistent, software-pipelined kernels: a CTA walks work items (group, position, head) with the head index
 // fastest (neighbouring heads share 128-byte lines of the qkv rows) and stages the next item's rows into the other
 // half of a double buffer with cp.async while the tensor cores work on the current one.  Memory latency is hidden by
-// the pipeline instead of by occupancy (the per-item kernels above are register-limited to 2 CTAs per SM and spend
-// 60% of their samples on the staging loads).  The softmax scale is applied to the accumulator (raw rows are copied).
+// the pipeline instead of by occupancy (the first, one-CTA-per-item kernels were register-limited to 2 CTAs per SM and
+// spent 60% of their samples on the staging loads).  The softmax scale is applied to the accumulator (raw rows are copied).
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
