@@ -27,7 +27,9 @@ def _layer_sd(d, n_head, seed):
 
 @pytest.mark.parametrize("backend", [1, 0])
 @pytest.mark.parametrize("d,n_head,S,L,G", [(128, 8, 5, 40, 1), (128, 8, 16, 300, 1), (256, 4, 7, 33, 2),
-                                            (256, 4, 64, 40, 1), (128, 8, 64, 20, 2)])
+                                            (256, 4, 64, 40, 1), (128, 8, 64, 20, 2),
+                                            # the reference's default batch (63), its test batch (49), a group > 64 lists
+                                            (128, 8, 63, 20, 2), (256, 4, 49, 24, 1), (128, 8, 100, 12, 1)])
 def test_encoder_layer_fwd_bwd_vs_oracle(backend, d, n_head, S, L, G):
     from rlt_b200 import _lib, ops
     from rlt_b200.autograd import EncoderStack
