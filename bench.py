@@ -268,16 +268,20 @@ def main():
         2: ("attention out-projection + residual (gemm_tn, TF32)", T * 3 * d * 4 + d * d * 4),
         3: ("FFN1: h = relu(y W1^T + b1), fp16 operands -> fp16 hidden (gemm_tn, tcgen05 kind::f16)", T * (d + dff) * 2 + dff * d * 2),
         4: ("FFN2: u2 = y + h W2^T + b2, fp16 hidden (gemm_tn, kind::f16)", T * dff * 2 + T * 2 * d * 4 + dff * d * 2),
-        5: ("dH = s (dU2 W2) [h > 0], fp16 in / fp16 out + bias-gradient column sums (gemm_tn, kind::f16)",
+        # d_model 128: the fused kernel (dH, db1 AND dW2 in one pass over h: ffn_bwd_fused.cuh), same bytes as dH alone
+        5: ("FFN backward, one pass over h: dH = s (dU2 W2) [h > 0] (fp16), db1 += colsum, dW2 += dU2^T h "
+            "(ffn_bwd_kernel, tcgen05 kind::f16, K-major + MN-major views of the same tiles)" if d == 128 else
+            "dH = s (dU2 W2) [h > 0], fp16 in / fp16 out + bias-gradient column sums (gemm_tn, kind::f16)",
             T * d * 2 + T * 2 * dff * 2 + dff * d * 2),
         6: ("dY = dU2 + dH W1 / s (gemm_tn, kind::f16)", T * dff * 2 + T * 2 * d * 4 + dff * d * 2),
         7: ("dW2 += dU2^T h (gemm_dw, kind::f16, MN-major operands)", T * (d + dff) * 2),
         8: ("dW1 += dH^T y (gemm_dw, kind::f16, MN-major operands)", T * (d + dff) * 2),
         9: ("cross-list attention forward (mma.sync TF32, cp.async pipeline)", T * (3 * d + d + nh) * 4),
         10: ("cross-list attention backward (mma.sync TF32, cp.async pipeline)", T * (3 * d + d + nh + 3 * d) * 4),
-        # mean over the 4 launches of a step: layer-0 forward has no P tensor (fused projection): saved 6 KB + y 1 KB;
-        # layer-1 forward adds P 4 KB; each backward reads saved 6 KB + dy 1 KB and writes dA 4 KB
-        12: ("BiLSTM recurrence (tcgen05 kind::f16, unit-major; mean of 2 forward + 2 backward launches)", T * 10240),
+        # mean over the 4 launches of a step, per token (both directions): layer-0 forward has no P tensor (fused
+        # projection): saved record 4 KB (fp16 gate pairs 2 KB, c 1 KB, h_prev 1 KB) + y 1 KB; layer-1 forward adds P 4 KB;
+        # each backward reads gates + c 3 KB (c_prev comes from L2) + dy 1 KB and writes dA 4 KB
+        12: ("BiLSTM recurrence (tcgen05 kind::f16, unit-major; mean of 2 forward + 2 backward launches)", T * 7680),
     }
     roof, kernels = None, {}
     if args.time_tag == -1:

@@ -400,8 +400,11 @@ int rlt_bilstm_bwd(const rlt_bilstm_desc* d, const rlt_bilstm_weights* w, const 
     const int K = l == 0 ? F : 2 * H;
     for (int dir = 0; dir < 2; ++dir) {
       const float* dAd = dA + dir * G4;
-      // dW_hh += dA^T Hprev   (Hprev plane of the saved record: row stride 2*6*128 floats)
-      RLT_TRY(gemm_dw(dAd, 2 * G4, sv + dir * (SAVE * H) + 5 * H, 2 * SAVE * H, T, G4, H, g->w_hh[l][dir], H, 1.f, stream));
+      // dW_hh += dA^T Hprev   (Hprev plane of the saved record; the two backends lay the record out differently)
+      if (lstm_backend() == 0)
+        RLT_TRY(gemm_dw(dAd, 2 * G4, sv + dir * U_REC + U_REC_HP, 2 * U_REC, T, G4, H, g->w_hh[l][dir], H, 1.f, stream));
+      else
+        RLT_TRY(gemm_dw(dAd, 2 * G4, sv + dir * (SAVE * H) + 5 * H, 2 * SAVE * H, T, G4, H, g->w_hh[l][dir], H, 1.f, stream));
       if (small_k(K)) {
         const int chunk = 256;
         const int grid = (T + chunk - 1) / chunk;

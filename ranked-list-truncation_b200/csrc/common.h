@@ -65,6 +65,9 @@ int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int 
 // fp16-operand variants (tensor-core backend only): C = A[M,K] B[N,K]^T and C += alpha * alpha_ptr[0] * A[T,M]^T B[T,N]
 int gemm_tn_h(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const EpiParams& ep,
               cudaStream_t stream);
+bool ffn_bwd_fused_ok(int d, int f);
+int ffn_bwd_fused(const __half* du16, const __half* w2th, const __half* hh, __half* dh16, int T, int d, int f, float alpha,
+                  const float* scale, float* db1, float* dW2, cudaStream_t stream, int tag);
 int gemm_dw_h(const __half* A, int lda, const __half* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
               const float* alpha_ptr, cudaStream_t stream, int tag = 0);
 // dst = half(src * scale[0]) (scale may be null); dst[c, r] = half(src[r, c])

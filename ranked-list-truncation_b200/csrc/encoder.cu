@@ -732,14 +732,19 @@ int rlt_encoder_layer_bwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
     RLT_TRY(pow2_scale(amax, scale, 6, stream));
     // the FFN branch sees dropout2(dU2); the residual branch below keeps the undropped d_u
     RLT_TRY(convert_f16(d_u, du16, size_t(T) * d, scale, stream, drop, DROP_AFTER_FFN));
-    // dW2 += dU2^T h
-    RLT_TRY(gemm_dw_h(du16, d, hh, f, T, d, f, gw->lin2_w, f, 1.f, scale + 1, stream, TAG_DW_FFN2));
-    // dHpre = ((s dU2) W2) * (h > 0) -> fp16 (the scale rides on the fp16 operand) ; db1 += colsum(dHpre) / s
     const __half* w2th = w1th + 2 * size_t(d) * f;
     EpiParams ep{};
-    ep.alpha = drop.scale; ep.out_h = dh16; ep.ldo = f; ep.gate_h = hh; ep.colsum = gw->lin1_b; ep.scale_ptr = scale;
-    ep.scale_mode = 3; ep.tag = TAG_D_FFN2;     // h is the dropped hidden: [h > 0] is relu-mask AND keep-mask; 1/(1-p) via alpha
-    RLT_TRY(gemm_tn_h(du16, d, w2th, d, T, f, d, ep, stream));
+    if (ffn_bwd_fused_ok(d, f)) {
+      // one pass over h: dHpre (fp16), db1 += colsum(dHpre) / s, dW2 += (s dU2)^T h / s
+      RLT_TRY(ffn_bwd_fused(du16, w2th, hh, dh16, T, d, f, drop.scale, scale, gw->lin1_b, gw->lin2_w, stream, TAG_D_FFN2));
+    } else {
+      // dW2 += dU2^T h
+      RLT_TRY(gemm_dw_h(du16, d, hh, f, T, d, f, gw->lin2_w, f, 1.f, scale + 1, stream, TAG_DW_FFN2));
+      // dHpre = ((s dU2) W2) * (h > 0) -> fp16 (the scale rides on the fp16 operand) ; db1 += colsum(dHpre) / s
+      ep.alpha = drop.scale; ep.out_h = dh16; ep.ldo = f; ep.gate_h = hh; ep.colsum = gw->lin1_b; ep.scale_ptr = scale;
+      ep.scale_mode = 3; ep.tag = TAG_D_FFN2;     // h is the dropped hidden: [h > 0] is relu-mask AND keep-mask; 1/(1-p) via alpha
+      RLT_TRY(gemm_tn_h(du16, d, w2th, d, T, f, d, ep, stream));
+    }
     // dW1 += dHpre^T y
     RLT_TRY(gemm_dw_h(dh16, f, y16, d, T, f, d, gw->lin1_w, d, 1.f, scale + 1, stream, TAG_DW_FFN1));
     // dY = dU2 + (dHpre W1) / s

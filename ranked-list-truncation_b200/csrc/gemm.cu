@@ -13,6 +13,7 @@
 #include "common.h"
 #include "gemm_tc.cuh"
 #include "gemm_f16out.cuh"
+#include "ffn_bwd_fused.cuh"
 
 namespace rlt {
 
@@ -40,6 +41,7 @@ static int g_gemm_backend = env_int("RLT_GEMM_BACKEND", 0);
 // tensor core would truncate the low 13 mantissa bits (a systematic -2^-11 relative bias per operand).
 static int g_tma_round = env_int("RLT_TMA_ROUND", 1);
 static int g_b_resident = env_int("RLT_B_RESIDENT", 1);
+static int g_ffn_bwd_fused = env_int("RLT_FFN_BWD_FUSED", 1);   // one-pass dH / dW1 / dW2 / db1 kernel (d_model 128)
 static int g_f16out_tma = env_int("RLT_F16OUT_TMA", 1);     // copy-engine epilogue kernel for the fp16-output GEMMs   // gemm_tn: keep the CTA's B slice in shared memory when it fits
 
 static std::atomic<unsigned long long> g_launches{0};
@@ -403,6 +405,33 @@ int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int 
   return launch_dw<32, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, nullptr, stream);
 }
 
+// Fused FFN backward (ffn_bwd_fused.cuh): dH (fp16), db1 and dW2 in one pass over h.
+bool ffn_bwd_fused_ok(int d, int f) {
+  return g_ffn_bwd_fused != 0 && gemm_backend() == 0 && d == FfnBwdCfg::D && f % FfnBwdCfg::BN == 0 && f / FfnBwdCfg::BN <= num_sms();
+}
+int ffn_bwd_fused(const __half* du16, const __half* w2th, const __half* hh, __half* dh16, int T, int d, int f, float alpha,
+                  const float* scale, float* db1, float* dW2, cudaStream_t stream, int tag) {
+  using Cfg = FfnBwdCfg;
+  RLT_REQUIRE(ffn_bwd_fused_ok(d, f), RLT_UNSUPPORTED_SHAPE, "ffn_bwd_fused: d=%d f=%d unsupported", d, f);
+  CUtensorMap tmDU, tmW2, tmH, tmDH;
+  RLT_TRY(make_tmap_h(&tmDU, du16, T, d, d, Cfg::BM));
+  RLT_TRY(make_tmap_h(&tmW2, w2th, f, d, d, Cfg::BN));
+  RLT_TRY(make_tmap_h(&tmH, hh, T, f, f, Cfg::BM));
+  RLT_TRY(make_tmap_any(&tmDH, dh16, 2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, T, f, f, 32, false, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(ffn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
+    attr_set = true;
+  }
+  const int tiles_m = (T + Cfg::BM - 1) / Cfg::BM, tiles_n = f / Cfg::BN;
+  int walkers = num_sms() / tiles_n;
+  if (walkers > tiles_m) walkers = tiles_m;
+  TimeScope scope(tag, stream);
+  ffn_bwd_kernel<<<walkers * tiles_n, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmDU, tmW2, tmH, tmDH, T, f, alpha, scale, db1, dW2);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+
 int gemm_dw_h(const __half* A, int lda, const __half* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
               const float* alpha_ptr, cudaStream_t stream, int tag) {
   TimeScope scope(tag, stream);
@@ -652,6 +681,7 @@ int rlt_set_option(const char* key, int value) {
   if (strcmp(key, "tma_round") == 0) { g_tma_round = value; return RLT_OK; }
   if (strcmp(key, "b_resident") == 0) { g_b_resident = value; return RLT_OK; }
   if (strcmp(key, "f16out_tma") == 0) { g_f16out_tma = value; return RLT_OK; }
+  if (strcmp(key, "ffn_bwd_fused") == 0) { g_ffn_bwd_fused = value; return RLT_OK; }
   return set_error(RLT_INVALID_ARG, "rlt_set_option: unknown option '%s'", key);
 }
 int rlt_get_option(const char* key) {
@@ -660,6 +690,7 @@ int rlt_get_option(const char* key) {
   if (strcmp(key, "tma_round") == 0) return g_tma_round;
   if (strcmp(key, "b_resident") == 0) return g_b_resident;
   if (strcmp(key, "f16out_tma") == 0) return g_f16out_tma;
+  if (strcmp(key, "ffn_bwd_fused") == 0) return g_ffn_bwd_fused;
   if (strcmp(key, "time_tag") == 0) return g_time_tag;
   if (strcmp(key, "lstm_backend") == 0) return lstm_backend();
   return set_error(RLT_INVALID_ARG, "rlt_get_option: unknown option '%s'", key);

@@ -27,7 +27,11 @@ namespace rlt {
 
 constexpr int UH = 128;          // hidden units
 constexpr int UG4 = 512;         // gate rows
-constexpr int USAVE = 6;         // saved planes per (token, direction): i, f, g, o, c, h_{t-1}
+// Saved record per (token, direction), U_REC 32-bit words: [0,128) half2(i, f) | [128,256) half2(g, o) | [256,384) c fp32 |
+// [384,512) h_{t-1} fp32.  The gate activations only feed the backward's products (11-bit significand is what the
+// TF32 GEMMs consuming dA keep anyway); c stays fp32 because tanh(c) and c_{t-1} multiply the recurrent gradient.
+constexpr int U_REC = 512;
+constexpr int U_REC_GO = 128, U_REC_C = 256, U_REC_HP = 384;
 constexpr int U_TILE = 64;       // lists per CTA
 constexpr int U_HALF = 32;       // lists per pipeline half (= MMA N)
 constexpr int U_CELLS = 16;      // lists per gate thread
@@ -73,6 +77,18 @@ __device__ __forceinline__ unsigned short f32_to_f16_bits(float x) {
   unsigned short r;
   asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
   return r;
+}
+
+// two fp32 values as one 32-bit word of fp16 (lo, hi), and back
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t w, float& lo, float& hi) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+  lo = f.x;
+  hi = f.y;
 }
 
 struct LstmUmFwdSmem {
@@ -201,7 +217,7 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
     // form compiled to (ncu: 22 % of the kernel's instructions were IMAD, 36 per cell).
     const uint32_t Lu = uint32_t(L);
     const uint32_t tok_list0 = uint32_t(list0) * Lu;      // token index of (list0, t = 0)
-    const uint32_t cP = uint32_t(dir * UG4 + u), cY = uint32_t(dir * UH + u), cS = uint32_t(dir * (USAVE * UH) + u);
+    const uint32_t cP = uint32_t(dir * UG4 + u), cY = uint32_t(dir * UH + u), cS = uint32_t(dir * U_REC + u);
     // fused input projection: this unit's four W_ih rows (F <= 4 columns, zero padded) and summed biases
     float wi[4][4], bsum[4];
     if (kFusedIn) {
@@ -238,8 +254,8 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
     for (int step = 0; step < L; ++step) {
       const int t = dir ? (L - 1 - step) : step;
       const uint32_t tokb = tok_list0 + uint32_t(t);       // token of this thread's first list at this step
-      // h_t is the "previous h" plane of the NEXT step's record: +-1 token, plane 5
-      const uint32_t dnext = (dir ? 0u - uint32_t(2 * USAVE * UH) : uint32_t(2 * USAVE * UH)) + uint32_t(5 * UH);
+      // h_t is the "previous h" plane of the NEXT step's record: +-1 token
+      const uint32_t dnext = (dir ? 0u - uint32_t(2 * U_REC) : uint32_t(2 * U_REC)) + uint32_t(U_REC_HP);
       const bool has_next = step + 1 < L;
       float pc[4][U_CHUNK];
       load_pre(pc, tokb, 0);
@@ -266,11 +282,13 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
           const float hv = go * tanh_2mufu(cn);
           if (live) {
             if (saved != nullptr) {
-              const uint32_t so = tk * uint32_t(2 * USAVE * UH) + cS;
+              const uint32_t so = tk * uint32_t(2 * U_REC) + cS;
               float* sv = saved + so;
-              sv[0 * UH] = gi; sv[1 * UH] = gf; sv[2 * UH] = gg; sv[3 * UH] = go; sv[4 * UH] = cn;
-              if (step == 0) sv[5 * UH] = 0.f;
-              if (has_next) saved[so + dnext] = hv;
+              sv[0] = __uint_as_float(pack_f16x2(gi, gf));
+              sv[U_REC_GO] = __uint_as_float(pack_f16x2(gg, go));
+              sv[U_REC_C] = cn;
+              if (step == 0) sv[U_REC_HP] = 0.f;
+              if (has_next) saved[uint32_t(so + dnext)] = hv;
             }
             y[tk * uint32_t(2 * UH) + cY] = hv;
           }
@@ -382,7 +400,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
       }
     }
   } else if (warp == 17) {
-    // L2 prefetch of the saved record (i, f, g, o, c: 2.5 KB) and dy row (512 B) of the step kAhead ahead
+    // L2 prefetch of the saved record (gates + c: 1.5 KB) and dy row (512 B) of the step kAhead ahead
     constexpr int kAhead = 2;
     for (int it = 0; it < L; ++it) {
       while (*s_progress < it - kAhead) __nanosleep(200);
@@ -392,7 +410,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
         const int bb = tile * U_TILE + r;
         if (bb < B) {
           const size_t tok = size_t(bb) * L + t;
-          prefetch_l2_bulk(saved + (tok * 2 + dir) * (USAVE * UH), 5 * UH * 4);
+          prefetch_l2_bulk(saved + (tok * 2 + dir) * U_REC, U_REC_HP * 4);
           prefetch_l2_bulk(dy + tok * (2 * UH) + dir * UH, UH * 4);
         }
       }
@@ -415,20 +433,21 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
     // 32-bit element offsets from the tensor bases, as in the forward kernel
     const uint32_t Lu = uint32_t(L);
     const uint32_t tok_list0 = uint32_t(list0) * Lu;
-    const uint32_t cS = uint32_t(dir * (USAVE * UH) + u), cY = uint32_t(dir * UH + u), cA = uint32_t(dir * UG4 + u);
+    const uint32_t cS = uint32_t(dir * U_REC + u), cY = uint32_t(dir * UH + u), cA = uint32_t(dir * UG4 + u);
     float dbs[4] = {0.f, 0.f, 0.f, 0.f};                // this unit's share of db = sum over (list, t) of da
-    // i, f, g, o, c of the step, c of the previous step, dy: U_CHUNK lists whose first token index is tok
-    auto load_rec = [&](float (&dst)[7][U_CHUNK], uint32_t tok, int c0, bool has_prev, uint32_t dprev) {
+    // (i, f), (g, o), c of the step, c of the previous step, dy: U_CHUNK lists whose first token index is tok
+    auto load_rec = [&](float (&dst)[5][U_CHUNK], uint32_t tok, int c0, bool has_prev, uint32_t dprev) {
 #pragma unroll
       for (int li = 0; li < U_CHUNK; ++li) {
         const bool live = list0 + c0 + li < B;
         const uint32_t tk = tok + uint32_t(li) * Lu;
-        const uint32_t so = tk * uint32_t(2 * USAVE * UH) + cS;
+        const uint32_t so = tk * uint32_t(2 * U_REC) + cS;
         const float* sr = saved + so;
-#pragma unroll
-        for (int pl = 0; pl < 5; ++pl) dst[pl][li] = live ? __ldg(sr + pl * UH) : 0.f;
-        dst[5][li] = (live && has_prev) ? __ldg(saved + uint32_t(so + dprev)) : 0.f;   // offset sum wraps in 32 bits
-        dst[6][li] = live ? __ldg(dy + (tk * uint32_t(2 * UH) + cY)) : 0.f;
+        dst[0][li] = live ? __ldg(sr) : 0.f;
+        dst[1][li] = live ? __ldg(sr + U_REC_GO) : 0.f;
+        dst[2][li] = live ? __ldg(sr + U_REC_C) : 0.f;
+        dst[3][li] = (live && has_prev) ? __ldg(saved + uint32_t(so + dprev)) : 0.f;   // offset sum wraps in 32 bits
+        dst[4][li] = live ? __ldg(dy + (tk * uint32_t(2 * UH) + cY)) : 0.f;
       }
     };
 
@@ -436,11 +455,11 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
       const int step = L - 1 - it;                      // forward step index being differentiated
       const int t = dir ? (L - 1 - step) : step;
       const uint32_t tokb = tok_list0 + uint32_t(t);
-      // c_{t-1} lives in the record of the previous forward step: -+1 token, plane 4 (relative to plane 0 of this one)
-      const uint32_t dprev = (dir ? uint32_t(2 * USAVE * UH) : 0u - uint32_t(2 * USAVE * UH)) + uint32_t(4 * UH);
+      // c_{t-1} lives in the record of the previous forward step: -+1 token
+      const uint32_t dprev = (dir ? uint32_t(2 * U_REC) : 0u - uint32_t(2 * U_REC)) + uint32_t(U_REC_C);
       const bool has_prev = step > 0;
       // operands of the first chunk: in flight while the tensor core finishes dh_rec
-      float vc[7][U_CHUNK];   // i, f, g, o, c, c_prev, dy
+      float vc[5][U_CHUNK];   // (i, f), (g, o), c, c_prev, dy
       load_rec(vc, tokb, 0, has_prev, dprev);
       if (it > 0) {
         mbar_wait(&bar_d[hf], (it - 1) & 1);
@@ -456,14 +475,17 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
 #pragma unroll
           for (int li = 0; li < U_CHUNK; ++li) dhr[li] = 0.f;
         }
-        float vn[7][U_CHUNK];
+        float vn[5][U_CHUNK];
         if (ch + 1 < U_CELLS / U_CHUNK) load_rec(vn, tok_ch + U_CHUNK * Lu, (ch + 1) * U_CHUNK, has_prev, dprev);
 #pragma unroll
         for (int li = 0; li < U_CHUNK; ++li) {
           const int cell = ch * U_CHUNK + li;
           const bool live = list0 + cell < B;
-          const float gi = vc[0][li], gf = vc[1][li], gg = vc[2][li], go = vc[3][li], cc = vc[4][li], cp = vc[5][li];
-          const float dh = fmaf(dhr[li], inv_scale, vc[6][li]);
+          float gi, gf, gg, go;
+          unpack_f16x2(__float_as_uint(vc[0][li]), gi, gf);
+          unpack_f16x2(__float_as_uint(vc[1][li]), gg, go);
+          const float cc = vc[2][li], cp = vc[3][li];
+          const float dh = fmaf(dhr[li], inv_scale, vc[4][li]);
           const float tc = tanh_2mufu(cc);
           const float d_o = dh * tc;
           const float dc = fmaf(dh * go, 1.f - tc * tc, sDC[cell * 512 + gt]);
@@ -485,7 +507,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
           *reinterpret_cast<unsigned short*>(dst + 3 * 2 * LstmUmBwdSmem::DA_KB) = f32_to_f16_bits(dao * scale);
         }
 #pragma unroll
-        for (int pl = 0; pl < 7; ++pl)
+        for (int pl = 0; pl < 5; ++pl)
 #pragma unroll
           for (int li = 0; li < U_CHUNK; ++li) vc[pl][li] = vn[pl][li];
       }
