@@ -128,62 +128,87 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// rows [0, S) of one head of a [T, ld] matrix -> dst[s][DH + 4] (asynchronous; rows >= S are never written)
-template <int DH>
-__device__ __forceinline__ void stage_head_rows(float* __restrict__ dst, const float* __restrict__ src, size_t tok0, int L,
-                                                int ld, int S) {
-  constexpr int P = DH + 4;
-  for (int i = threadIdx.x; i < S * (DH / 4); i += blockDim.x) {
-    const int s_ = i / (DH / 4), c = (i % (DH / 4)) * 4;
-    cp_async16(dst + s_ * P + c, src + (tok0 + size_t(s_) * L) * ld + c);
-  }
-}
-
-struct AttnItem {
-  size_t tok0;
-  int h;
+// Work item (group g, position l, head h), head fastest.  A CTA visits items blockIdx.x, + gridDim.x, ...: the
+// (g, l, h) digits are advanced with carries instead of being re-derived by division (the 64-bit divisions and the
+// 64-bit address products of every staged 16-byte chunk were ~25 % of the kernels' instructions).
+struct AttnPos {
+  int g, l, h;
 };
-__device__ __forceinline__ AttnItem attn_item(long long i, int S, int L, int n_head) {
-  AttnItem it;
-  it.h = int(i % n_head);
-  const long long r = i / n_head;
-  const int l = int(r % L);
-  const long long g = r / L;
-  it.tok0 = size_t(g) * S * L + l;
-  return it;
-}
+struct AttnWalk {
+  int dg, dl, dh, L, n_head;
+  __device__ __forceinline__ AttnWalk(int step, int L_, int n_head_) : L(L_), n_head(n_head_) {
+    dh = step % n_head_;
+    const int r = step / n_head_;
+    dl = r % L_;
+    dg = r / L_;
+  }
+  __device__ __forceinline__ AttnPos first(int item) const {
+    AttnPos p;
+    p.h = item % n_head;
+    const int r = item / n_head;
+    p.l = r % L;
+    p.g = r / L;
+    return p;
+  }
+  __device__ __forceinline__ AttnPos next(AttnPos p) const {
+    p.h += dh;
+    int c = p.h >= n_head ? 1 : 0;
+    p.h -= c ? n_head : 0;
+    p.l += dl + c;
+    c = p.l >= L ? 1 : 0;
+    p.l -= c ? L : 0;
+    p.g += dg + c;
+    return p;
+  }
+};
+// token index of list 0 of the item's group at the item's position
+__device__ __forceinline__ size_t attn_tok0(const AttnPos& p, int S, int L) { return size_t(p.g) * S * L + p.l; }
 
 // kDrop: train-mode dropout on the attention probabilities (a separate instantiation: the hash code costs registers)
-template <int DH, int NT, bool kDrop>
+// kFull: S == 8 NT (no padded rows / columns: the bounds predicates compile away)
+template <int DH, int NT, bool kDrop, bool kFull>
 __global__ void __launch_bounds__(128) attn_lists_fwd_pipe_kernel(const float* __restrict__ qkv, float* __restrict__ o,
                                                                   float* __restrict__ lse, int S, int L, int d, int n_head,
-                                                                  float scale, long long n_items, DropCfg drop) {
+                                                                  float scale, int n_items, DropCfg drop) {
   constexpr int P = DH + 4;
   constexpr int ROWS = NT * 8;
   constexpr int BUF = 3 * ROWS * P;
+  constexpr int CH = DH / 4, RS = 128 / CH;     // 16-byte chunks per row; rows covered by one pass of the 128 threads
   extern __shared__ float sm[];
   const int ld = 3 * d;
-  for (int i = threadIdx.x; i < 2 * BUF; i += blockDim.x) sm[i] = 0.f;   // padded rows stay zero for the whole kernel
+  for (int i = threadIdx.x; i < 2 * BUF; i += 128) sm[i] = 0.f;   // padded rows stay zero for the whole kernel
   __syncthreads();
-  auto stage = [&](long long item, int b) {
-    const AttnItem it = attn_item(item, S, L, n_head);
-    float* base = sm + b * BUF;
-    stage_head_rows<DH>(base, qkv + it.h * DH, it.tok0, L, ld, S);
-    stage_head_rows<DH>(base + ROWS * P, qkv + d + it.h * DH, it.tok0, L, ld, S);
-    stage_head_rows<DH>(base + 2 * ROWS * P, qkv + 2 * d + it.h * DH, it.tok0, L, ld, S);
+  // staging: thread -> (row s0 + k RS, chunk c0) of every matrix; 32-bit element offsets from the item's base pointer
+  const int s0 = threadIdx.x / CH, c0 = (threadIdx.x % CH) * 4;
+  const uint32_t goff0 = uint32_t(s0) * uint32_t(L) * uint32_t(ld) + uint32_t(c0), gstep = uint32_t(RS) * uint32_t(L) * uint32_t(ld);
+  const int soff0 = s0 * P + c0;
+  const AttnWalk walk(int(gridDim.x), L, n_head);
+  auto stage = [&](const AttnPos& it, int b) {
+    float* base = sm + b * BUF + soff0;
+    const float* src = qkv + attn_tok0(it, S, L) * ld + it.h * DH;
+    uint32_t go = goff0;
+    int so = 0;
+    for (int s_ = s0; s_ < S; s_ += RS, go += gstep, so += RS * P) {
+      cp_async16(base + so, src + go);
+      cp_async16(base + ROWS * P + so, src + d + go);
+      cp_async16(base + 2 * ROWS * P + so, src + 2 * d + go);
+    }
     cp_async_commit();
   };
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gq = lane >> 2, t = lane & 3;
   const float sc = scale * kLog2e;
-  long long item = blockIdx.x;
-  if (item < n_items) stage(item, 0);
+  int item = blockIdx.x;
+  AttnPos cur = walk.first(item);
+  if (item < n_items) stage(cur, 0);
   int b = 0;
   for (; item < n_items; item += gridDim.x, b ^= 1) {
-    const long long nxt = item + gridDim.x;
-    if (nxt < n_items) { stage(nxt, b ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    const AttnPos nxt = walk.next(cur);
+    if (item + int(gridDim.x) < n_items) { stage(nxt, b ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
-    const AttnItem it = attn_item(item, S, L, n_head);
+    const size_t tok0 = attn_tok0(cur, S, L);
+    float* o_item = o + tok0 * d + cur.h * DH;
+    float* lse_item = lse != nullptr ? lse + tok0 * n_head + cur.h : nullptr;
     const float* sQ = sm + b * BUF;
     const float* sK = sQ + ROWS * P;
     const float* sV = sK + ROWS * P;
@@ -196,23 +221,24 @@ __global__ void __launch_bounds__(128) attn_lists_fwd_pipe_kernel(const float* _
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         const int c = j * 8 + 2 * t;
-        acc[j][0] = c < S ? acc[j][0] * sc : -INFINITY; acc[j][2] = c < S ? acc[j][2] * sc : -INFINITY;
-        acc[j][1] = c + 1 < S ? acc[j][1] * sc : -INFINITY; acc[j][3] = c + 1 < S ? acc[j][3] * sc : -INFINITY;
+        const bool ok0 = kFull || c < S, ok1 = kFull || c + 1 < S;
+        acc[j][0] = ok0 ? acc[j][0] * sc : -INFINITY; acc[j][2] = ok0 ? acc[j][2] * sc : -INFINITY;
+        acc[j][1] = ok1 ? acc[j][1] * sc : -INFINITY; acc[j][3] = ok1 ? acc[j][3] * sc : -INFINITY;
         m0 = fmaxf(m0, fmaxf(acc[j][0], acc[j][1]));
         m1 = fmaxf(m1, fmaxf(acc[j][2], acc[j][3]));
       }
       m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
       m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-      float s0 = 0.f, s1 = 0.f;
+      float s0_ = 0.f, s1_ = 0.f;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         acc[j][0] = ex2_fast(acc[j][0] - m0); acc[j][1] = ex2_fast(acc[j][1] - m0);
         acc[j][2] = ex2_fast(acc[j][2] - m1); acc[j][3] = ex2_fast(acc[j][3] - m1);
-        s0 += acc[j][0] + acc[j][1];
-        s1 += acc[j][2] + acc[j][3];
+        s0_ += acc[j][0] + acc[j][1];
+        s1_ += acc[j][2] + acc[j][3];
       }
-      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      s0_ += __shfl_xor_sync(0xffffffffu, s0_, 1); s0_ += __shfl_xor_sync(0xffffffffu, s0_, 2);
+      s1_ += __shfl_xor_sync(0xffffffffu, s1_, 1); s1_ += __shfl_xor_sync(0xffffffffu, s1_, 2);
       const int ra = r0 + gq, rb = r0 + gq + 8;
       if (kDrop) {   // dropout on the attention probabilities (the row sums above stay undropped)
         const uint64_t ea = (uint64_t(item) * S + ra) * S, eb = (uint64_t(item) * S + rb) * S;
@@ -227,23 +253,25 @@ __global__ void __launch_bounds__(128) attn_lists_fwd_pipe_kernel(const float* _
 #pragma unroll
       for (int n = 0; n < DH / 8; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
       tile_pB<DH, NT>(acc, sV, oacc, lane);
-      const float i0 = 1.f / s0, i1 = 1.f / s1;
-      if (ra < S) {
-        float* op = o + (it.tok0 + size_t(ra) * L) * d + it.h * DH;
+      const float i0 = 1.f / s0_, i1 = 1.f / s1_;
+      const uint32_t rowa = uint32_t(ra) * uint32_t(L), rowb = uint32_t(rb) * uint32_t(L);   // token offsets of the two rows
+      if (kFull || ra < S) {
+        float* op = o_item + rowa * uint32_t(d);
 #pragma unroll
         for (int n = 0; n < DH / 8; ++n)
           *reinterpret_cast<float2*>(op + n * 8 + 2 * t) = make_float2(oacc[n][0] * i0, oacc[n][1] * i0);
-        if (t == 0 && lse != nullptr) lse[(it.tok0 + size_t(ra) * L) * n_head + it.h] = (m0 + log2f(s0)) * kLn2;
+        if (t == 0 && lse_item != nullptr) lse_item[rowa * uint32_t(n_head)] = (m0 + log2f(s0_)) * kLn2;
       }
-      if (rb < S) {
-        float* op = o + (it.tok0 + size_t(rb) * L) * d + it.h * DH;
+      if (kFull || rb < S) {
+        float* op = o_item + rowb * uint32_t(d);
 #pragma unroll
         for (int n = 0; n < DH / 8; ++n)
           *reinterpret_cast<float2*>(op + n * 8 + 2 * t) = make_float2(oacc[n][2] * i1, oacc[n][3] * i1);
-        if (t == 0 && lse != nullptr) lse[(it.tok0 + size_t(rb) * L) * n_head + it.h] = (m1 + log2f(s1)) * kLn2;
+        if (t == 0 && lse_item != nullptr) lse_item[rowb * uint32_t(n_head)] = (m1 + log2f(s1_)) * kLn2;
       }
     }
     __syncthreads();   // every warp is done with buffer b before the next iteration refills it
+    cur = nxt;
   }
 }
 
@@ -252,11 +280,11 @@ __global__ void __launch_bounds__(128) attn_lists_fwd_pipe_kernel(const float* _
 // dK / dV instead of recomputing the scores a second time (the kernel is instruction-issue bound).
 // kBufs: 2 = cp.async double buffer over items; 1 = single staging buffer (large head dims: two buffers would leave room
 // for ONE CTA per SM; a second resident CTA hides the staging latency instead)
-template <int DH, int NT, bool kDrop, int kBufs>
+template <int DH, int NT, bool kDrop, int kBufs, bool kFull>
 __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* __restrict__ qkv, const float* __restrict__ lse,
                                                                   const float* __restrict__ d_o, float* __restrict__ dqkv,
                                                                   int S, int L, int d, int n_head, float scale,
-                                                                  long long n_items, DropCfg drop) {
+                                                                  int n_items, DropCfg drop) {
   constexpr int P = DH + 4;
   constexpr int ROWS = NT * 8;
   constexpr int BUF = 4 * ROWS * P + ROWS;      // q, k, v, dO rows + lse
@@ -265,38 +293,53 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
   float* sPm = sm + kBufs * BUF;                // [ROWS][PP] (dropped) probabilities of the current item
   float* sS = sPm + ROWS * PP;                  // [ROWS][PP] dS of the current item
   const int ld = 3 * d;
-  for (int i = threadIdx.x; i < kBufs * BUF + 2 * ROWS * PP; i += blockDim.x) sm[i] = 0.f;   // padded rows stay zero
+  for (int i = threadIdx.x; i < kBufs * BUF + 2 * ROWS * PP; i += 128) sm[i] = 0.f;   // padded rows stay zero
   __syncthreads();
   for (int b = 0; b < kBufs; ++b)
-    for (int s_ = S + threadIdx.x; s_ < ROWS; s_ += blockDim.x) sm[b * BUF + 4 * ROWS * P + s_] = INFINITY;  // padded queries: P = 0
+    for (int s_ = S + threadIdx.x; s_ < ROWS; s_ += 128) sm[b * BUF + 4 * ROWS * P + s_] = INFINITY;  // padded queries: P = 0
   __syncthreads();
-  auto stage = [&](long long item, int b) {
-    const AttnItem it = attn_item(item, S, L, n_head);
+  // staging: thread -> (row s0 + k RS, chunk c0) of every matrix; 32-bit element offsets from the item's base pointers
+  constexpr int CH = DH / 4, RS = 128 / CH;
+  const int s0 = threadIdx.x / CH, c0 = (threadIdx.x % CH) * 4;
+  const uint32_t rowtok = uint32_t(s0) * uint32_t(L), rowstep = uint32_t(RS) * uint32_t(L);
+  const int soff0 = s0 * P + c0;
+  const AttnWalk walk(int(gridDim.x), L, n_head);
+  auto stage = [&](const AttnPos& it, int b) {
     float* base = sm + b * BUF;
-    stage_head_rows<DH>(base, qkv + it.h * DH, it.tok0, L, ld, S);
-    stage_head_rows<DH>(base + ROWS * P, qkv + d + it.h * DH, it.tok0, L, ld, S);
-    stage_head_rows<DH>(base + 2 * ROWS * P, qkv + 2 * d + it.h * DH, it.tok0, L, ld, S);
-    stage_head_rows<DH>(base + 3 * ROWS * P, d_o + it.h * DH, it.tok0, L, d, S);
-    for (int s_ = threadIdx.x; s_ < S; s_ += blockDim.x)
-      cp_async4(base + 4 * ROWS * P + s_, lse + (it.tok0 + size_t(s_) * L) * n_head + it.h);
+    const size_t tok0 = attn_tok0(it, S, L);
+    const float* src = qkv + tok0 * ld + it.h * DH + c0;
+    const float* srcg = d_o + tok0 * d + it.h * DH + c0;
+    uint32_t rt = rowtok;
+    int so = soff0;
+    for (int s_ = s0; s_ < S; s_ += RS, rt += rowstep, so += RS * P) {
+      const uint32_t go = rt * uint32_t(ld);
+      cp_async16(base + so, src + go);
+      cp_async16(base + ROWS * P + so, src + d + go);
+      cp_async16(base + 2 * ROWS * P + so, src + 2 * d + go);
+      cp_async16(base + 3 * ROWS * P + so, srcg + rt * uint32_t(d));
+    }
+    const float* srcl = lse + tok0 * n_head + it.h;
+    for (int s_ = threadIdx.x; s_ < S; s_ += 128)
+      cp_async4(base + 4 * ROWS * P + s_, srcl + uint32_t(s_) * uint32_t(L) * uint32_t(n_head));
     cp_async_commit();
   };
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gq = lane >> 2, t = lane & 3;
   const float sc = scale * kLog2e;
-  long long item = blockIdx.x;
-  if (kBufs == 2 && item < n_items) stage(item, 0);
+  int item = blockIdx.x;
+  AttnPos cur = walk.first(item);
+  if (kBufs == 2 && item < n_items) stage(cur, 0);
   int b = 0;
   for (; item < n_items; item += gridDim.x, b ^= (kBufs - 1)) {
+    const AttnPos nxt = walk.next(cur);
     if (kBufs == 2) {
-      const long long nxt = item + gridDim.x;
-      if (nxt < n_items) { stage(nxt, b ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+      if (item + int(gridDim.x) < n_items) { stage(nxt, b ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     } else {
-      stage(item, 0);
+      stage(cur, 0);
       cp_async_wait<0>();
     }
     __syncthreads();
-    const AttnItem it = attn_item(item, S, L, n_head);
+    float* dq_item = dqkv + attn_tok0(cur, S, L) * ld + cur.h * DH;
     const float* sQ = sm + b * BUF;
     const float* sK = sQ + ROWS * P;
     const float* sV = sK + ROWS * P;
@@ -319,7 +362,7 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         const int c = j * 8 + 2 * t;
-        const bool ok0 = c < S, ok1 = c + 1 < S;
+        const bool ok0 = kFull || c < S, ok1 = kFull || c + 1 < S;
         p[j][0] = ok0 ? ex2_fast(fmaf(p[j][0], sc, -la)) : 0.f;
         p[j][1] = ok1 ? ex2_fast(fmaf(p[j][1], sc, -la)) : 0.f;
         p[j][2] = ok0 ? ex2_fast(fmaf(p[j][2], sc, -lb)) : 0.f;
@@ -353,14 +396,14 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
       for (int n = 0; n < DH / 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
       tile_pB<DH, NT>(p, sK, acc, lane);
       const int ra = r0 + gq, rb = r0 + gq + 8;
-      if (ra < S) {
-        float* out = dqkv + (it.tok0 + size_t(ra) * L) * ld + it.h * DH;
+      if (kFull || ra < S) {
+        float* out = dq_item + uint32_t(ra) * uint32_t(L) * uint32_t(ld);
 #pragma unroll
         for (int n = 0; n < DH / 8; ++n)
           *reinterpret_cast<float2*>(out + n * 8 + 2 * t) = make_float2(acc[n][0] * scale, acc[n][1] * scale);
       }
-      if (rb < S) {
-        float* out = dqkv + (it.tok0 + size_t(rb) * L) * ld + it.h * DH;
+      if (kFull || rb < S) {
+        float* out = dq_item + uint32_t(rb) * uint32_t(L) * uint32_t(ld);
 #pragma unroll
         for (int n = 0; n < DH / 8; ++n)
           *reinterpret_cast<float2*>(out + n * 8 + 2 * t) = make_float2(acc[n][2] * scale, acc[n][3] * scale);
@@ -378,16 +421,16 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
       tile_tAB<DH, NT>(sS, PP, c0, sQ, ak, lane);
       tile_tAB<DH, NT>(sPm, PP, c0, sG, av, lane);
       const int ka = c0 + gq, kb = c0 + gq + 8;
-      if (ka < S) {
-        float* outk = dqkv + (it.tok0 + size_t(ka) * L) * ld + d + it.h * DH;
+      if (kFull || ka < S) {
+        float* outk = dq_item + uint32_t(ka) * uint32_t(L) * uint32_t(ld) + d;
 #pragma unroll
         for (int n = 0; n < DH / 8; ++n) {
           *reinterpret_cast<float2*>(outk + n * 8 + 2 * t) = make_float2(ak[n][0] * scale, ak[n][1] * scale);
           *reinterpret_cast<float2*>(outk + d + n * 8 + 2 * t) = make_float2(av[n][0], av[n][1]);
         }
       }
-      if (kb < S) {
-        float* outk = dqkv + (it.tok0 + size_t(kb) * L) * ld + d + it.h * DH;
+      if (kFull || kb < S) {
+        float* outk = dq_item + uint32_t(kb) * uint32_t(L) * uint32_t(ld) + d;
 #pragma unroll
         for (int n = 0; n < DH / 8; ++n) {
           *reinterpret_cast<float2*>(outk + n * 8 + 2 * t) = make_float2(ak[n][2] * scale, ak[n][3] * scale);
@@ -396,6 +439,7 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
       }
     }
     __syncthreads();   // every warp is done with buffer b (and sD) before the next iteration refills them
+    cur = nxt;
   }
 }
 

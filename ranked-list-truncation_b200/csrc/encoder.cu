@@ -402,23 +402,25 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_kernel(const float* __rest
 }
 
 // persistent pipelined kernels: as many CTAs as are co-resident (occupancy API), each walking items with stride gridDim.x
-template <int DH, int NT, bool kDrop>
+template <int DH, int NT, bool kDrop, bool kFull>
 static int attention_fwd_launch(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head, float scale,
                                 cudaStream_t stream, DropCfg drop) {
   const size_t smem = size_t(2) * 3 * NT * 8 * (DH + 4) * sizeof(float);
   static bool attr_set = false;
   static int per_sm = 0;
   if (!attr_set) {
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_pipe_kernel<DH, NT, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_fwd_pipe_kernel<DH, NT, kDrop>, 128, smem));
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_pipe_kernel<DH, NT, kDrop, kFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_fwd_pipe_kernel<DH, NT, kDrop, kFull>, 128, smem));
     if (per_sm < 1) per_sm = 1;
     attr_set = true;
   }
   const long long n_items = (long long)G * L * n_head;
+  RLT_REQUIRE(n_items < (1ll << 31) && size_t(S) * L * 3 * d < (size_t(1) << 32), RLT_UNSUPPORTED_SHAPE,
+              "attention: %lld work items / group span exceed the 32-bit index range", n_items);
   long long grid = (long long)num_sms() * per_sm;
   if (grid > n_items) grid = n_items;
   time_begin(TAG_ATTN_FWD, stream);
-  attn_lists_fwd_pipe_kernel<DH, NT, kDrop><<<int(grid), 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, n_items, drop);
+  attn_lists_fwd_pipe_kernel<DH, NT, kDrop, kFull><<<int(grid), 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, int(n_items), drop);
   time_end(TAG_ATTN_FWD, stream);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
@@ -426,10 +428,13 @@ static int attention_fwd_launch(const float* qkv, float* o, float* lse, int G, i
 template <int DH, int NT>
 static int attention_fwd_mma(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head, float scale,
                              cudaStream_t stream, DropCfg drop) {
-  return drop.thr ? attention_fwd_launch<DH, NT, true>(qkv, o, lse, G, S, L, d, n_head, scale, stream, drop)
-                  : attention_fwd_launch<DH, NT, false>(qkv, o, lse, G, S, L, d, n_head, scale, stream, drop);
+  if (S == NT * 8)
+    return drop.thr ? attention_fwd_launch<DH, NT, true, true>(qkv, o, lse, G, S, L, d, n_head, scale, stream, drop)
+                    : attention_fwd_launch<DH, NT, false, true>(qkv, o, lse, G, S, L, d, n_head, scale, stream, drop);
+  return drop.thr ? attention_fwd_launch<DH, NT, true, false>(qkv, o, lse, G, S, L, d, n_head, scale, stream, drop)
+                  : attention_fwd_launch<DH, NT, false, false>(qkv, o, lse, G, S, L, d, n_head, scale, stream, drop);
 }
-template <int DH, int NT, bool kDrop>
+template <int DH, int NT, bool kDrop, bool kFull>
 static int attention_bwd_launch(const float* qkv, const float* lse, const float* d_o, float* dqkv, int G, int S, int L, int d,
                                 int n_head, float scale, cudaStream_t stream, DropCfg drop) {
   // double-buffered staging when two buffers still leave room for two CTAs per SM, else one buffer
@@ -440,16 +445,18 @@ static int attention_bwd_launch(const float* qkv, const float* lse, const float*
   static bool attr_set = false;
   static int per_sm = 0;
   if (!attr_set) {
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_pipe_kernel<DH, NT, kDrop, kBufs>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_bwd_pipe_kernel<DH, NT, kDrop, kBufs>, 128, smem));
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_pipe_kernel<DH, NT, kDrop, kBufs, kFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_bwd_pipe_kernel<DH, NT, kDrop, kBufs, kFull>, 128, smem));
     if (per_sm < 1) per_sm = 1;
     attr_set = true;
   }
   const long long n_items = (long long)G * L * n_head;
+  RLT_REQUIRE(n_items < (1ll << 31) && size_t(S) * L * 3 * d < (size_t(1) << 32), RLT_UNSUPPORTED_SHAPE,
+              "attention: %lld work items / group span exceed the 32-bit index range", n_items);
   long long grid = (long long)num_sms() * per_sm;
   if (grid > n_items) grid = n_items;
   time_begin(TAG_ATTN_BWD, stream);
-  attn_lists_bwd_pipe_kernel<DH, NT, kDrop, kBufs><<<int(grid), 128, smem, stream>>>(qkv, lse, d_o, dqkv, S, L, d, n_head, scale, n_items, drop);
+  attn_lists_bwd_pipe_kernel<DH, NT, kDrop, kBufs, kFull><<<int(grid), 128, smem, stream>>>(qkv, lse, d_o, dqkv, S, L, d, n_head, scale, int(n_items), drop);
   time_end(TAG_ATTN_BWD, stream);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
@@ -458,8 +465,11 @@ template <int DH, int NT>
 static int attention_bwd_mma(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int G,
                              int S, int L, int d, int n_head, float scale, cudaStream_t stream, DropCfg drop) {
   (void)o;   // D = rowsum(P * dP) is recomputed from the fragments; the attention output is not needed
-  return drop.thr ? attention_bwd_launch<DH, NT, true>(qkv, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream, drop)
-                  : attention_bwd_launch<DH, NT, false>(qkv, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream, drop);
+  if (S == NT * 8)
+    return drop.thr ? attention_bwd_launch<DH, NT, true, true>(qkv, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream, drop)
+                    : attention_bwd_launch<DH, NT, false, true>(qkv, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream, drop);
+  return drop.thr ? attention_bwd_launch<DH, NT, true, false>(qkv, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream, drop)
+                  : attention_bwd_launch<DH, NT, false, false>(qkv, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream, drop);
 }
 // tensor-core path available for S <= 128 and dh in {16, 32, 64}
 static bool attention_mma_ok(int S, int dh) { return gemm_backend() == 0 && S <= 128 && (dh == 16 || dh == 32 || dh == 64); }
