@@ -108,6 +108,35 @@ __device__ __forceinline__ void tile_tAB(const float* __restrict__ sT, int PP, i
   }
 }
 
+// Two 16-column tiles (c0, c0 + 16) of the same transposed operand against the same B rows: the B fragments are loaded
+// once per k-step and feed both tiles (the backward kernel is bound by shared-memory wavefronts, not by MMA issue).
+template <int DH, int NT>
+__device__ __forceinline__ void tile_tAB2(const float* __restrict__ sT, int PP, int c0, const float* __restrict__ sB,
+                                          float (&acc0)[DH / 8][4], float (&acc1)[DH / 8][4], int lane) {
+  constexpr int P = DH + 4;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < NT; ++ks) {
+    uint32_t b0[DH / 8], b1[DH / 8];
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      b0[n] = tf32_bits(sB[(ks * 8 + 2 * t) * P + n * 8 + g]);
+      b1[n] = tf32_bits(sB[(ks * 8 + 2 * t + 1) * P + n * 8 + g]);
+    }
+    const float* r0 = sT + (ks * 8 + 2 * t) * PP + c0 + g;
+    {
+      const uint32_t a0 = tf32_bits(r0[0]), a1 = tf32_bits(r0[8]), a2 = tf32_bits(r0[PP]), a3 = tf32_bits(r0[PP + 8]);
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) mma_tf32(acc0[n], a0, a1, a2, a3, b0[n], b1[n]);
+    }
+    {
+      const uint32_t a0 = tf32_bits(r0[16]), a1 = tf32_bits(r0[24]), a2 = tf32_bits(r0[PP + 16]), a3 = tf32_bits(r0[PP + 24]);
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) mma_tf32(acc1[n], a0, a1, a2, a3, b0[n], b1[n]);
+    }
+  }
+}
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -410,31 +439,34 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
       }
     }
     __syncthreads();   // P and dS complete
-    // ---------------- phase B: key tiles -> dK = dS^T Q, dV = (dropped P)^T dO, operands read transposed from smem
-    for (int c0 = warp * 16; c0 < S; c0 += 64) {
-      float ak[DH / 8][4], av[DH / 8][4];
-#pragma unroll
-      for (int n = 0; n < DH / 8; ++n) {
-        ak[n][0] = ak[n][1] = ak[n][2] = ak[n][3] = 0.f;
-        av[n][0] = av[n][1] = av[n][2] = av[n][3] = 0.f;
-      }
-      tile_tAB<DH, NT>(sS, PP, c0, sQ, ak, lane);
-      tile_tAB<DH, NT>(sPm, PP, c0, sG, av, lane);
-      const int ka = c0 + gq, kb = c0 + gq + 8;
-      if (kFull || ka < S) {
-        float* outk = dq_item + uint32_t(ka) * uint32_t(L) * uint32_t(ld) + d;
+    // ---------------- phase B: key tiles -> dK = dS^T Q (warps 0, 1), dV = (dropped P)^T dO (warps 2, 3); operands are
+    // read transposed from smem, each warp takes pairs of 16-key tiles so that the Q / dO fragments are loaded once per pair
+    {
+      const bool is_v = warp >= 2;
+      const float* sT = is_v ? sPm : sS;
+      const float* sB = is_v ? sG : sQ;
+      const float osc = is_v ? 1.f : scale;
+      float* out_m = dq_item + (is_v ? 2 * d : d);
+      for (int c0 = (warp & 1) * 32; c0 < S; c0 += 64) {
+        float a0[DH / 8][4], a1[DH / 8][4];
 #pragma unroll
         for (int n = 0; n < DH / 8; ++n) {
-          *reinterpret_cast<float2*>(outk + n * 8 + 2 * t) = make_float2(ak[n][0] * scale, ak[n][1] * scale);
-          *reinterpret_cast<float2*>(outk + d + n * 8 + 2 * t) = make_float2(av[n][0], av[n][1]);
+          a0[n][0] = a0[n][1] = a0[n][2] = a0[n][3] = 0.f;
+          a1[n][0] = a1[n][1] = a1[n][2] = a1[n][3] = 0.f;
         }
-      }
-      if (kFull || kb < S) {
-        float* outk = dq_item + uint32_t(kb) * uint32_t(L) * uint32_t(ld) + d;
+        tile_tAB2<DH, NT>(sT, PP, c0, sB, a0, a1, lane);
 #pragma unroll
-        for (int n = 0; n < DH / 8; ++n) {
-          *reinterpret_cast<float2*>(outk + n * 8 + 2 * t) = make_float2(ak[n][2] * scale, ak[n][3] * scale);
-          *reinterpret_cast<float2*>(outk + d + n * 8 + 2 * t) = make_float2(av[n][2], av[n][3]);
+        for (int hrow = 0; hrow < 4; ++hrow) {            // key rows c0 + gq + {0, 8, 16, 24}
+          const int kr = c0 + gq + 8 * hrow;
+          if (kFull || kr < S) {
+            float* outk = out_m + uint32_t(kr) * uint32_t(L) * uint32_t(ld);
+#pragma unroll
+            for (int n = 0; n < DH / 8; ++n) {
+              const float v0 = hrow < 2 ? a0[n][2 * (hrow & 1)] : a1[n][2 * (hrow & 1)];
+              const float v1 = hrow < 2 ? a0[n][2 * (hrow & 1) + 1] : a1[n][2 * (hrow & 1) + 1];
+              *reinterpret_cast<float2*>(outk + n * 8 + 2 * t) = make_float2(v0 * osc, v1 * osc);
+            }
+          }
         }
       }
     }
