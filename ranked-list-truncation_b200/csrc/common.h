@@ -59,8 +59,10 @@ int gemm_tn(const float* A, int lda, const float* B, int ldb, int M, int N, int 
 int gemm_nn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const EpiParams& ep,
             cudaStream_t stream);
 // C[M,N] += alpha * sum_t A[t,m] * B[t,n]   (A: [T,lda], B: [T,ldb]; C pre-initialised by the caller)
+// colsum_out (optional): colsum_out[m] += alpha * sum_t A[t, m] (the bias gradient), folded into the same pass over A
 int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
-            cudaStream_t stream, int tag = 0);
+            cudaStream_t stream, int tag = 0, float* colsum_out = nullptr);
+int colsum(const float* src, float* out, int T, int C, cudaStream_t stream);   // encoder.cu
 
 // fp16-operand variants (tensor-core backend only): C = A[M,K] B[N,K]^T and C += alpha * alpha_ptr[0] * A[T,M]^T B[T,N]
 int gemm_tn_h(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const EpiParams& ep,

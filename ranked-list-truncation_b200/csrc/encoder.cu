@@ -795,8 +795,7 @@ int rlt_encoder_layer_bwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   RLT_TRY(attention_bwd(sv + sl.qkv, sv + sl.o, sv + sl.lse, d_o, d_qkv, e->n_groups, e->group_size, e->seq_len, d,
                         e->n_head, stream, drop));
   // db_in += colsum(dQKV) ; dWin += dQKV^T x ; dX = dU1 + dQKV Win
-  RLT_TRY(colsum(d_qkv, gw->in_proj_b, T, 3 * d, stream));
-  RLT_TRY(gemm_dw(d_qkv, 3 * d, x, d, T, 3 * d, d, gw->in_proj_w, d, 1.f, stream));
+  RLT_TRY(gemm_dw(d_qkv, 3 * d, x, d, T, 3 * d, d, gw->in_proj_w, d, 1.f, stream, 0, gw->in_proj_b));
   ep = EpiParams{}; ep.alpha = 1.f; ep.out = d_x; ep.ldo = d; ep.residual = d_u; ep.accumulate = e->accumulate_dx ? 1 : 0;
   RLT_TRY(gemm_nn(d_qkv, 3 * d, w->in_proj_w, d, T, d, 3 * d, ep, stream));
   return RLT_OK;

@@ -41,7 +41,8 @@ static int g_gemm_backend = env_int("RLT_GEMM_BACKEND", 0);
 // tensor core would truncate the low 13 mantissa bits (a systematic -2^-11 relative bias per operand).
 static int g_tma_round = env_int("RLT_TMA_ROUND", 1);
 static int g_b_resident = env_int("RLT_B_RESIDENT", 1);
-static int g_ffn_bwd_fused = env_int("RLT_FFN_BWD_FUSED", 1);   // one-pass dH / dW1 / dW2 / db1 kernel (d_model 128)
+static int g_ffn_bwd_fused = env_int("RLT_FFN_BWD_FUSED", 1);   // one-pass dH / dW2 / db1 kernel (d_model 128)
+static int g_dw_colsum = env_int("RLT_DW_COLSUM", 1);         // bias-gradient column sums as an extra MMA of the weight-gradient GEMM
 static int g_f16out_tma = env_int("RLT_F16OUT_TMA", 1);     // copy-engine epilogue kernel for the fp16-output GEMMs   // gemm_tn: keep the CTA's B slice in shared memory when it fits
 
 static std::atomic<unsigned long long> g_launches{0};
@@ -353,7 +354,7 @@ int gemm_tn_h(const __half* A, int lda, const __half* B, int ldb, int M, int N, 
 
 template <int BN, bool kF16>
 static int launch_dw(const void* A, int lda, const void* B, int ldb, int T, int M, int N, float* C, int ldc,
-                     float alpha, const float* alpha_ptr, cudaStream_t stream) {
+                     float alpha, const float* alpha_ptr, cudaStream_t stream, float* colsum_out = nullptr) {
   using Cfg = GemmDwCfg<BN, kF16>;
   CUtensorMap tmA, tmB;
   if (kF16) {
@@ -376,7 +377,7 @@ static int launch_dw(const void* A, int lda, const void* B, int ldb, int T, int 
   if (splits < 1) splits = 1;
   const int max_splits = (num_tb + 7) / 8;
   if (splits > max_splits) splits = max_splits;
-  gemm_dw_kernel<BN, kF16><<<dim3(tiles, splits), 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, T, M, N, C, ldc, alpha, alpha_ptr);
+  gemm_dw_kernel<BN, kF16><<<dim3(tiles, splits), 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, T, M, N, C, ldc, alpha, alpha_ptr, colsum_out);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }
@@ -388,9 +389,13 @@ struct TimeScope {
 };
 
 int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
-            cudaStream_t stream, int tag) {
+            cudaStream_t stream, int tag, float* colsum_out) {
   TimeScope scope(tag, stream);
   RLT_REQUIRE(T > 0 && M > 0 && N > 0, RLT_INVALID_ARG, "gemm_dw: empty problem T=%d M=%d N=%d", T, M, N);
+  if (gemm_backend() == 1 || g_dw_colsum == 0) {
+    if (colsum_out != nullptr) RLT_TRY(colsum(A, colsum_out, T, M, stream));   // A is [T, lda] with lda == M at every such call site
+    if (gemm_backend() != 1) colsum_out = nullptr;
+  }
   if (gemm_backend() == 1) {
     const int tchunk = 2048;
     dim3 grid((N + 15) / 16, (M + 15) / 16, (T + tchunk - 1) / tchunk);
@@ -399,10 +404,10 @@ int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int 
     return RLT_OK;
   }
   RLT_REQUIRE(N % 32 == 0, RLT_UNSUPPORTED_SHAPE, "gemm_dw: N=%d must be a multiple of 32", N);
-  if (N % 256 == 0) return launch_dw<256, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, nullptr, stream);
-  if (N % 128 == 0) return launch_dw<128, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, nullptr, stream);
-  if (N % 64 == 0) return launch_dw<64, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, nullptr, stream);
-  return launch_dw<32, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, nullptr, stream);
+  if (N % 256 == 0) return launch_dw<256, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, nullptr, stream, colsum_out);
+  if (N % 128 == 0) return launch_dw<128, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, nullptr, stream, colsum_out);
+  if (N % 64 == 0) return launch_dw<64, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, nullptr, stream, colsum_out);
+  return launch_dw<32, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, nullptr, stream, colsum_out);
 }
 
 // Fused FFN backward (ffn_bwd_fused.cuh): dH (fp16), db1 and dW2 in one pass over h.
@@ -682,6 +687,7 @@ int rlt_set_option(const char* key, int value) {
   if (strcmp(key, "b_resident") == 0) { g_b_resident = value; return RLT_OK; }
   if (strcmp(key, "f16out_tma") == 0) { g_f16out_tma = value; return RLT_OK; }
   if (strcmp(key, "ffn_bwd_fused") == 0) { g_ffn_bwd_fused = value; return RLT_OK; }
+  if (strcmp(key, "dw_colsum") == 0) { g_dw_colsum = value; return RLT_OK; }
   return set_error(RLT_INVALID_ARG, "rlt_set_option: unknown option '%s'", key);
 }
 int rlt_get_option(const char* key) {
@@ -691,6 +697,7 @@ int rlt_get_option(const char* key) {
   if (strcmp(key, "b_resident") == 0) return g_b_resident;
   if (strcmp(key, "f16out_tma") == 0) return g_f16out_tma;
   if (strcmp(key, "ffn_bwd_fused") == 0) return g_ffn_bwd_fused;
+  if (strcmp(key, "dw_colsum") == 0) return g_dw_colsum;
   if (strcmp(key, "time_tag") == 0) return g_time_tag;
   if (strcmp(key, "lstm_backend") == 0) return lstm_backend();
   return set_error(RLT_INVALID_ARG, "rlt_get_option: unknown option '%s'", key);

@@ -432,21 +432,28 @@ struct GemmDwCfg {
   static constexpr int B_BYTES = (BN / BOX_COLS) * BOX_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (STAGE_BYTES >= 48 * 1024) ? 4 : 6;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr size_t SMEM_BYTES = 1024 + size_t(STAGES) * STAGE_BYTES + 256;
+  // accumulator columns [0, BN) + 32 columns for the optional column-sum product (A^T . ones), as a power of two
+  static constexpr int TMEM_COLS = BN + 32 <= 64 ? 64 : BN + 32 <= 128 ? 128 : BN + 32 <= 256 ? 256 : 512;
+  static constexpr int ONES_BYTES = BOX_BYTES;        // one box filled with 1.0: the B operand of the column-sum product
+  static constexpr size_t SMEM_BYTES = 1024 + size_t(STAGES) * STAGE_BYTES + ONES_BYTES + 256;
 };
 
 // kF16: both operands fp16, MN-major with the plain SWIZZLE_128B layout (an atom is 8 tokens x 128 B = 64 columns;
 // SBO = 1024 B to the next 8 tokens, LBO = one box to the next 64 columns; one K = 16 MMA spans two atoms).
 // alpha_ptr (optional): the partial tile is multiplied by alpha * alpha_ptr[0] (device-side unscale of fp16 gradients).
+// colsum (optional): colsum[m] += alpha * sum_t A[t, m] -- the bias gradient that goes with the weight gradient.  It is
+// one more (N = 16) MMA per k-step against a shared-memory box of ones, so A is not read a second time by a separate
+// column-sum kernel; only the CTAs of the first column block (n0 == 0) add it.
 template <int BN, bool kF16>
 __global__ void __launch_bounds__(192, 1)
 gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int T, int M,
-               int N, float* __restrict__ C, int ldc, float alpha, const float* __restrict__ alpha_ptr) {
+               int N, float* __restrict__ C, int ldc, float alpha, const float* __restrict__ alpha_ptr,
+               float* __restrict__ colsum) {
   using Cfg = GemmDwCfg<BN, kF16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(Cfg::STAGES) * Cfg::STAGE_BYTES);
+  uint8_t* ones = smem + size_t(Cfg::STAGES) * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + Cfg::ONES_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
   uint64_t* tfull = bars + 2 * Cfg::STAGES;
@@ -463,6 +470,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tb0 = blockIdx.y * per;
   const int tb1 = min(num_tb, tb0 + per);
   const int nblk = tb1 - tb0;  // may be <= 0 for trailing splits
+  const bool do_colsum = colsum != nullptr && n0 == 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -474,6 +482,11 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
     tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  if (do_colsum) {
+    const uint32_t one = kF16 ? 0x3c003c00u : 0x3f800000u;
+    for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = one;
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -500,6 +513,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
       if (lane == 0) {
         constexpr uint32_t idesc = make_idesc(kF16 ? kFmtF16 : kFmtTF32, Cfg::BM, BN, true, true);
+        constexpr uint32_t idesc_cs = make_idesc(kF16 ? kFmtF16 : kFmtTF32, Cfg::BM, 16, true, true);
         constexpr uint32_t kLayout = kF16 ? kLayoutSw128 : kLayoutSw128Base32;
         constexpr uint32_t kSbo = kF16 ? 1024 : 512;
         // next MMA: 8 tf32 tokens = 1024 B (+64 in the address field), 16 fp16 tokens = 2048 B (+128)
@@ -515,6 +529,14 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < 4; ++k) {
             if constexpr (kF16) umma_f16(tmem_base, da + kStep * uint64_t(k), db + kStep * uint64_t(k), idesc, (i | k) != 0 ? 1u : 0u);
             else umma_tf32(tmem_base, da + kStep * uint64_t(k), db + kStep * uint64_t(k), idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          if (do_colsum) {                     // [128, 16] += A^T . ones: every column is the column sum of A's rows
+            const uint64_t d1 = make_smem_desc_sw128(smem_u32(ones), Cfg::BOX_BYTES, kSbo, kLayout);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if constexpr (kF16) umma_f16(tmem_base + BN, da + kStep * uint64_t(k), d1, idesc_cs, (i | k) != 0 ? 1u : 0u);
+              else umma_tf32(tmem_base + BN, da + kStep * uint64_t(k), d1, idesc_cs, (i | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty[s]);
         }
@@ -535,6 +557,11 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) atomicAdd(dst + j, a * v[j]);
         }
+      }
+      if (do_colsum) {
+        float v[32];
+        tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + BN, v);
+        if (row < M) atomicAdd(colsum + row, a * v[0]);
       }
     }
   }
