@@ -8,7 +8,7 @@
 // next MMA's A fragment (cols t, t+4) without any shuffle: key 8j+2t -> k-slot t, key 8j+2t+1 -> k-slot t+4, and
 // the B fragment rows are read from shared memory with the same permutation.
 // Backward recomputes P from the saved log-sum-exp (no S x S tensor in HBM): phase A per query tile (dQ; P and dS stay
-// in shared memory), phase B per key tile contracts them transposed (dK, dV); no atomics.
+// in shared memory, column-swizzled), phase B per pair of key tiles contracts them transposed (dK, dV); no atomics.
 #pragma once
 #include "dropout.cuh"
 #include "sm100.cuh"
@@ -87,34 +87,27 @@ __device__ __forceinline__ void tile_pB(const float (&p)[NT][4], const float* __
   }
 }
 
-// acc[n] (16 x 8 tiles over the head dim) += T[0 : 8*NT, c0 : c0+16]^T * B[0 : 8*NT, 0:DH]: the A operand is read
-// TRANSPOSED from a [rows][PP] shared-memory matrix (PP % 16 == 4: conflict-free), B rows with pitch DH + 4.  The
-// contraction index is permuted (slot t <-> row 8ks+2t, slot t+4 <-> row 8ks+2t+1) so that both loads are conflict-free.
-template <int DH, int NT>
-__device__ __forceinline__ void tile_tAB(const float* __restrict__ sT, int PP, int c0, const float* __restrict__ sB,
-                                         float (&acc)[DH / 8][4], int lane) {
-  constexpr int P = DH + 4;
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int ks = 0; ks < NT; ++ks) {
-    const float* r0 = sT + (ks * 8 + 2 * t) * PP + c0 + g;
-    const uint32_t a0 = tf32_bits(r0[0]), a1 = tf32_bits(r0[8]), a2 = tf32_bits(r0[PP]), a3 = tf32_bits(r0[PP + 8]);
-#pragma unroll
-    for (int n = 0; n < DH / 8; ++n) {
-      const uint32_t b0 = tf32_bits(sB[(ks * 8 + 2 * t) * P + n * 8 + g]);
-      const uint32_t b1 = tf32_bits(sB[(ks * 8 + 2 * t + 1) * P + n * 8 + g]);
-      mma_tf32(acc[n], a0, a1, a2, a3, b0, b1);
-    }
-  }
-}
+// Column swizzle of the [ROWS][ROWS] probability / dS matrices of the backward kernel (no row padding): element
+// (row, col) lives at row * ROWS + (col ^ (8 * pswz(row))).  pswz takes four distinct values on rows {0..3}, {4..7},
+// {0,2,4,6} and {1,3,5,7} (mod 8), which makes BOTH access patterns conflict-free: the 64-bit accumulator-fragment
+// stores of phase A (a half-warp = 4 rows x 8 words) and the transposed fragment loads of phase B (rows 2t / 2t+1 x 8
+// columns).  With the padded pitch 68 the stores were 2-way conflicted: 128 of ~370 wavefronts per warp and item.
+__device__ __forceinline__ int pswz(int row) { return (row & 3) ^ ((row >> 2) & 1); }
 
-// Two 16-column tiles (c0, c0 + 16) of the same transposed operand against the same B rows: the B fragments are loaded
-// once per k-step and feed both tiles (the backward kernel is bound by shared-memory wavefronts, not by MMA issue).
+// Two 16-column tiles (c0, c0 + 16; c0 % 32 == 0) of the same transposed, swizzled operand against the same B rows: the
+// B fragments are loaded once per k-step and feed both tiles (the kernel is bound by shared-memory wavefronts).  The
+// contraction index is permuted (slot t <-> row 8ks+2t, slot t+4 <-> row 8ks+2t+1) so that the B loads are conflict-free.
 template <int DH, int NT>
-__device__ __forceinline__ void tile_tAB2(const float* __restrict__ sT, int PP, int c0, const float* __restrict__ sB,
+__device__ __forceinline__ void tile_tAB2(const float* __restrict__ sT, int c0, const float* __restrict__ sB,
                                           float (&acc0)[DH / 8][4], float (&acc1)[DH / 8][4], int lane) {
   constexpr int P = DH + 4;
+  constexpr int PP = NT * 8;
   const int g = lane >> 2, t = lane & 3;
+  const int fe = pswz(2 * t), fo = pswz(2 * t + 1);
+  const float* pe = sT + (2 * t) * PP + c0 + g;
+  const float* po = pe + PP;
+  const int e0 = (0 ^ fe) * 8, e1 = (1 ^ fe) * 8, e2 = (2 ^ fe) * 8, e3 = (3 ^ fe) * 8;
+  const int o0 = (0 ^ fo) * 8, o1 = (1 ^ fo) * 8, o2 = (2 ^ fo) * 8, o3 = (3 ^ fo) * 8;
 #pragma unroll
   for (int ks = 0; ks < NT; ++ks) {
     uint32_t b0[DH / 8], b1[DH / 8];
@@ -123,14 +116,15 @@ __device__ __forceinline__ void tile_tAB2(const float* __restrict__ sT, int PP, 
       b0[n] = tf32_bits(sB[(ks * 8 + 2 * t) * P + n * 8 + g]);
       b1[n] = tf32_bits(sB[(ks * 8 + 2 * t + 1) * P + n * 8 + g]);
     }
-    const float* r0 = sT + (ks * 8 + 2 * t) * PP + c0 + g;
+    const float* re = pe + ks * 8 * PP;
+    const float* ro = po + ks * 8 * PP;
     {
-      const uint32_t a0 = tf32_bits(r0[0]), a1 = tf32_bits(r0[8]), a2 = tf32_bits(r0[PP]), a3 = tf32_bits(r0[PP + 8]);
+      const uint32_t a0 = tf32_bits(re[e0]), a1 = tf32_bits(re[e1]), a2 = tf32_bits(ro[o0]), a3 = tf32_bits(ro[o1]);
 #pragma unroll
       for (int n = 0; n < DH / 8; ++n) mma_tf32(acc0[n], a0, a1, a2, a3, b0[n], b1[n]);
     }
     {
-      const uint32_t a0 = tf32_bits(r0[16]), a1 = tf32_bits(r0[24]), a2 = tf32_bits(r0[PP + 16]), a3 = tf32_bits(r0[PP + 24]);
+      const uint32_t a0 = tf32_bits(re[e2]), a1 = tf32_bits(re[e3]), a2 = tf32_bits(ro[o2]), a3 = tf32_bits(ro[o3]);
 #pragma unroll
       for (int n = 0; n < DH / 8; ++n) mma_tf32(acc1[n], a0, a1, a2, a3, b0[n], b1[n]);
     }
@@ -317,7 +311,7 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
   constexpr int P = DH + 4;
   constexpr int ROWS = NT * 8;
   constexpr int BUF = 4 * ROWS * P + ROWS;      // q, k, v, dO rows + lse
-  constexpr int PP = ROWS + 4;                  // pitch of the probability / dS matrices (== 4 mod 16)
+  constexpr int PP = ROWS;                      // probability / dS matrices: unpadded rows, columns swizzled by pswz(row)
   extern __shared__ float sm[];
   float* sPm = sm + kBufs * BUF;                // [ROWS][PP] (dropped) probabilities of the current item
   float* sS = sPm + ROWS * PP;                  // [ROWS][PP] dS of the current item
@@ -386,6 +380,7 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
       tile_abT<DH, NT, false>(sG, r0, sV, dp, lane);
       const float la = sL[r0 + gq] * kLog2e, lb = sL[r0 + gq + 8] * kLog2e;
       float da = 0.f, db = 0.f;
+      const int fsw = pswz(gq);                 // rows r0 + gq and r0 + gq + 8 share the swizzle (r0 % 16 == 0)
       float* pa_row = sPm + (r0 + gq) * PP + 2 * t;
       float* pb_row = pa_row + 8 * PP;
 #pragma unroll
@@ -404,8 +399,8 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
           m2 = drop_factor(bb, 0, drop.thr, drop.scale); m3 = drop_factor(bb, 1, drop.thr, drop.scale);
           dp[j][0] *= m0; dp[j][1] *= m1; dp[j][2] *= m2; dp[j][3] *= m3;
         }
-        *reinterpret_cast<float2*>(pa_row + j * 8) = make_float2(p[j][0] * m0, p[j][1] * m1);
-        *reinterpret_cast<float2*>(pb_row + j * 8) = make_float2(p[j][2] * m2, p[j][3] * m3);
+        *reinterpret_cast<float2*>(pa_row + ((j ^ fsw) << 3)) = make_float2(p[j][0] * m0, p[j][1] * m1);
+        *reinterpret_cast<float2*>(pb_row + ((j ^ fsw) << 3)) = make_float2(p[j][2] * m2, p[j][3] * m3);
         da = fmaf(p[j][0], dp[j][0], fmaf(p[j][1], dp[j][1], da));
         db = fmaf(p[j][2], dp[j][2], fmaf(p[j][3], dp[j][3], db));
       }
@@ -417,8 +412,8 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
       for (int j = 0; j < NT; ++j) {
         p[j][0] *= dp[j][0] - da; p[j][1] *= dp[j][1] - da;
         p[j][2] *= dp[j][2] - db; p[j][3] *= dp[j][3] - db;
-        *reinterpret_cast<float2*>(sa_row + j * 8) = make_float2(p[j][0], p[j][1]);
-        *reinterpret_cast<float2*>(sb_row + j * 8) = make_float2(p[j][2], p[j][3]);
+        *reinterpret_cast<float2*>(sa_row + ((j ^ fsw) << 3)) = make_float2(p[j][0], p[j][1]);
+        *reinterpret_cast<float2*>(sb_row + ((j ^ fsw) << 3)) = make_float2(p[j][2], p[j][3]);
       }
       float acc[DH / 8][4];
 #pragma unroll
@@ -454,7 +449,7 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_pipe_kernel(const float* _
           a0[n][0] = a0[n][1] = a0[n][2] = a0[n][3] = 0.f;
           a1[n][0] = a1[n][1] = a1[n][2] = a1[n][3] = 0.f;
         }
-        tile_tAB2<DH, NT>(sT, PP, c0, sB, a0, a1, lane);
+        tile_tAB2<DH, NT>(sT, c0, sB, a0, a1, lane);
 #pragma unroll
         for (int hrow = 0; hrow < 4; ++hrow) {            // key rows c0 + gq + {0, 8, 16, 24}
           const int kr = c0 + gq + 8 * hrow;

@@ -439,7 +439,7 @@ static int attention_bwd_launch(const float* qkv, const float* lse, const float*
                                 int n_head, float scale, cudaStream_t stream, DropCfg drop) {
   // double-buffered staging when two buffers still leave room for two CTAs per SM, else one buffer
   constexpr size_t kBuf = (4 * NT * 8 * (DH + 4) + NT * 8) * sizeof(float);
-  constexpr size_t kPS = size_t(2) * NT * 8 * (NT * 8 + 4) * sizeof(float);
+  constexpr size_t kPS = size_t(2) * NT * 8 * (NT * 8) * sizeof(float);
   constexpr int kBufs = (2 * kBuf + kPS <= 110 * 1024) ? 2 : 1;
   constexpr size_t smem = kBufs * kBuf + kPS;
   static bool attr_set = false;
