@@ -352,10 +352,10 @@ int gemm_tn_h(const __half* A, int lda, const __half* B, int ldb, int M, int N, 
   return gemm_any<OP_F16_K>(A, lda, B, ldb, M, N, K, ep, stream);
 }
 
-template <int BN, bool kF16>
-static int launch_dw(const void* A, int lda, const void* B, int ldb, int T, int M, int N, float* C, int ldc,
-                     float alpha, const float* alpha_ptr, cudaStream_t stream, float* colsum_out = nullptr) {
-  using Cfg = GemmDwCfg<BN, kF16>;
+template <int BN, bool kF16, bool kColsum>
+static int launch_dw_impl(const void* A, int lda, const void* B, int ldb, int T, int M, int N, float* C, int ldc,
+                          float alpha, const float* alpha_ptr, cudaStream_t stream, float* colsum_out) {
+  using Cfg = GemmDwCfg<BN, kF16, kColsum>;
   CUtensorMap tmA, tmB;
   if (kF16) {
     RLT_TRY(make_tmap_h(&tmA, static_cast<const __half*>(A), T, M, lda, Cfg::BT));
@@ -366,7 +366,7 @@ static int launch_dw(const void* A, int lda, const void* B, int ldb, int T, int 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_dw_kernel<BN, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_dw_kernel<BN, kF16, kColsum>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         int(Cfg::SMEM_BYTES)));
     attr_set = true;
   }
@@ -377,9 +377,19 @@ static int launch_dw(const void* A, int lda, const void* B, int ldb, int T, int 
   if (splits < 1) splits = 1;
   const int max_splits = (num_tb + 7) / 8;
   if (splits > max_splits) splits = max_splits;
-  gemm_dw_kernel<BN, kF16><<<dim3(tiles, splits), 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, T, M, N, C, ldc, alpha, alpha_ptr, colsum_out);
+  gemm_dw_kernel<BN, kF16, kColsum><<<dim3(tiles, splits), 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, T, M, N, C, ldc, alpha, alpha_ptr, colsum_out);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
+}
+template <int BN, bool kF16>
+static int launch_dw(const void* A, int lda, const void* B, int ldb, int T, int M, int N, float* C, int ldc,
+                     float alpha, const float* alpha_ptr, cudaStream_t stream, float* colsum_out = nullptr) {
+  if constexpr (!kF16 && BN == 128) {      // the one call site with a fused bias gradient: dW_in (N = d_model 128)
+    if (colsum_out != nullptr)
+      return launch_dw_impl<BN, kF16, true>(A, lda, B, ldb, T, M, N, C, ldc, alpha, alpha_ptr, stream, colsum_out);
+  }
+  RLT_REQUIRE(colsum_out == nullptr, RLT_UNSUPPORTED_SHAPE, "gemm_dw: fused column sums are built for N %% 256 == 128 only (N=%d)", N);
+  return launch_dw_impl<BN, kF16, false>(A, lda, B, ldb, T, M, N, C, ldc, alpha, alpha_ptr, stream, nullptr);
 }
 
 struct TimeScope {
@@ -392,9 +402,10 @@ int gemm_dw(const float* A, int lda, const float* B, int ldb, int T, int M, int 
             cudaStream_t stream, int tag, float* colsum_out) {
   TimeScope scope(tag, stream);
   RLT_REQUIRE(T > 0 && M > 0 && N > 0, RLT_INVALID_ARG, "gemm_dw: empty problem T=%d M=%d N=%d", T, M, N);
-  if (gemm_backend() == 1 || g_dw_colsum == 0) {
-    if (colsum_out != nullptr) RLT_TRY(colsum(A, colsum_out, T, M, stream));   // A is [T, lda] with lda == M at every such call site
-    if (gemm_backend() != 1) colsum_out = nullptr;
+  if (colsum_out != nullptr && (gemm_backend() == 1 || g_dw_colsum == 0 || N % 256 != 128)) {
+    RLT_REQUIRE(lda == M, RLT_INVALID_ARG, "gemm_dw: column sums need a dense A (lda=%d, M=%d)", lda, M);
+    RLT_TRY(colsum(A, colsum_out, T, M, stream));
+    colsum_out = nullptr;
   }
   if (gemm_backend() == 1) {
     const int tchunk = 2048;

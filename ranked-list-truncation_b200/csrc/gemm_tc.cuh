@@ -422,7 +422,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // grid = (tiles_m * tiles_n, splits); every CTA reduces a contiguous token range and red.adds its
 // partial tile into C (C must be initialised by the caller: zeros or the running gradient).
 // -----------------------------------------------------------------------------------------------
-template <int BN, bool kF16>
+template <int BN, bool kF16, bool kColsum = false>
 struct GemmDwCfg {
   static constexpr int BM = 128;
   static constexpr int BT = kF16 ? 64 : 32;           // tokens per stage (4 MMAs of K = 8 tf32 / 16 fp16)
@@ -433,8 +433,9 @@ struct GemmDwCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (STAGE_BYTES >= 48 * 1024) ? 4 : 6;
   // accumulator columns [0, BN) + 32 columns for the optional column-sum product (A^T . ones), as a power of two
-  static constexpr int TMEM_COLS = BN + 32 <= 64 ? 64 : BN + 32 <= 128 ? 128 : BN + 32 <= 256 ? 256 : 512;
-  static constexpr int ONES_BYTES = BOX_BYTES;        // one box filled with 1.0: the B operand of the column-sum product
+  static constexpr int ACC_COLS = kColsum ? BN + 32 : BN;
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+  static constexpr int ONES_BYTES = kColsum ? BOX_BYTES : 0;   // one box filled with 1.0: the B operand of the column-sum product
   static constexpr size_t SMEM_BYTES = 1024 + size_t(STAGES) * STAGE_BYTES + ONES_BYTES + 256;
 };
 
@@ -443,13 +444,14 @@ struct GemmDwCfg {
 // alpha_ptr (optional): the partial tile is multiplied by alpha * alpha_ptr[0] (device-side unscale of fp16 gradients).
 // colsum (optional): colsum[m] += alpha * sum_t A[t, m] -- the bias gradient that goes with the weight gradient.  It is
 // one more (N = 16) MMA per k-step against a shared-memory box of ones, so A is not read a second time by a separate
-// column-sum kernel; only the CTAs of the first column block (n0 == 0) add it.
-template <int BN, bool kF16>
+// column-sum kernel; only the CTAs of the first column block (n0 == 0) add it.  kColsum is a template flag: the plain
+// instantiation keeps its smaller TMEM allocation and issue loop.
+template <int BN, bool kF16, bool kColsum>
 __global__ void __launch_bounds__(192, 1)
 gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int T, int M,
                int N, float* __restrict__ C, int ldc, float alpha, const float* __restrict__ alpha_ptr,
                float* __restrict__ colsum) {
-  using Cfg = GemmDwCfg<BN, kF16>;
+  using Cfg = GemmDwCfg<BN, kF16, kColsum>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* ones = smem + size_t(Cfg::STAGES) * Cfg::STAGE_BYTES;
@@ -470,7 +472,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tb0 = blockIdx.y * per;
   const int tb1 = min(num_tb, tb0 + per);
   const int nblk = tb1 - tb0;  // may be <= 0 for trailing splits
-  const bool do_colsum = colsum != nullptr && n0 == 0;
+  const bool do_colsum = kColsum && colsum != nullptr && n0 == 0;
 
   if (warp == 0) {
     if (lane == 0) {

@@ -12,10 +12,9 @@ cat gpurun_out/${TAG}_bench_ref.json gpurun_out/${TAG}_bench.json | cut -c1-600
 B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
 # launch list of the same bench command (1 warm-up + 1 timed step, full batch)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${TAG}_launches.csv $B > gpurun_out/${TAG}_ncu_bench.log 2>&1
-# full captures: fused FFN backward (2nd launch of a step), FFN1 (3rd f16out launch), attention backward / forward
+# full captures (each .ncu-rep is ~20 MB with sources and gpurun copies back at most 64 MiB per call: two here, the
+# others with tools/gpu_round_more.sh): fused FFN backward (2nd launch of a step), attention backward
 N="ncu --set full --clock-control none --import-source on"
 timeout 600 $N -k regex:ffn_bwd_kernel -s 1 -c 1 -o gpurun_out/${TAG}_ffn_bwd -f $B > gpurun_out/${TAG}_ncu_full.log 2>&1
-timeout 600 $N -k regex:gemm_f16out_kernel -s 2 -c 1 -o gpurun_out/${TAG}_ffn1 -f $B >> gpurun_out/${TAG}_ncu_full.log 2>&1
 timeout 600 $N -k regex:attn_lists_bwd -s 1 -c 1 -o gpurun_out/${TAG}_attn_bwd -f $B >> gpurun_out/${TAG}_ncu_full.log 2>&1
-timeout 600 $N -k regex:attn_lists_fwd -s 1 -c 1 -o gpurun_out/${TAG}_attn_fwd -f $B >> gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out | tail -14
