@@ -189,7 +189,7 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
     // pull the P rows (2 KB per list and step, contiguous) of the step that is kAhead ahead into L2, paced by a step
     // counter the gate warps publish (an mbarrier parity wait aliases when the waiter is two phases behind: the
     // backward version of this loop dead-locked on its last iterations)
-    constexpr int kAhead = 2;
+    constexpr int kAhead = 1;
     for (int step = 0; step < L && !kFusedIn; ++step) {
       while (*s_progress < step - kAhead) __nanosleep(200);
       const int t = dir ? (L - 1 - step) : step;
@@ -401,7 +401,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
     }
   } else if (warp == 17) {
     // L2 prefetch of the saved record (gates + c: 1.5 KB) and dy row (512 B) of the step kAhead ahead
-    constexpr int kAhead = 2;
+    constexpr int kAhead = 1;
     for (int it = 0; it < L; ++it) {
       while (*s_progress < it - kAhead) __nanosleep(200);
       const int step = L - 1 - it;
