@@ -46,7 +46,11 @@ typedef void* rlt_stream_t; /* cudaStream_t */
 const char* rlt_version(void);
 const char* rlt_last_error(void);
 /* options: "gemm_backend" (0 = tcgen05 tensor cores [default], 1 = SIMT validation kernels),
- *          "tma_round"    (1 = encode tensor maps as TFLOAT32 so TMA rounds operands on load). */
+ *          "tma_round"    (1 = encode tensor maps as TFLOAT32 so TMA rounds operands on load),
+ *          "lstm_backend" (0 = tcgen05 recurrence [default], 1 = plain validation kernels),
+ *          A/B switches, all default 1: "b_resident", "f16out_tma", "ffn_bwd_fused" (one-pass dH + db1 + dW2 kernel,
+ *          d_model 128; tag 5 then covers it and tag 7 is not emitted), "dw_colsum" (in-projection bias gradient as an
+ *          extra MMA of the weight-gradient GEMM instead of a separate column-sum kernel). */
 int rlt_set_option(const char* key, int value);
 int rlt_get_option(const char* key);
 /* Number of CUDA kernels this library has launched in this process (all entry points). */
