@@ -91,6 +91,21 @@ int rlt_linear_out_f16(const float* A, const float* B, const float* bias, void* 
 int rlt_dropout_mask(uint64_t seed, int site, float p, size_t n, int group_size, float* out, rlt_stream_t stream);
 /* out[c] += sum_t src[t, c]  (bias gradients). n_cols must be a multiple of 4. */
 int rlt_colsum(const float* src, float* out, int n_rows, int n_cols, rlt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* optimizer step                                               */
+/* ------------------------------------------------------------------------------------------ */
+/* Replaces run.py:104,129  `optim.Adam(model.parameters(), lr, weight_decay)` / `optimizer.step()`
+ * (torch/optim/adam.py _single_tensor_adam: L2 decay added to the gradient, no amsgrad, no maximize) with ONE launch
+ * over all parameter tensors.  param_ptrs / grad_ptrs: DEVICE arrays [n_tensors] of device addresses (fp32 tensors);
+ * exp_avg / exp_avg_sq: flat fp32 moment buffers, tensor t at state_offset[t]; the work list chunk_* (device int
+ * arrays [n_chunks]) names for every CTA a tensor, its first element and element count (<= rlt_adam_chunk_elems()).
+ * step counts from 1; grad_scale multiplies the gradient first (1/world after a SUM all-reduce). */
+int rlt_adam_chunk_elems(void);
+int rlt_adam_step(const unsigned long long* param_ptrs, const unsigned long long* grad_ptrs, float* exp_avg,
+                  float* exp_avg_sq, const long long* state_offset, const int* chunk_tensor, const int* chunk_first,
+                  const int* chunk_len, int n_chunks, double lr, double beta1, double beta2, double eps,
+                  double weight_decay, long long step, double grad_scale, rlt_stream_t stream);
 /* Probe: TMA-load a [rows<=128, 32] fp32 tile of src through a TFLOAT32 tensor map and copy the
  * shared-memory image (de-swizzled) to dst.  Used once to learn whether TMA rounds or truncates. */
 int rlt_probe_tma_tf32(const float* src, float* dst, int rows, rlt_stream_t stream);

@@ -457,3 +457,29 @@ def criterion_for(model_name: str, metric: str = "f1", loop: bool = False, **kw)
     return lambda out, y: mtcut_loss(out, y, metric=metric, num_tasks=kw.get("num_tasks", 3),
                                      rerank_weight=kw.get("rerank_weight", 0.5),
                                      classi_weight=kw.get("classi_weight", 0.5), loop=loop)
+
+
+# ----------------------------------------------------------------------------------------------
+# optimizer step
+# ----------------------------------------------------------------------------------------------
+def adam_step(params, grads, exp_avgs, exp_avg_sqs, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+              grad_scale=1.0):
+    """One step of the optimizer the reference builds at run.py:104 (`optim.Adam(params, lr, weight_decay)`), restated
+    from torch/optim/adam.py `_single_tensor_adam` (amsgrad=False, maximize=False) operation by operation on float32
+    numpy arrays; `step` counts from 1.  Updates the arrays in place.  Python-float scalars are formed in double and
+    rounded to float32 where torch hands them to a float32 kernel."""
+    f = np.float32
+    b1, b2 = betas
+    bc1 = 1.0 - b1 ** step
+    bc2 = 1.0 - b2 ** step
+    step_size = f(lr / bc1)
+    bc2_sqrt = f(math.sqrt(bc2))
+    for p, g, m, v in zip(params, grads, exp_avgs, exp_avg_sqs):
+        g = g.astype(f) * f(grad_scale)
+        if weight_decay != 0:
+            g = g + f(weight_decay) * p                      # grad.add(param, alpha=weight_decay)
+        m += f(1.0 - b1) * (g - m)                           # exp_avg.lerp_(grad, 1 - beta1)   (weight < 0.5 branch)
+        v *= f(b2)                                           # exp_avg_sq.mul_(beta2)
+        v += (f(1.0 - b2) * g) * g                           #            .addcmul_(grad, grad, value=1 - beta2)
+        denom = np.sqrt(v) / bc2_sqrt + f(eps)               # (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+        p += (-step_size) * (m / denom)                      # param.addcdiv_(exp_avg, denom, value=-step_size)
