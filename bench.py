@@ -129,7 +129,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": lps, "unit": "lists/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * GROUP / lps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.model} train step, synthetic robust04-shaped lists x {SEQ_LEN}, groups of {GROUP}",
+            "config": {"workload": f"{args.model} train step (fwd + criterion + bwd + torch Adam step), synthetic robust04-shaped lists x {SEQ_LEN}, groups of {GROUP}",
                        "note": "reference algorithm on host CPU cores (oracle port of the reference's torch calls + Python reward loop)"},
             "inference": {"value": ilps, "unit": "lists/s"},
             "cpu_baseline": {"value": lps, "unit": "lists/s", "cores": cores, "kind": "port", "sample": sample},
@@ -148,6 +148,7 @@ def main():
     from rlt_b200 import _lib, ops, parallel
     from rlt_b200.data import synthetic_lists
     from rlt_b200.engine import Engine
+    from rlt_b200.optim import FusedAdam
     import models
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -175,10 +176,14 @@ def main():
     model = build_model(models, args.model).to(dev)
     eng = Engine(model, n_groups=G, group_size=GROUP, seq_len=SEQ_LEN, training=True)
 
+    # run.py:104,129: Adam with L2 decay, stepped once per batch -- here one fused launch reading the (all-reduced) bucket
+    opt = FusedAdam.for_engine(eng, lr=3e-5, weight_decay=1e-3)
+
     def step(i):
         c = i % n_chunks
         eng.train_step(x_all[c * B:(c + 1) * B], y_all[c * B:(c + 1) * B])
         parallel.allreduce_mean_(eng.grad_bucket, G, G * world)
+        opt.step()
 
     def barrier():
         if world > 1:
@@ -236,6 +241,7 @@ def main():
         dy.copy_(hy, non_blocking=True)
         eng.train_step(dx, dy)
         parallel.allreduce_mean_(eng.grad_bucket, G, G * world)
+        opt.step()
         return eng.loss.item()        # device -> host read of the step's result
     for _ in range(2):
         e2e_step()
@@ -328,13 +334,13 @@ def main():
         cx, cy = synthetic_lists(GROUP * 2, SEQ_LEN, N_FEATURES[args.model], seed=20240229, device="cpu")
         lps, times = torch_port.time_lists_per_s(args.model, cx, cy, GROUP, "train", steps=3, warmup=1)
         cpu = {"value": lps, "unit": "lists/s", "cores": cores, "kind": "port",
-               "sample": f"3 reference-style train steps (fwd + Python-loop criterion + bwd + host metrics) on one batch of "
+               "sample": f"3 reference-style train steps (fwd + Python-loop criterion + bwd + torch Adam step + host metrics) on one batch of "
                          f"{GROUP} lists x {SEQ_LEN}, median, 1 warm-up; step times {[round(v, 3) for v in times]} s"}
 
     line = {"metric": METRIC, "value": train_lps, "unit": "lists/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "tf32 / fp16 operands (11-bit significand), fp32 accumulate, fp32 master tensors", "data": "synthetic",
-            "config": {"workload": f"{args.model} train step (fwd + {CRITERION[args.model]} + bwd{' + NCCL grad all-reduce' if world > 1 else ''}), "
+            "config": {"workload": f"{args.model} train step (fwd + {CRITERION[args.model]} + bwd{' + NCCL grad all-reduce' if world > 1 else ''} + fused Adam step), "
                                    f"{DATASET_LISTS} synthetic robust04-shaped lists x {SEQ_LEN} resident in HBM",
                        "lists_per_step_per_gpu": B, "attention_group": GROUP, "seq_len": SEQ_LEN,
                        "l2": "inputs and activations of one step (>10 GB) exceed the 126 MB L2; no explicit flush",

@@ -71,12 +71,15 @@ class PortModel(nn.Module):
         return outs
 
 
-def train_step(model: PortModel, x, y, metric="f1"):
-    """run.py:121-145 minus the optimizer: forward, criterion (Python reward loop), backward, host cut + metrics."""
+def train_step(model: PortModel, x, y, metric="f1", optimizer=None):
+    """run.py:121-145: forward, criterion (Python reward loop), backward, optimizer step (run.py:129, when an optimizer
+    is given), host cut + metrics."""
     model.zero_grad(set_to_none=True)
     out = model(x)
     loss = O.criterion_for(model.kind, metric=metric, loop=True)(out, y)
     loss.backward()
+    if optimizer is not None:
+        optimizer.step()
     last = out[-1] if isinstance(out, list) else out
     if model.kind == "bicut":
         ks = O.bicut_cut_positions(last.detach().numpy())
@@ -101,6 +104,7 @@ def time_lists_per_s(kind: str, x, y, group_size: int = 64, mode: str = "train",
     torch.manual_seed(1234)
     model = PortModel(kind, seq_len=x.shape[1], n_features=x.shape[2])
     model.train() if mode == "train" else model.eval()
+    optimizer = torch.optim.Adam(model.parameters(), lr=3e-5, weight_decay=1e-3) if mode == "train" else None   # run.py:104
     n_batches = x.shape[0] // group_size
     times = []
     for i in range(warmup + steps):
@@ -108,7 +112,7 @@ def time_lists_per_s(kind: str, x, y, group_size: int = 64, mode: str = "train",
         xb, yb = x[b * group_size:(b + 1) * group_size], y[b * group_size:(b + 1) * group_size]
         t0 = time.perf_counter()
         if mode == "train":
-            train_step(model, xb, yb)
+            train_step(model, xb, yb, optimizer=optimizer)
         else:
             infer_step(model, xb, yb)
         dt = time.perf_counter() - t0
