@@ -33,6 +33,9 @@ MODELS = {
     "mtchoopy": ("MtChoopy", dict(seq_len=300, num_tasks=3, dropout=0.0), 1),
     "mtattncut": ("MtAttnCut", dict(input_size=3, num_tasks=3, dropout=0.0), 3),
     "mmoecut": ("MMOECut", dict(seq_len=300, num_tasks=3, input_size=3, dropout=0.0, num_experts=3), 3),
+    # SURVEY section 8(f) row N4 (run.py:91-102)
+    "moecut": ("MOECut", dict(seq_len=300, num_tasks=3, input_size=3, dropout=0.0), 3),
+    "plecut": ("PLECut", dict(seq_len=300, input_size=3, dropout=0.0, num_experts=3), 3),
 }
 
 
@@ -57,8 +60,10 @@ def build_criterion(ref_losses, name: str, metric: str):
     return ref_losses.MtCutLoss(metric=metric, num_tasks=3)
 
 
-def model_goldens(ref_models, ref_losses):
+def model_goldens(ref_models, ref_losses, only=None):
     for name, (cls_name, kwargs, feats) in MODELS.items():
+        if only and name not in only:
+            continue
         for B in (5, 16):
             torch.manual_seed(WEIGHT_SEED)
             model = getattr(ref_models, cls_name)(**kwargs)
@@ -194,9 +199,11 @@ def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     ref_models, ref_losses, ref_metrics = refshim.load()
     torch.set_num_threads(8)
-    metric_goldens(ref_metrics)
-    loss_goldens(ref_losses)
-    model_goldens(ref_models, ref_losses)
+    only = set(sys.argv[1:])          # e.g. `python -m oracle.make_golden moecut plecut`: only those model fixtures
+    if not only:
+        metric_goldens(ref_metrics)
+        loss_goldens(ref_losses)
+    model_goldens(ref_models, ref_losses, only)
 
 
 if __name__ == "__main__":

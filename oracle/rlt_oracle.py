@@ -439,9 +439,52 @@ def mmoecut_forward(sd, x, num_tasks=3, n_head=4, attend="lists"):
     return outs
 
 
+_TOWERS3 = [("classification_layer", "sigmoid"), ("rerank_layer", "softmax"), ("cut_layer", "softmax")]
+
+
+def _experts(sd, h, n_head, attend):
+    n_exp = 0
+    while f"experts.{n_exp}.attention_layer.layers.0.linear1.weight" in sd:
+        n_exp += 1
+    return [encoder_stack(h, sd, f"experts.{e}.attention_layer.", n_head, attend) for e in range(n_exp)]
+
+
+def _tower_out(sd, mix, t, name, act):
+    z = _linear(mix, sd, f"towers.{t}.{name}.0")
+    return torch.sigmoid(z) if act == "sigmoid" else torch.softmax(z, dim=1)
+
+
+def moecut_forward(sd, x, num_tasks=3, n_head=4, attend="lists"):
+    """models/MOECut.py:86-109: as MMOECut, but ONE gate (`w_gates`, a single Parameter, :68) whose softmax weights
+    (:94) mix the experts once (:100-101); every tower reads the same mixture (:104)."""
+    h = bilstm(x, sd, "pre_encoding.")
+    B = h.shape[0]
+    experts = torch.stack(_experts(sd, h, n_head, attend))
+    gate = torch.softmax(h.reshape(B, -1) @ sd["w_gates"], dim=1)
+    mix = (gate.t().reshape(experts.shape[0], B, 1, 1) * experts).sum(dim=0)
+    towers = _TOWERS3 if num_tasks == 3 else ([_TOWERS3[0], _TOWERS3[2]] if num_tasks == 2.1 else _TOWERS3[1:])
+    return [_tower_out(sd, mix, t, name, act) for t, (name, act) in enumerate(towers)]
+
+
+def plecut_forward(sd, x, n_head=2, attend="lists"):
+    """models/PLECut.py:77-104: gates of width 2, 2, 3 (:68-70) over the expert subsets [0:2], [1:3], [0:3]
+    (:81-83, :94-96), one mixture per tower."""
+    h = bilstm(x, sd, "pre_encoding.")
+    B = h.shape[0]
+    experts = _experts(sd, h, n_head, attend)
+    outs = []
+    for t, ((name, act), (lo, hi)) in enumerate(zip(_TOWERS3, ((0, 2), (1, 3), (0, 3)))):
+        sub = torch.stack(experts[lo:hi])
+        gate = torch.softmax(h.reshape(B, -1) @ sd[f"w_gates.{t}"], dim=1)
+        mix = (gate.t().reshape(hi - lo, B, 1, 1) * sub).sum(dim=0)
+        outs.append(_tower_out(sd, mix, t, name, act))
+    return outs
+
+
 FORWARDS = {
     "bicut": bicut_forward, "choopy": choopy_forward, "attncut": attncut_forward,
     "mtchoopy": mtchoopy_forward, "mtattncut": mtattncut_forward, "mmoecut": mmoecut_forward,
+    "moecut": moecut_forward, "plecut": plecut_forward,
 }
 
 

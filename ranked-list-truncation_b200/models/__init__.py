@@ -4,6 +4,6 @@ Same class names, constructor arguments, forward signatures, attribute names and
 the forward/backward math runs in librlt_b200.so (sm_100a).  `from models import *` in the
 reference's run.py resolves here when this directory precedes the reference on sys.path.
 """
-from .truncation import AttnCut, BiCut, Choopy, MMOECut, MtAttnCut, MtChoopy
+from .truncation import AttnCut, BiCut, Choopy, MMOECut, MOECut, MtAttnCut, MtChoopy, PLECut
 
-__all__ = ["BiCut", "Choopy", "AttnCut", "MtChoopy", "MtAttnCut", "MMOECut"]
+__all__ = ["BiCut", "Choopy", "AttnCut", "MtChoopy", "MtAttnCut", "MMOECut", "MOECut", "PLECut"]

@@ -237,3 +237,80 @@ class MMOECut(_Base):
         for t, tower in enumerate(self.towers):
             outs.append((torch.sigmoid(z[t]) if tower.act == "sigmoid" else F.SoftmaxLists.apply(z[t])).unsqueeze(2))
         return outs
+
+
+class MOECut(_Base):
+    """Reference models/MOECut.py:56-109: MMOECut with ONE gate Parameter shared by all
+    towers (`w_gates` [2*encoding_size*seq_len, num_experts], :68; every tower sees the same mixture, :94-104)."""
+
+    def __init__(self, seq_len: int = 300, num_experts=3, num_tasks=3, input_size=3, encoding_size=128, d_model=256,
+                 n_head=4, num_layers=1, dropout=0.2):
+        super().__init__()
+        self.seq_len = seq_len
+        self.expert_hidden = d_model
+        self._dropout_p = float(dropout)
+        self.pre_encoding = _bilstm(input_size, encoding_size)
+        self.softmax = nn.Softmax(dim=1)
+        self.experts = nn.ModuleList([_Expert(self.expert_hidden, n_head, num_layers, dropout)
+                                      for _ in range(num_experts)])
+        self.w_gates = nn.Parameter(torch.randn(encoding_size * self.seq_len * 2, num_experts), requires_grad=True)
+        cls = lambda: _Tower(self.expert_hidden, "classification_layer", "sigmoid")  # noqa: E731
+        rer = lambda: _Tower(self.expert_hidden, "rerank_layer", "softmax")          # noqa: E731
+        cut = lambda: _Tower(self.expert_hidden, "cut_layer", "softmax")             # noqa: E731
+        if num_tasks == 3:
+            self.towers = nn.ModuleList([cls(), rer(), cut()])
+        elif num_tasks == 2.1:
+            self.towers = nn.ModuleList([cls(), cut()])
+        elif num_tasks == 2.2:
+            self.towers = nn.ModuleList([rer(), cut()])
+
+    def forward(self, x):
+        self._check_mode()
+        e = self.pre_encoding
+        h = F.BiLstm.apply(x, e.hidden_size, e.num_layers, *e._flat_weights)
+        experts = [self._encode(h, ex.attention_layer) for ex in self.experts]
+        w = torch.cat([t.linear.weight for t in self.towers], dim=0)
+        b = torch.cat([t.linear.bias for t in self.towers], dim=0)
+        # the shared gate is presented once per tower; autograd sums the three gate gradients into the one Parameter
+        z = F.MoeGateMix.apply(h, torch.stack([self.w_gates] * len(self.towers)), w, b, *experts)
+        outs = []
+        for t, tower in enumerate(self.towers):
+            outs.append((torch.sigmoid(z[t]) if tower.act == "sigmoid" else F.SoftmaxLists.apply(z[t])).unsqueeze(2))
+        return outs
+
+
+class PLECut(_Base):
+    """Reference models/PLECut.py:56-104 (row N4): three towers, each with its own gate over a SUBSET of the experts --
+    class tower: experts [0:2], rerank tower: experts [1:3], cut tower: experts [0:3] (gate widths 2, 2, 3; :68-70,
+    :81-83, :94-96).  Each tower is one gate/mix/tower call on its expert subset."""
+
+    _SUBSETS = ((0, 2), (1, 3), (0, 3))
+
+    def __init__(self, seq_len: int = 300, num_experts=3, input_size=3, encoding_size=128, d_model=256, n_head=2,
+                 num_layers=1, dropout=0.1):
+        super().__init__()
+        self.seq_len = seq_len
+        self.expert_hidden = d_model
+        self._dropout_p = float(dropout)
+        self.pre_encoding = _bilstm(input_size, encoding_size)
+        self.softmax = nn.Softmax(dim=1)
+        self.experts = nn.ModuleList([_Expert(self.expert_hidden, n_head, num_layers, dropout)
+                                      for _ in range(num_experts)])
+        n_in = encoding_size * self.seq_len * 2
+        self.w_gates = nn.ParameterList([nn.Parameter(torch.randn(n_in, 2), requires_grad=True),
+                                         nn.Parameter(torch.randn(n_in, 2), requires_grad=True),
+                                         nn.Parameter(torch.randn(n_in, 3), requires_grad=True)])
+        self.towers = nn.ModuleList([_Tower(self.expert_hidden, "classification_layer", "sigmoid"),
+                                     _Tower(self.expert_hidden, "rerank_layer", "softmax"),
+                                     _Tower(self.expert_hidden, "cut_layer", "softmax")])
+
+    def forward(self, x):
+        self._check_mode()
+        e = self.pre_encoding
+        h = F.BiLstm.apply(x, e.hidden_size, e.num_layers, *e._flat_weights)
+        experts = [self._encode(h, ex.attention_layer) for ex in self.experts]
+        outs = []
+        for tower, gate, (lo, hi) in zip(self.towers, self.w_gates, self._SUBSETS):
+            z = F.MoeGateMix.apply(h, gate.unsqueeze(0), tower.linear.weight, tower.linear.bias, *experts[lo:hi])[0]
+            outs.append((torch.sigmoid(z) if tower.act == "sigmoid" else F.SoftmaxLists.apply(z)).unsqueeze(2))
+        return outs

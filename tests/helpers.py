@@ -16,6 +16,8 @@ MODEL_KW = {
     "mtchoopy": ("MtChoopy", dict(seq_len=300, num_tasks=3, dropout=0.0)),
     "mtattncut": ("MtAttnCut", dict(input_size=3, num_tasks=3, dropout=0.0)),
     "mmoecut": ("MMOECut", dict(seq_len=300, num_tasks=3, input_size=3, dropout=0.0, num_experts=3)),
+    "moecut": ("MOECut", dict(seq_len=300, num_tasks=3, input_size=3, dropout=0.0)),
+    "plecut": ("PLECut", dict(seq_len=300, input_size=3, dropout=0.0, num_experts=3)),
 }
 
 

@@ -48,7 +48,7 @@ def _criterion(name):
 
 
 @pytest.mark.parametrize("B", [5, 16])
-@pytest.mark.parametrize("name", ["bicut", "attncut", "mtattncut", "mmoecut"])
+@pytest.mark.parametrize("name", ["bicut", "attncut", "mtattncut", "mmoecut", "moecut", "plecut"])
 def test_lstm_family_vs_reference_golden(name, B):
     g = load_golden(f"model_{name}_B{B}.npz")
     model = build_model(name)
