@@ -302,6 +302,32 @@ class Engine:
             ops.bilstm_bwd(self.lstm_desc, self.lstm_w, self.lstm_g, x, self.lstm_saved, d_front, None, self.lstm_ws)
         return self.loss
 
+    def capture_train_step(self, x, y, warmup: int = 3):
+        """CUDA-graph capture of `train_step` on the static input buffers x, y (the
+        reference's batch of 63 lists is launch-bound -- ~250 launches for ~1 ms of device work).  Returns a
+        zero-argument callable that replays the whole forward + criterion + backward as ONE graph launch; new batches
+        are copied into x / y before the replay, gradients land in `grad_bucket`, the loss in `self.loss`.  Everything
+        the step touches is pre-allocated by the Engine and every kernel is launched on the current stream without host
+        synchronisation, so the capture needs no special path.  Dropout draws its seeds on the host once per step, which
+        a replay would freeze: capture is refused for p > 0.  The optimizer step stays outside the graph (its
+        bias-correction scalars change every step)."""
+        if not self.training:
+            raise RuntimeError("Engine built with training=False")
+        if float(getattr(self.model, "_dropout_p", 0.0)) > 0.0 or any(float(getattr(st, "p", 0.0)) > 0.0 for st in self.stacks):
+            raise RuntimeError("capture_train_step: dropout seeds are drawn on the host every step; capture with dropout = 0")
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):           # warm-up off the capture: attribute settings, occupancy queries, tables
+            for _ in range(max(1, warmup)):
+                self.train_step(x, y)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.train_step(x, y)
+        self._graph = graph                     # keeps the captured pool alive
+        return graph.replay
+
     def infer(self, x, y):
         """Forward + fused cut selection and per-list F1 / DCG (K4).  Returns (k, f1, dcg) device tensors."""
         self._forward(x)

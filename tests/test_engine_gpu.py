@@ -62,3 +62,31 @@ def test_engine_matches_module_path(name):
     assert [int(v) for v in k.cpu().numpy()] == [int(v) for v in ref_k]
     assert float(np.mean(f1.cpu().numpy())) == pytest.approx(float(Metric.f1(y.cpu().numpy(), ref_k)), abs=1e-12)
     assert np.array_equal(dcg.cpu().numpy(), np.array(O.dcg_per_list(y.cpu().numpy(), ref_k)))
+
+
+@pytest.mark.parametrize("name", ["choopy", "bicut", "attncut"])
+def test_cuda_graph_replay_matches_eager_step(name):
+    """Row N2: the captured train step (one graph launch) reproduces the eager step's loss and gradient bucket on new
+    data copied into the static buffers (bit-exact up to the order of the weight-gradient atomics)."""
+    import models
+    from rlt_b200.data import synthetic_lists
+    from rlt_b200.engine import Engine
+    feats = {"choopy": 1, "bicut": 3, "attncut": 3}[name]
+    kw = {"choopy": dict(seq_len=300, dropout=0.0), "bicut": dict(input_size=3, dropout=0.0),
+          "attncut": dict(input_size=3, dropout=0.0)}[name]
+    torch.manual_seed(1234)
+    model = getattr(models, {"choopy": "Choopy", "bicut": "BiCut", "attncut": "AttnCut"}[name])(**kw).cuda()
+    eng = Engine(model, n_groups=1, group_size=63, seq_len=300, training=True)
+    xs, ys = synthetic_lists(63, 300, feats, seed=5, device="cuda")
+    replay = eng.capture_train_step(xs, ys)
+    x2, y2 = synthetic_lists(63, 300, feats, seed=6, device="cuda")
+    eng.train_step(x2, y2)
+    ref_loss, ref_bucket = eng.loss.item(), eng.grad_bucket.clone()
+    xs.copy_(x2)
+    ys.copy_(y2)
+    eng.grad_bucket.fill_(123.0)          # the replay must zero and refill the bucket itself
+    replay()
+    torch.cuda.synchronize()
+    assert abs(eng.loss.item() - ref_loss) <= 1e-6 * max(1.0, abs(ref_loss))
+    d = (eng.grad_bucket - ref_bucket).abs().max().item()
+    assert d <= 1e-5 * ref_bucket.abs().max().item(), d
