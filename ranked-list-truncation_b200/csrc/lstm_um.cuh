@@ -264,9 +264,9 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
       uint32_t tok_ch = tokb;                              // token of the first list of the current chunk
 #pragma unroll 1
       for (int ch = 0; ch < U_CELLS / U_CHUNK; ++ch, tok_ch += U_CHUNK * Lu) {
-        float a[4][U_CHUNK];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tmem_ld4(t_lane + q * U_HALF + ch * U_CHUNK, a[q]);
+        float a[4][U_CHUNK];   // the four gate blocks of this chunk: four TMEM loads in flight, one wait
+        tmem_ld4x4(t_lane + 0 * U_HALF + ch * U_CHUNK, t_lane + 1 * U_HALF + ch * U_CHUNK, t_lane + 2 * U_HALF + ch * U_CHUNK,
+                   t_lane + 3 * U_HALF + ch * U_CHUNK, a);
         float pn[4][U_CHUNK];
         if (ch + 1 < U_CELLS / U_CHUNK) load_pre(pn, tok_ch + U_CHUNK * Lu, (ch + 1) * U_CHUNK);
 #pragma unroll

@@ -262,6 +262,28 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Four such loads (column offsets c0..c3 from one base) in flight together, ONE wait: the registers pass through the wait
+// statement as in/out operands so that the compiler cannot schedule a consumer above it.
+__device__ __forceinline__ void tmem_ld4x4(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, float (&a)[4][4]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(t0) : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(t1) : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]) : "r"(t2) : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(t3) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[q][i] = __uint_as_float(r[4 * q + i]);
+}
+
 // 128-byte swizzle used by TMA SWIZZLE_128B and the UMMA SWIZZLE_128B layouts: inside each 1024 B
 // atom (8 rows x 128 B) the 16-byte chunk index is XORed with the row index.
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16) {
