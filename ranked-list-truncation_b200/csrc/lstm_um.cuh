@@ -269,32 +269,39 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
                    t_lane + 3 * U_HALF + ch * U_CHUNK, a);
         float pn[4][U_CHUNK];
         if (ch + 1 < U_CELLS / U_CHUNK) load_pre(pn, tok_ch + U_CHUNK * Lu, (ch + 1) * U_CHUNK);
+        // Pure math for the chunk's four cells first, in ONE branch-free block: the per-cell chains are four MUFU
+        // latencies deep (ex2 -> rcp -> ex2 -> rcp) and the `if (live)` store blocks used to sit between the cells as
+        // control-flow barriers, so the compiler evaluated the cells one after the other.  Stores follow below.
+        float gi[U_CHUNK], gf[U_CHUNK], gg[U_CHUNK], go[U_CHUNK], cn[U_CHUNK], hv[U_CHUNK];
+#pragma unroll
+        for (int li = 0; li < U_CHUNK; ++li) {
+          const int cell = ch * U_CHUNK + li;
+          lstm_gate_values(a[0][li] + pc[0][li], a[1][li] + pc[1][li], a[2][li] + pc[2][li], a[3][li] + pc[3][li], gi[li],
+                           gf[li], gg[li], go[li]);
+          cn[li] = fmaf(gf[li], sC[cell * 512 + gt], gi[li] * gg[li]);
+          sC[cell * 512 + gt] = cn[li];
+          hv[li] = go[li] * tanh_2mufu(cn[li]);
+        }
 #pragma unroll
         for (int li = 0; li < U_CHUNK; ++li) {
           const int cell = ch * U_CHUNK + li;
           const bool live = list0 + cell < B;
           const uint32_t tk = tok_ch + uint32_t(li) * Lu;
-          float gi, gf, gg, go;
-          lstm_gate_values(a[0][li] + pc[0][li], a[1][li] + pc[1][li], a[2][li] + pc[2][li], a[3][li] + pc[3][li], gi, gf,
-                           gg, go);
-          const float cn = fmaf(gf, sC[cell * 512 + gt], gi * gg);
-          sC[cell * 512 + gt] = cn;
-          const float hv = go * tanh_2mufu(cn);
           if (live) {
             if (saved != nullptr) {
               const uint32_t so = tk * uint32_t(2 * U_REC) + cS;
               float* sv = saved + so;
-              sv[0] = __uint_as_float(pack_f16x2(gi, gf));
-              sv[U_REC_GO] = __uint_as_float(pack_f16x2(gg, go));
-              sv[U_REC_C] = cn;
+              sv[0] = __uint_as_float(pack_f16x2(gi[li], gf[li]));
+              sv[U_REC_GO] = __uint_as_float(pack_f16x2(gg[li], go[li]));
+              sv[U_REC_C] = cn[li];
               if (step == 0) sv[U_REC_HP] = 0.f;
-              if (has_next) saved[uint32_t(so + dnext)] = hv;
+              if (has_next) saved[uint32_t(so + dnext)] = hv[li];
             }
-            y[tk * uint32_t(2 * UH) + cY] = hv;
+            y[tk * uint32_t(2 * UH) + cY] = hv[li];
           }
           const int r = row0 + cell;
           *reinterpret_cast<unsigned short*>(hbase + (r >> 3) * 1024 + (r & 7) * 128 + (((hunit ^ r) & 7) << 4)) =
-              f32_to_f16_bits(hv);
+              f32_to_f16_bits(hv[li]);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -477,10 +484,11 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
         }
         float vn[5][U_CHUNK];
         if (ch + 1 < U_CELLS / U_CHUNK) load_rec(vn, tok_ch + U_CHUNK * Lu, (ch + 1) * U_CHUNK, has_prev, dprev);
+        // math of the chunk's four cells in one branch-free block (see the forward kernel), stores afterwards
+        float dai[U_CHUNK], daf[U_CHUNK], dag[U_CHUNK], dao[U_CHUNK];
 #pragma unroll
         for (int li = 0; li < U_CHUNK; ++li) {
           const int cell = ch * U_CHUNK + li;
-          const bool live = list0 + cell < B;
           float gi, gf, gg, go;
           unpack_f16x2(__float_as_uint(vc[0][li]), gi, gf);
           unpack_f16x2(__float_as_uint(vc[1][li]), gg, go);
@@ -490,21 +498,26 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
           const float d_o = dh * tc;
           const float dc = fmaf(dh * go, 1.f - tc * tc, sDC[cell * 512 + gt]);
           sDC[cell * 512 + gt] = dc * gf;
-          const float dai = dc * gg * gi * (1.f - gi);
-          const float daf = dc * cp * gf * (1.f - gf);
-          const float dag = dc * gi * (1.f - gg * gg);
-          const float dao = d_o * go * (1.f - go);
+          dai[li] = dc * gg * gi * (1.f - gi);
+          daf[li] = dc * cp * gf * (1.f - gf);
+          dag[li] = dc * gi * (1.f - gg * gg);
+          dao[li] = d_o * go * (1.f - go);
+        }
+#pragma unroll
+        for (int li = 0; li < U_CHUNK; ++li) {
+          const int cell = ch * U_CHUNK + li;
+          const bool live = list0 + cell < B;
           if (live) {
             float* o = dA + ((tok_ch + uint32_t(li) * Lu) * uint32_t(2 * UG4) + cA);
-            o[0 * UH] = dai; o[1 * UH] = daf; o[2 * UH] = dag; o[3 * UH] = dao;
-            dbs[0] += dai; dbs[1] += daf; dbs[2] += dag; dbs[3] += dao;
+            o[0 * UH] = dai[li]; o[1 * UH] = daf[li]; o[2 * UH] = dag[li]; o[3 * UH] = dao[li];
+            dbs[0] += dai[li]; dbs[1] += daf[li]; dbs[2] += dag[li]; dbs[3] += dao[li];
           }
           const int r = row0 + cell;
           uint8_t* dst = dabase + (r >> 3) * 1024 + (r & 7) * 128 + (((dunit ^ r) & 7) << 4);
-          *reinterpret_cast<unsigned short*>(dst + 0 * 2 * LstmUmBwdSmem::DA_KB) = f32_to_f16_bits(dai * scale);
-          *reinterpret_cast<unsigned short*>(dst + 1 * 2 * LstmUmBwdSmem::DA_KB) = f32_to_f16_bits(daf * scale);
-          *reinterpret_cast<unsigned short*>(dst + 2 * 2 * LstmUmBwdSmem::DA_KB) = f32_to_f16_bits(dag * scale);
-          *reinterpret_cast<unsigned short*>(dst + 3 * 2 * LstmUmBwdSmem::DA_KB) = f32_to_f16_bits(dao * scale);
+          *reinterpret_cast<unsigned short*>(dst + 0 * 2 * LstmUmBwdSmem::DA_KB) = f32_to_f16_bits(dai[li] * scale);
+          *reinterpret_cast<unsigned short*>(dst + 1 * 2 * LstmUmBwdSmem::DA_KB) = f32_to_f16_bits(daf[li] * scale);
+          *reinterpret_cast<unsigned short*>(dst + 2 * 2 * LstmUmBwdSmem::DA_KB) = f32_to_f16_bits(dag[li] * scale);
+          *reinterpret_cast<unsigned short*>(dst + 3 * 2 * LstmUmBwdSmem::DA_KB) = f32_to_f16_bits(dao[li] * scale);
         }
 #pragma unroll
         for (int pl = 0; pl < 5; ++pl)
