@@ -217,6 +217,16 @@ def main():
     train_lps = world * B * args.steps / (ms * 1e-3)
     loss_val = float(eng.loss.item())
 
+    # ---------------- the optimizer step alone (throughput is reported with the optimizer included; this is
+    # the share it takes, so that the excluded figure can be read off as well)
+    barrier()
+    e0.record()
+    for _ in range(20):
+        opt.step()
+    e1.record()
+    barrier()
+    opt_us = e0.elapsed_time(e1) / 20 * 1e3
+
     # ---------------- inference (forward + fused cut/F1/DCG)
     for i in range(2):
         eng.infer(x_all[:B], y_all[:B])
@@ -345,6 +355,9 @@ def main():
                        "lists_per_step_per_gpu": B, "attention_group": GROUP, "seq_len": SEQ_LEN,
                        "l2": "inputs and activations of one step (>10 GB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"dp{world}"},
+            "optimizer": {"kind": "FusedAdam (rlt_adam_step: one launch over all parameter tensors, L2 weight decay)",
+                          "included_in_value": True, "us_per_step": opt_us,
+                          "value_without_optimizer": world * B * args.steps / ((ms - args.steps * opt_us * 1e-3) * 1e-3)},
             "inference": {"value": infer_lps, "unit": "lists/s", "what": "forward + fused argmax-cut + per-list F1/DCG"},
             "e2e": {"value": e2e_lps, "unit": "lists/s", "h2d_bytes_per_step": int(hx.numel() * 4 + hy.numel() * 4),
                     "d2h_bytes_per_step": 4},
