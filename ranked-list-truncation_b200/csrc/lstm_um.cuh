@@ -92,10 +92,13 @@ __device__ __forceinline__ void unpack_f16x2(uint32_t w, float& lo, float& hi) {
 }
 
 struct LstmUmFwdSmem {
-  static constexpr int W_BYTES = 2 * UG4 * 128;            // two k-blocks of [512 rows x 128 B]
+  static constexpr int W_BYTES = 0;                        // W_hh lives in tensor memory (A operand), not in shared memory
   static constexpr int H_BYTES = 2 * U_HALF * 128;         // per half: two k-blocks of [32 rows x 128 B]
   static constexpr int C_BYTES = U_CELLS * 512 * 4;        // cell state, [cell][gate thread]
-  static constexpr size_t TOTAL = 1024 + W_BYTES + 2 * H_BYTES + C_BYTES + 256;
+  // the kernel owns ALL 512 TMEM columns: requesting more than half of the SM's shared memory keeps a second CTA (whose
+  // tcgen05.alloc would block until this one exits) off the SM
+  static constexpr size_t USED = 1024 + W_BYTES + 2 * H_BYTES + C_BYTES + 256;
+  static constexpr size_t TOTAL = USED > 120 * 1024 ? USED : 120 * 1024;
 };
 
 // Layer-0 input projection fused into the recurrence (kFusedIn): with F <= 4 input features (robust04: 3) the
@@ -128,18 +131,7 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
   const int tile = blockIdx.x, dir = blockIdx.y;
   const float* whh = dir ? whh_r : whh_f;
 
-  // ---- one-time: W_hh (fp32 [512,128]) -> fp16 K-major SWIZZLE_128B operand; zero h_0 and c_0
-  for (int i = threadIdx.x; i < UG4 * 16; i += blockDim.x) {
-    const int n = i >> 4, c = i & 15;                 // c: 8-element chunk along k (0..15)
-    const float* src = whh + size_t(n) * UH + c * 8;
-    const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
-    uint4 pk;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.x) : "f"(v0.x), "f"(v0.y));
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.y) : "f"(v0.z), "f"(v0.w));
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.z) : "f"(v1.x), "f"(v1.y));
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.w) : "f"(v1.z), "f"(v1.w));
-    *reinterpret_cast<uint4*>(sW + (c >> 3) * (UG4 * 128) + sw128_offset(n, c & 7)) = pk;
-  }
+  // ---- one-time: zero h_0 and c_0 (W_hh goes to tensor memory below)
   for (int i = threadIdx.x; i < (2 * LstmUmFwdSmem::H_BYTES + LstmUmFwdSmem::C_BYTES) / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(sH)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (warp == 0) {
@@ -149,19 +141,40 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc<256>(tmem_slot);
+    tmem_alloc<512>(tmem_slot);
   }
-  fence_proxy_async_smem();   // generic-proxy writes of sW / sH -> visible to the tensor core (async proxy)
+  fence_proxy_async_smem();   // generic-proxy writes of sH -> visible to the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // W_hh as the TMEM-resident A operand: columns [256, 512), gate block q at 256 + 64 q, lane = row of the block,
+  // column c = fp16 pair (k = 2c, 2c + 1).  Written once by the 16 gate warps (TMEM lane quarter x gate block).
+  if (warp >= 1 && warp <= 16) {
+    const int quarter = warp & 3, qblk = (warp - 1) >> 2;
+    const float* src = whh + size_t(qblk * 128 + quarter * 32 + lane) * UH;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t r[16];
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const float4 v = *reinterpret_cast<const float4*>(src + 2 * (c0 + j));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(r[j]) : "f"(v.x), "f"(v.y));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(r[j + 1]) : "f"(v.z), "f"(v.w));
+      }
+      tmem_st16(tmem_base + (uint32_t(quarter * 32) << 16) + 256 + qblk * 64 + c0, r);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------ MMA issuer ------------------------------
       constexpr uint32_t idesc = make_idesc(kFmtF16, 128, U_HALF, false, false);
-      const uint32_t w_addr = smem_u32(sW), h_addr = smem_u32(sH);
+      const uint32_t h_addr = smem_u32(sH);
       for (int step = 0; step < L; ++step) {
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
@@ -173,12 +186,11 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
           for (int q = 0; q < 4; ++q) {
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
-              const uint64_t da = make_smem_desc_sw128(w_addr + kb * (UG4 * 128) + q * (128 * 128), 16, 1024);
               const uint64_t db = make_smem_desc_sw128(h_addr + hf * LstmUmFwdSmem::H_BYTES + kb * (U_HALF * 128), 16, 1024);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)   // K = 16 fp16 = 32 B per MMA
-                umma_f16(tmem_base + hf * 128 + q * U_HALF, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
-                         (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)   // K = 16 fp16: 8 TMEM columns of A, 32 B of B per MMA
+                umma_f16_ts(tmem_base + hf * 128 + q * U_HALF, tmem_base + 256 + q * 64 + (kb * 4 + k) * 8,
+                            db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(&bar_acc[hf]);
@@ -316,7 +328,7 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem_base);
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -327,11 +339,12 @@ lstm_um_fwd_kernel(const float* __restrict__ P, LstmInProj inp, const float* __r
 // ------------------------------------------------------------------------------------------------------------
 struct LstmUmBwdSmem {
   static constexpr int KB_BYTES = 128 * 128;               // one k-block of W_hh^T
-  static constexpr int W_BYTES = 8 * KB_BYTES;
+  static constexpr int W_BYTES = 0;                        // W_hh^T lives in tensor memory (A operand)
   static constexpr int DA_KB = U_HALF * 128;               // one k-block of da (32 rows x 128 B)
   static constexpr int DA_BYTES = 8 * DA_KB;               // per half
   static constexpr int C_BYTES = U_CELLS * 512 * 4;        // dc_rec, [cell][gate thread]
-  static constexpr size_t TOTAL = 1024 + W_BYTES + 2 * DA_BYTES + C_BYTES + 256;
+  static constexpr size_t USED = 1024 + W_BYTES + 2 * DA_BYTES + C_BYTES + 256;
+  static constexpr size_t TOTAL = USED > 120 * 1024 ? USED : 120 * 1024;   // one CTA per SM (it owns all of TMEM)
 };
 
 __global__ void __launch_bounds__(U_THREADS, 1)
@@ -353,20 +366,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
   const int tile = blockIdx.x, dir = blockIdx.y;
   const float* whh = dir ? whh_r : whh_f;
 
-  // ---- one-time: W_hh^T as fp16 K-major operand: element (row k, col n) = W_hh[n][k]
-  for (int i = threadIdx.x; i < 8 * 8 * 128; i += blockDim.x) {
-    const int k = i & 127, c = (i >> 7) & 7, kb = i >> 10;    // k fastest: coalesced reads of W_hh rows
-    const float* src = whh + size_t(kb * 64 + c * 8) * UH + k;
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = src[size_t(e) * UH];
-    uint4 pk;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.x) : "f"(v[0]), "f"(v[1]));
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.y) : "f"(v[2]), "f"(v[3]));
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.z) : "f"(v[4]), "f"(v[5]));
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(pk.w) : "f"(v[6]), "f"(v[7]));
-    *reinterpret_cast<uint4*>(sW + kb * LstmUmBwdSmem::KB_BYTES + sw128_offset(k, c)) = pk;
-  }
+  // ---- one-time: zero da and dc_rec (W_hh^T goes to tensor memory below)
   for (int i = threadIdx.x; i < (2 * LstmUmBwdSmem::DA_BYTES + LstmUmBwdSmem::C_BYTES) / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(sDA)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (warp == 0) {
@@ -376,19 +376,39 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc<64>(tmem_slot);
+    tmem_alloc<512>(tmem_slot);
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // W_hh^T as the TMEM-resident A operand: columns [256, 512): lane = hidden unit k, column 256 + c = fp16 pair of gate
+  // rows n = 2c, 2c + 1 (A[k][n] = W_hh[n][k]).  Written once by the 16 gate warps: lane quarter x 128-row gate block.
+  if (warp >= 1 && warp <= 16) {
+    const int quarter = warp & 3, qblk = (warp - 1) >> 2;
+    const float* src = whh + size_t(qblk * 128) * UH + quarter * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t r[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float lo = src[size_t(2 * (c0 + j)) * UH], hi = src[size_t(2 * (c0 + j) + 1) * UH];
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(r[j]) : "f"(lo), "f"(hi));
+      }
+      tmem_st16(tmem_base + (uint32_t(quarter * 32) << 16) + 256 + qblk * 64 + c0, r);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------ MMA issuer ------------------------------
       constexpr uint32_t idesc = make_idesc(kFmtF16, 128, U_HALF, false, false);
-      const uint32_t w_addr = smem_u32(sW), da_addr = smem_u32(sDA);
+      const uint32_t da_addr = smem_u32(sDA);
       for (int it = 0; it + 1 < L; ++it) {             // the last processed step has no consumer for dh_rec
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
@@ -396,11 +416,11 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
           tc_fence_after();
 #pragma unroll
           for (int kb = 0; kb < 8; ++kb) {
-            const uint64_t da = make_smem_desc_sw128(w_addr + kb * LstmUmBwdSmem::KB_BYTES, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(da_addr + hf * LstmUmBwdSmem::DA_BYTES + kb * LstmUmBwdSmem::DA_KB, 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_base + hf * U_HALF, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16_ts(tmem_base + hf * U_HALF, tmem_base + 256 + (kb * 4 + k) * 8, db + uint64_t(2 * k), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&bar_d[hf]);
         }
@@ -536,7 +556,7 @@ lstm_um_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<64>(tmem_base);
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace rlt
