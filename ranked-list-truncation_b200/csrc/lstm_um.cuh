@@ -1,8 +1,10 @@
 // K1 — persistent BiLSTM recurrence on tcgen05, "unit-major" mapping.
 //
 // The per-step contraction is computed TRANSPOSED:  a^T[512 gate rows, lists] = W_hh[512, 128] . h^T[128, lists]
-//   * A operand = W_hh as stored by nn.LSTM ([4H, H], gate blocks i,f,g,o), fp16, K-major, resident in shared memory
-//     for the whole scan (128 KB); one M = 128 block per gate.
+//   * A operand = W_hh as stored by nn.LSTM ([4H, H], gate blocks i,f,g,o), fp16, RESIDENT IN TENSOR MEMORY for the
+//     whole scan (tcgen05.mma with a TMEM A operand: lane = row of the 128-row gate block, one 32-bit column = two
+//     consecutive k; 4 blocks x 64 columns = 256 columns, written once with tcgen05.st).  The other 256 columns are the
+//     accumulators: the kernel owns all of TMEM and no shared memory is spent on the weights.
 //   * B operand = h_{t-1} of the CTA's lists ([lists, 128] fp16, K-major, 8 KB per 32 lists), rewritten every step
 //     by the gate warps.
 //   * D lives in TMEM with lane = hidden unit and column = list, so a gate thread owns ONE hidden unit of a few
@@ -10,7 +12,7 @@
 //     gates, y, dy, dA) is a 128-byte contiguous warp access on the plain [token, feature] layouts.  (The earlier
 //     list-per-lane mapping touched 32 cache lines per warp instruction and ran at ~50 us per step.)
 //   * A CTA carries TWO independent halves of 32 lists each (MMA N = 32).  While the gate warps of one half evaluate
-//     the nonlinearities, the tensor core runs the other half's contraction; W_hh is shared by both.
+//     the nonlinearities, the tensor core runs the other half's contraction; the TMEM-resident W_hh serves both.
 //   * fp16 operands keep the 10-bit mantissa of TF32 (|h| < 1, |W_hh| small), fp32 accumulation in TMEM; the cell
 //     state c stays in fp32 (shared memory, one private slot per thread and list).
 //   * Nonlinearities: 4 ex2 + ONE rcp for the four gates (the four denominators share a reciprocal), ex2 + rcp for
