@@ -38,6 +38,19 @@ def test_oracle_adam_matches_torch_golden(case):
         assert np.abs(v[i] - vT[i]).max() <= 1e-6 * np.abs(vT[i]).max() + 1e-30, ("v", i)
 
 
+def test_fused_adam_refuses_cpu_parameters_and_bad_hyperparameters():
+    from rlt_b200.optim import FusedAdam
+    p = [torch.nn.Parameter(torch.zeros(4))]
+    with pytest.raises(RuntimeError, match="no CPU"):
+        FusedAdam(p)
+    with pytest.raises(ValueError):
+        FusedAdam(p, lr=-1.0)
+    with pytest.raises(ValueError):
+        FusedAdam([])
+    with pytest.raises(NotImplementedError):
+        FusedAdam(p, amsgrad=True)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["wd", "nowd"])
 def test_fused_adam_matches_golden_and_oracle(case):
