@@ -19,6 +19,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "ranked-list-truncation_b200"))
 
 from oracle import refshim  # noqa: E402
+from oracle.rlt_oracle import flat_outputs, loss_input  # noqa: E402
 from rlt_b200.data import synthetic_lists  # noqa: E402
 
 GOLDEN = ROOT / "tests" / "golden"
@@ -36,6 +37,8 @@ MODELS = {
     # SURVEY section 8(f) row N4 (run.py:91-102)
     "moecut": ("MOECut", dict(seq_len=300, num_tasks=3, input_size=3, dropout=0.0), 3),
     "plecut": ("PLECut", dict(seq_len=300, input_size=3, dropout=0.0, num_experts=3), 3),
+    # verify_probe.py:61: the base model of the probing experiment; forward returns (experts_in, experts_o, towers)
+    "probebase": ("ProbeBase", dict(seq_len=300, num_tasks=3, input_size=3, dropout=0.0, num_experts=2), 3),
 }
 
 
@@ -45,6 +48,17 @@ def digest(t: torch.Tensor, rng: np.random.Generator, n: int = 512) -> dict:
     idx = np.arange(a.size) if a.size <= n else np.sort(rng.choice(a.size, size=n, replace=False))
     return {"l2": np.float64(np.sqrt((a * a).sum())), "sum": np.float64(a.sum()), "absmax": np.float64(np.abs(a).max()),
             "idx": idx.astype(np.int64), "val": a[idx].astype(np.float64), "size": np.int64(a.size)}
+
+
+def store_output(rec: dict, key: str, t: torch.Tensor, rng: np.random.Generator, full_below: int = 50_000):
+    """Model outputs are stored whole; the [B, L, 256] representations ProbeBase also returns are stored as a shape plus
+    a digest of 4096 sampled entries (tests/helpers.py::output_error reads both forms)."""
+    if t.numel() <= full_below:
+        rec[key] = t.detach().numpy()
+        return
+    rec[key + "/shape"] = np.array(t.shape, dtype=np.int64)
+    for k, v in digest(t, rng, n=4096).items():
+        rec[f"{key}/{k}"] = v
 
 
 def build_criterion(ref_losses, name: str, metric: str):
@@ -72,13 +86,13 @@ def model_goldens(ref_models, ref_losses, only=None):
             out = model(x)
             torch.manual_seed(0)  # MtCutLoss draws an (unused) random Parameter
             crit = build_criterion(ref_losses, name, "f1")
-            loss = crit(out, y)
+            loss = crit(loss_input(out), y)     # ProbeBase: the tower outputs, `output[-1]` (verify_probe.py:107)
             loss.backward()
             rng = np.random.default_rng(7)
             rec = {"x": x.numpy(), "y": y.numpy(), "loss": np.float64(loss.item())}
-            outs = out if isinstance(out, (list, tuple)) else [out]
+            outs = flat_outputs(out)
             for i, o in enumerate(outs):
-                rec[f"out{i}"] = o.detach().numpy()
+                store_output(rec, f"out{i}", o, rng)
             rec["n_out"] = np.int64(len(outs))
             names = []
             for pname, p in model.named_parameters():
@@ -94,11 +108,57 @@ def model_goldens(ref_models, ref_losses, only=None):
             m64.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
             m64.train()
             out64 = m64(x.double())
-            outs64 = out64 if isinstance(out64, (list, tuple)) else [out64]
+            outs64 = flat_outputs(out64)
             for i, o in enumerate(outs64):
-                rec[f"out{i}_f64"] = o.detach().numpy()
+                store_output(rec, f"out{i}_f64", o, rng)
             np.savez_compressed(GOLDEN / f"model_{name}_B{B}.npz", **rec)
             print(f"model_{name}_B{B}: loss={loss.item():.8f}")
+
+
+PROBE_SEED = 4321
+
+
+def probe_inputs(B: int, L: int = 300, d: int = 256):
+    """Seeded stand-ins for ProbeBase's (experts_in, experts_o): regenerated by the tests instead of being stored."""
+    g = torch.Generator().manual_seed(PROBE_SEED + B)
+    return torch.randn(B, L, d, generator=g), [torch.randn(B, L, d, generator=g), torch.randn(B, L, d, generator=g)]
+
+
+def probe_goldens(ref_models, ref_losses):
+    """models/Probe.py:102-122 and the stand-alone towers (verify_probe.py:66-71, TaskC / TaskR) with the criteria
+    verify_probe.py:82-83 pairs them with: BCELoss for the class probes, RerankLoss for the rerank probes."""
+    for B in (4, 9):
+        torch.manual_seed(WEIGHT_SEED)
+        model = ref_models.Probe()
+        e_in, e_o = probe_inputs(B)
+        _, y = synthetic_lists(B, 300, 1, seed=DATA_SEED + 50 + B, device="cpu")
+        e_in.requires_grad_(True)
+        for t in e_o:
+            t.requires_grad_(True)
+        outs = model(e_in, e_o)
+        bce, rr = torch.nn.BCELoss(), ref_losses.RerankLoss()
+        parts = [bce(outs[0].squeeze(), y), rr(outs[1].squeeze(), y), bce(outs[2].squeeze(), y),
+                 bce(outs[3].squeeze(), y), rr(outs[4].squeeze(), y), rr(outs[5].squeeze(), y)]
+        loss = sum(parts)
+        loss.backward()
+        rng = np.random.default_rng(11)
+        rec = {"y": y.numpy(), "loss": np.float64(loss.item()), "losses": np.array([p.item() for p in parts])}
+        for i, o in enumerate(outs):
+            rec[f"out{i}"] = o.detach().numpy()
+        rec["n_out"] = np.int64(len(outs))
+        names = []
+        for pname, p in model.named_parameters():
+            names.append(pname)
+            for k, v in digest(p.grad if p.grad is not None else torch.zeros_like(p), rng).items():
+                rec[f"grad/{pname}/{k}"] = v
+            rec[f"wsum/{pname}"] = np.float64(p.detach().double().sum().item())
+            rec[f"wabs/{pname}"] = np.float64(p.detach().double().abs().sum().item())
+        rec["param_names"] = np.array(names)
+        for tag, t in (("in", e_in), ("o0", e_o[0]), ("o1", e_o[1])):
+            for k, v in digest(t.grad, rng).items():
+                rec[f"dx/{tag}/{k}"] = v
+        np.savez_compressed(GOLDEN / f"probe_B{B}.npz", **rec)
+        print(f"probe_B{B}: loss={loss.item():.8f}")
 
 
 def loss_goldens(ref_losses):
@@ -203,7 +263,10 @@ def main():
     if not only:
         metric_goldens(ref_metrics)
         loss_goldens(ref_losses)
-    model_goldens(ref_models, ref_losses, only)
+    if not only or "probe" in only:
+        probe_goldens(ref_models, ref_losses)
+    if only != {"probe"}:
+        model_goldens(ref_models, ref_losses, only)
 
 
 if __name__ == "__main__":

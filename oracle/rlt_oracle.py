@@ -234,6 +234,14 @@ def rerank_loss(scores: Tensor, labels: Tensor, margin: float = 5e-4) -> Tensor:
     return gap if gap > 0 else torch.zeros((), dtype=scores.dtype, requires_grad=True)
 
 
+def bce_loss(p: Tensor, labels: Tensor) -> Tensor:
+    """nn.BCELoss on squeezed probabilities (verify_probe.py:82, :193-196; the class term of MtCutLoss, losses.py:189):
+    mean over all B*L entries of -(y log p + (1-y) log(1-p)) with torch's clamp of each log at -100."""
+    q = p.squeeze()
+    lp, l1p = torch.log(q).clamp_min(-100.), torch.log(1. - q).clamp_min(-100.)
+    return -(labels * lp + (1. - labels) * l1p).mean()
+
+
 def mtcut_loss(outputs: Sequence[Tensor], labels: Tensor, metric: str = "f1", rerank_weight: float = 0.5,
                classi_weight: float = 0.5, num_tasks: float = 3, loop: bool = False) -> Tensor:
     """MtCutLoss.forward (utils/losses.py:180-191)."""
@@ -481,10 +489,52 @@ def plecut_forward(sd, x, n_head=2, attend="lists"):
     return outs
 
 
+def probebase_forward(sd, x, n_head=4, attend="lists"):
+    """models/Probe.py:76-99: the MMOECut graph (two experts by default, one gate per task :68, towers class | rerank |
+    cut :69-73) returning `(experts_in, experts_o, final_output)` -- the LSTM representation, the list of expert
+    outputs and the list of tower outputs."""
+    h = bilstm(x, sd, "pre_encoding.")
+    B = h.shape[0]
+    experts = _experts(sd, h, n_head, attend)
+    stacked = torch.stack(experts)
+    outs = []
+    for t, (name, act) in enumerate(_TOWERS3):
+        if f"w_gates.{t}" not in sd:
+            break                                                                     # zip(towers, towers_input), :93
+        gate = torch.softmax(h.reshape(B, -1) @ sd[f"w_gates.{t}"], dim=1)
+        mix = (gate.t().reshape(len(experts), B, 1, 1) * stacked).sum(dim=0)
+        outs.append(_tower_out(sd, mix, t, name, act))
+    return h, experts, outs
+
+
+def probe_forward(sd, experts_in, experts_o):
+    """models/Probe.py:113-122: class (sigmoid) and rerank (softmax over positions) probes on the LSTM representation
+    and on both expert outputs; returned in the reference's order c1, r1, ce1, ce2, re1, re2."""
+    def cls(name, h):
+        return torch.sigmoid(_linear(h, sd, f"{name}.classification_layer.0"))
+
+    def rer(name, h):
+        return torch.softmax(_linear(h, sd, f"{name}.rerank_layer.0"), dim=1)
+    return (cls("probe_c1", experts_in), rer("probe_r1", experts_in), cls("probe_ce1", experts_o[0]),
+            cls("probe_ce2", experts_o[1]), rer("probe_re1", experts_o[0]), rer("probe_re2", experts_o[1]))
+
+
+def flat_outputs(out):
+    """One flat list of a model's output tensors: ProbeBase's `(experts_in, [experts], [towers])` in that order."""
+    if isinstance(out, tuple):
+        return [out[0], *out[1], *out[2]]
+    return list(out) if isinstance(out, list) else [out]
+
+
+def loss_input(out):
+    """What the criterion reads: the tower outputs (`output[-1]`, verify_probe.py:107) for ProbeBase."""
+    return out[-1] if isinstance(out, tuple) else out
+
+
 FORWARDS = {
     "bicut": bicut_forward, "choopy": choopy_forward, "attncut": attncut_forward,
     "mtchoopy": mtchoopy_forward, "mtattncut": mtattncut_forward, "mmoecut": mmoecut_forward,
-    "moecut": moecut_forward, "plecut": plecut_forward,
+    "moecut": moecut_forward, "plecut": plecut_forward, "probebase": probebase_forward,
 }
 
 

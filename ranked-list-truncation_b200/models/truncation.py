@@ -314,3 +314,106 @@ class PLECut(_Base):
             z = F.MoeGateMix.apply(h, gate.unsqueeze(0), tower.linear.weight, tower.linear.bias, *experts[lo:hi])[0]
             outs.append((torch.sigmoid(z) if tower.act == "sigmoid" else F.SoftmaxLists.apply(z)).unsqueeze(2))
         return outs
+
+
+class _StandaloneTower(_Tower):
+    """TowerClass / TowerRerank / TowerCut used on their own (verify_probe.py:66-71 builds them directly as probes):
+    Linear(d_model, 1) evaluated by the head kernel, then sigmoid or the softmax over the list positions."""
+
+    def forward(self, x):
+        z = F.HeadDots.apply(x, self.linear.weight, self.linear.bias)[0]
+        return (torch.sigmoid(z) if self.act == "sigmoid" else F.SoftmaxLists.apply(z)).unsqueeze(2)
+
+
+class TowerCut(_StandaloneTower):
+    """Reference models/Probe.py:17-27."""
+
+    def __init__(self, d_model):
+        super().__init__(d_model, "cut_layer", "softmax")
+
+
+class TowerClass(_StandaloneTower):
+    """Reference models/Probe.py:30-40."""
+
+    def __init__(self, d_model):
+        super().__init__(d_model, "classification_layer", "sigmoid")
+
+
+class TowerRerank(_StandaloneTower):
+    """Reference models/Probe.py:43-53."""
+
+    def __init__(self, d_model):
+        super().__init__(d_model, "rerank_layer", "softmax")
+
+
+class TaskC(_StandaloneTower):
+    """Reference models/Classification.py:3-13 (the single-task classifier of verify_classification.py)."""
+
+    def __init__(self, d_model: int = 128) -> None:
+        super().__init__(d_model, "classification_layer", "sigmoid")
+
+
+class TaskR(_StandaloneTower):
+    """Reference models/Rerank.py:3-13."""
+
+    def __init__(self, d_model: int = 128) -> None:
+        super().__init__(d_model, "rerank_layer", "softmax")
+
+
+class ProbeBase(_Base):
+    """Reference models/Probe.py:56-99 (row N4): the MMOECut graph with two experts by default and always three towers
+    (class, rerank, cut; :67-71 -- `num_tasks` only sets the number of gates, and the towers zip against them, :93),
+    returning the intermediate representations next to the tower outputs: `(experts_in, experts_o, final_output)`."""
+
+    def __init__(self, seq_len: int = 300, num_experts=2, num_tasks=3, input_size=3, encoding_size=128, d_model=256,
+                 n_head=4, num_layers=1, dropout=0.2):
+        super().__init__()
+        self.seq_len = seq_len
+        self.expert_hidden = d_model
+        self._dropout_p = float(dropout)
+        self.pre_encoding = _bilstm(input_size, encoding_size)
+        self.softmax = nn.Softmax(dim=1)
+        self.experts = nn.ModuleList([_Expert(self.expert_hidden, n_head, num_layers, dropout)
+                                      for _ in range(num_experts)])
+        self.w_gates = nn.ParameterList([nn.Parameter(torch.randn(encoding_size * self.seq_len * 2, num_experts),
+                                                      requires_grad=True) for _ in range(int(num_tasks))])
+        self.towers = nn.ModuleList([TowerClass(self.expert_hidden), TowerRerank(self.expert_hidden),
+                                     TowerCut(self.expert_hidden)])
+
+    def forward(self, x):
+        self._check_mode()
+        e = self.pre_encoding
+        h = F.BiLstm.apply(x, e.hidden_size, e.num_layers, *e._flat_weights)
+        experts = [self._encode(h, ex.attention_layer) for ex in self.experts]
+        towers = list(self.towers)[:len(self.w_gates)]          # zip(towers, towers_input) of Probe.py:93
+        w = torch.cat([t.linear.weight for t in towers], dim=0)
+        b = torch.cat([t.linear.bias for t in towers], dim=0)
+        z = F.MoeGateMix.apply(h, torch.stack(list(self.w_gates)), w, b, *experts)
+        outs = []
+        for t, tower in enumerate(towers):
+            outs.append((torch.sigmoid(z[t]) if tower.act == "sigmoid" else F.SoftmaxLists.apply(z[t])).unsqueeze(2))
+        return h, experts, outs
+
+
+class Probe(_Base):
+    """Reference models/Probe.py:102-122: six Linear(d, 1) probes -- class / rerank on the LSTM representation and on
+    each of the two expert outputs.  The two probes that read the same tensor share one pass of the head kernel."""
+
+    def __init__(self, encoding_size=128, d_model=256) -> None:
+        super().__init__()
+        self.probe_c1 = TowerClass(d_model=encoding_size * 2)
+        self.probe_r1 = TowerRerank(d_model=encoding_size * 2)
+        self.probe_ce1 = TowerClass(d_model=d_model)
+        self.probe_ce2 = TowerClass(d_model=d_model)
+        self.probe_re1 = TowerRerank(d_model=d_model)
+        self.probe_re2 = TowerRerank(d_model=d_model)
+
+    def _pair(self, h, cls: TowerClass, rer: TowerRerank):
+        z = self._heads(h, [cls.linear, rer.linear])
+        return torch.sigmoid(z[0]).unsqueeze(2), F.SoftmaxLists.apply(z[1]).unsqueeze(2)
+
+    def forward(self, experts_in, experts_o):
+        c1, r1 = self._pair(experts_in, self.probe_c1, self.probe_r1)
+        ce1, re1 = self._pair(experts_o[0], self.probe_ce1, self.probe_re1)
+        ce2, re2 = self._pair(experts_o[1], self.probe_ce2, self.probe_re2)
+        return c1, r1, ce1, ce2, re1, re2

@@ -18,7 +18,29 @@ MODEL_KW = {
     "mmoecut": ("MMOECut", dict(seq_len=300, num_tasks=3, input_size=3, dropout=0.0, num_experts=3)),
     "moecut": ("MOECut", dict(seq_len=300, num_tasks=3, input_size=3, dropout=0.0)),
     "plecut": ("PLECut", dict(seq_len=300, input_size=3, dropout=0.0, num_experts=3)),
+    "probebase": ("ProbeBase", dict(seq_len=300, num_tasks=3, input_size=3, dropout=0.0, num_experts=2)),
 }
+PROBE_SEED = 4321
+
+
+def probe_inputs(B: int, L: int = 300, d: int = 256):
+    """The seeded (experts_in, experts_o) of tests/golden/probe_B*.npz (oracle/make_golden.py::probe_inputs)."""
+    g = torch.Generator().manual_seed(PROBE_SEED + B)
+    return torch.randn(B, L, d, generator=g), [torch.randn(B, L, d, generator=g), torch.randn(B, L, d, generator=g)]
+
+
+def output_error(o, g, key: str):
+    """(max |o - ref|, max |ref|) of one model output against the golden entry `key`, stored either whole or as a
+    shape + sampled digest (oracle/make_golden.py::store_output).  Asserts the shape."""
+    a = o.detach().double().cpu().numpy()
+    if key in g.files:
+        ref = g[key]
+        assert a.shape == ref.shape, (key, a.shape, ref.shape)
+        return float(np.abs(a - ref).max()), float(np.abs(ref).max())
+    assert a.shape == tuple(int(v) for v in g[key + "/shape"]), (key, a.shape)
+    assert a.size == int(g[key + "/size"])
+    return float(np.abs(a.ravel()[g[key + "/idx"]] - g[key + "/val"]).max()), float(g[key + "/absmax"])
+
 
 
 def load_golden(name: str):

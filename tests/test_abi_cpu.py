@@ -52,3 +52,23 @@ def test_state_dict_keys_match_reference_layout():
     keys = set(models.MtAttnCut().state_dict())
     assert {"pre_encoding.weight_hh_l0", "encoding_layer.layers.0.linear1.weight", "classi.0.weight", "rerank.bias",
             "decison_layer.0.bias"} <= keys
+
+
+def test_probe_modules_match_reference_layout():
+    """models/Probe.py, Classification.py, Rerank.py: state_dict keys, constructor defaults and the CPU refusal."""
+    import models
+    torch.manual_seed(0)
+    base = models.ProbeBase(seq_len=40, dropout=0.0)
+    keys = set(base.state_dict())
+    assert {"pre_encoding.weight_ih_l0", "experts.1.attention_layer.layers.0.linear2.weight", "w_gates.2",
+            "towers.0.classification_layer.0.weight", "towers.1.rerank_layer.0.bias", "towers.2.cut_layer.0.weight"} <= keys
+    assert "experts.2.attention_layer.layers.0.linear2.weight" not in keys          # num_experts defaults to 2
+    assert base.w_gates[0].shape == (40 * 256, 2)
+    keys = set(models.Probe().state_dict())
+    assert keys == {f"probe_{n}.{layer}.0.{p}" for n, layer in (("c1", "classification_layer"), ("r1", "rerank_layer"),
+                    ("ce1", "classification_layer"), ("ce2", "classification_layer"), ("re1", "rerank_layer"),
+                    ("re2", "rerank_layer")) for p in ("weight", "bias")}
+    assert set(models.TaskC().state_dict()) == {"classification_layer.0.weight", "classification_layer.0.bias"}
+    assert models.TaskR().rerank_layer[0].in_features == 128
+    with pytest.raises(RuntimeError, match="no CPU"):
+        models.TowerClass(d_model=256)(torch.randn(2, 40, 256))

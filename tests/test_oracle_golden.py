@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import MODEL_KW, build_model, check_weights, grad_errors, load_golden
+from helpers import MODEL_KW, build_model, check_weights, grad_errors, load_golden, output_error, probe_inputs
 from oracle import rlt_oracle as O
 
 
@@ -119,13 +119,12 @@ def test_model_oracle_vs_reference(name, B):
     sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
     x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
     out = O.FORWARDS[name](sd, x)
-    outs = out if isinstance(out, list) else [out]
+    outs = O.flat_outputs(out)
     assert len(outs) == int(g["n_out"])
     for i, o in enumerate(outs):
-        ref = g[f"out{i}"]
-        assert o.shape == ref.shape
-        assert np.abs(o.detach().numpy() - ref).max() <= 5e-5 * np.abs(ref).max(), (name, i)
-    loss = O.criterion_for(name)(out, y)
+        err, ref_max = output_error(o, g, f"out{i}")
+        assert err <= 5e-5 * ref_max, (name, i)
+    loss = O.criterion_for(name)(O.loss_input(out), y)
     assert abs(loss.item() - float(g["loss"])) <= 5e-5 * max(1e-2, abs(float(g["loss"])))
     loss.backward()
     named = {k: (sd[k].grad if sd[k].grad is not None else torch.zeros_like(sd[k])) for k in map(str, g["param_names"])}
@@ -134,7 +133,34 @@ def test_model_oracle_vs_reference(name, B):
     # float64 restatement vs the reference module run in float64
     sd64 = {k: v.detach().double() for k, v in model.state_dict().items()}
     out64 = O.FORWARDS[name](sd64, x.double())
-    outs64 = out64 if isinstance(out64, list) else [out64]
-    for i, o in enumerate(outs64):
-        ref = g[f"out{i}_f64"]
-        assert np.abs(o.numpy() - ref).max() <= 1e-9 * np.abs(ref).max(), (name, i)
+    for i, o in enumerate(O.flat_outputs(out64)):
+        err, ref_max = output_error(o, g, f"out{i}_f64")
+        assert err <= 1e-9 * ref_max, (name, i)
+
+
+@pytest.mark.parametrize("B", [4, 9])
+def test_probe_oracle_vs_reference(B):
+    """models/Probe.py:102-122 with the criteria of verify_probe.py:82-83 (BCELoss / RerankLoss per probe)."""
+    import models
+    g = load_golden(f"probe_B{B}.npz")
+    torch.manual_seed(1234)
+    model = models.Probe()
+    check_weights(model, g)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    e_in, e_o = probe_inputs(B)
+    leaves = [e_in.requires_grad_(True)] + [t.requires_grad_(True) for t in e_o]
+    y = torch.from_numpy(g["y"])
+    outs = O.probe_forward(sd, e_in, e_o)
+    assert len(outs) == int(g["n_out"])
+    for i, o in enumerate(outs):
+        err, ref_max = output_error(o, g, f"out{i}")
+        assert err <= 2e-6 * ref_max, i
+    parts = [O.bce_loss(outs[0], y), O.rerank_loss(outs[1], y), O.bce_loss(outs[2], y), O.bce_loss(outs[3], y),
+             O.rerank_loss(outs[4], y), O.rerank_loss(outs[5], y)]
+    assert np.abs(np.array([p.item() for p in parts]) - g["losses"]).max() <= 1e-6
+    sum(parts).backward()
+    rel_l2, rel_max, _ = grad_errors({k: v.grad for k, v in sd.items()}, g)
+    assert rel_l2 <= 1e-5 and rel_max <= 1e-5
+    for tag, t in zip(("in", "o0", "o1"), leaves):
+        d = t.grad.double().numpy().ravel()[g[f"dx/{tag}/idx"]] - g[f"dx/{tag}/val"]
+        assert np.abs(d).max() <= 1e-5 * float(g[f"dx/{tag}/absmax"]), tag
