@@ -294,6 +294,15 @@ int rlt_eval_cut(const float* probs, const float* labels, int n_lists, int seq_l
  * pyint_in[b] = 1 marks a k that was a Python int in the reference (float32 precision, run.py:135). */
 int rlt_eval_given_k(const float* labels, const int32_t* k_in, const int32_t* pyint_in, int n_lists, int seq_len,
                      int32_t* count_out, int32_t* nrel_out, double* f1_out, double* dcg_out, rlt_stream_t stream);
+/* Full-list metrics of the verify scripts, one value per list:
+ *   dcg_out[b]  = Metric.taskr_metric's DCG_sample (utils/metrics.py:51-57): documents ordered by descending score
+ *                 (ties keep list order), +-inv_log2[i] added left to right in float64; inv_log2[i] = 1/math.log2(i+2)
+ *                 is supplied by the caller (seq_len doubles, device memory) so the table is the host libm's;
+ *   auc_out[b]  = sklearn.metrics.roc_auc_score(labels[b], scores[b]) (utils/metrics.py:73) as the Mann-Whitney
+ *                 statistic, auc_valid[b] = 0 for the one-class lists utils/metrics.py:72 skips.
+ * Either output may be NULL.  The means over lists (utils/metrics.py:58, :76) are taken by the caller. */
+int rlt_rank_metrics(const float* scores, const float* labels, const double* inv_log2, int n_lists, int seq_len,
+                     double* dcg_out, double* auc_out, int32_t* auc_valid, rlt_stream_t stream);
 /* Reward matrix r[b, j] = Metric_for_Loss.f1 / .dcg (label_b, k = j+1)  (utils/metrics.py:85-101). */
 int rlt_reward_matrix(const float* labels, float* rewards, int n_lists, int seq_len, int metric_dcg,
                       rlt_stream_t stream);

@@ -255,12 +255,41 @@ def metric_goldens(ref_metrics):
     print("metrics.npz written", rec["known/f1"], rec["known/dcg"])
 
 
+def rank_metric_goldens(ref_metrics):
+    """Metric.taskr_metric / taskc_metric (utils/metrics.py:40-76) on seeded predictions.  The taskr inputs are
+    tie-free (checked): the reference's argsort is unstable, so tied inputs have no reference answer; AUC is
+    well-defined under ties and gets a tied variant."""
+    rec = {}
+    for (B, L) in ((16, 300), (5, 40)):
+        _, y = synthetic_lists(B, L, 1, seed=DATA_SEED + 300 + L, device="cpu")
+        y = y.numpy()
+        y[3] = 0.0   # a one-class list: skipped by taskc_metric, all-negative for taskr_metric
+        rng = np.random.default_rng(17 + L)
+        p = rng.random((B, L), dtype=np.float32)
+        assert all(len(np.unique(row)) == L for row in p)
+        p_tied = np.round(p, 1).astype(np.float32)
+        rec[f"y_{L}"], rec[f"p_{L}"], rec[f"p_tied_{L}"] = y, p, p_tied
+        rec[f"taskr_{L}"] = np.array([ref_metrics.Metric.taskr_metric(y[i:i + 1], p[i:i + 1]) for i in range(B)])
+        rec[f"taskr_mean_{L}"] = np.float64(ref_metrics.Metric.taskr_metric(y, p))
+        for tag, pp in (("", p), ("_tied", p_tied)):
+            two = [i for i in range(B) if 0 < y[i].sum() < L]
+            rec[f"auc_lists{tag}_{L}"] = np.array(two, dtype=np.int64)
+            rec[f"auc{tag}_{L}"] = np.array([ref_metrics.Metric.taskc_metric(y[i:i + 1], pp[i:i + 1]) for i in two])
+            rec[f"taskc_mean{tag}_{L}"] = np.float64(ref_metrics.Metric.taskc_metric(y, pp))
+    np.savez_compressed(GOLDEN / "rank_metrics.npz", **rec)
+    print("rank_metrics.npz written", rec["taskr_mean_300"], rec["taskc_mean_300"], rec["taskc_mean_tied_300"])
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     ref_models, ref_losses, ref_metrics = refshim.load()
     torch.set_num_threads(8)
     only = set(sys.argv[1:])          # e.g. `python -m oracle.make_golden moecut plecut`: only those model fixtures
+    if only == {"rank"}:
+        rank_metric_goldens(ref_metrics)
+        return
     if not only:
+        rank_metric_goldens(ref_metrics)
         metric_goldens(ref_metrics)
         loss_goldens(ref_losses)
     if not only or "probe" in only:

@@ -234,6 +234,51 @@ def rerank_loss(scores: Tensor, labels: Tensor, margin: float = 5e-4) -> Tensor:
     return gap if gap > 0 else torch.zeros((), dtype=scores.dtype, requires_grad=True)
 
 
+def taskr_dcg_per_list(labels, predictions) -> list:
+    """The DCG_sample values of Metric.taskr_metric (utils/metrics.py:51-57): documents in descending-prediction order,
+    +-1/log2(i+2) accumulated left to right as Python floats.  Ties: list order (stable sort); the reference's default
+    np.argsort is unstable, so its own answer for tied predictions is implementation-defined."""
+    out = []
+    for pred, lab in zip(np.asarray(predictions), np.asarray(labels)):
+        acc = 0
+        for i, origin in enumerate(np.argsort(-pred, kind="stable")):
+            acc += (1 / math.log2(i + 2)) if lab[origin] else (-1 / math.log2(i + 2))
+        out.append(acc)
+    return out
+
+
+def taskr_metric(labels, predictions):
+    """Metric.taskr_metric (utils/metrics.py:40-58)."""
+    return np.mean(taskr_dcg_per_list(labels, predictions))
+
+
+def auc_per_list(labels, predictions):
+    """roc_auc_score per list (utils/metrics.py:73) as the Mann-Whitney statistic: the share of (relevant, irrelevant)
+    pairs ranked correctly, ties counted half.  Returns (auc [n] float64, valid [n] bool); one-class lists
+    (utils/metrics.py:72) are invalid."""
+    labels, predictions = np.asarray(labels), np.asarray(predictions)
+    auc, valid = np.zeros(len(labels)), np.zeros(len(labels), dtype=bool)
+    for b, (lab, pred) in enumerate(zip(labels, predictions)):
+        pos, neg = pred[lab == 1], pred[lab != 1]
+        if len(pos) == 0 or len(neg) == 0:
+            continue
+        u2 = 2 * int((pos[:, None] > neg[None, :]).sum()) + int((pos[:, None] == neg[None, :]).sum())
+        auc[b], valid[b] = u2 / (2.0 * len(pos) * len(neg)), True
+    return auc, valid
+
+
+def taskc_metric(labels, predictions):
+    """Metric.taskc_metric (utils/metrics.py:60-76): running sum of the per-list AUCs over the two-class lists, divided
+    by their number."""
+    auc, valid = auc_per_list(labels, predictions)
+    tmp_auc, count_auc = 0, 0
+    for a, v in zip(auc, valid):
+        if v:
+            tmp_auc += np.float64(a)
+            count_auc += 1
+    return tmp_auc / count_auc
+
+
 def bce_loss(p: Tensor, labels: Tensor) -> Tensor:
     """nn.BCELoss on squeezed probabilities (verify_probe.py:82, :193-196; the class term of MtCutLoss, losses.py:189):
     mean over all B*L entries of -(y log p + (1-y) log(1-p)) with torch's clamp of each log at -100."""

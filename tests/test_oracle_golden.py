@@ -1,5 +1,7 @@
 """CPU: pins oracle/rlt_oracle.py against the reference's known-answer vector and the golden fixtures
 produced by the unmodified reference (oracle/make_golden.py)."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -164,3 +166,23 @@ def test_probe_oracle_vs_reference(B):
     for tag, t in zip(("in", "o0", "o1"), leaves):
         d = t.grad.double().numpy().ravel()[g[f"dx/{tag}/idx"]] - g[f"dx/{tag}/val"]
         assert np.abs(d).max() <= 1e-5 * float(g[f"dx/{tag}/absmax"]), tag
+
+
+@pytest.mark.parametrize("L", [300, 40])
+def test_rank_metrics_vs_reference(L):
+    """Metric.taskr_metric bit for bit (tie-free predictions), Metric.taskc_metric to 1e-12 (sklearn integrates the ROC
+    curve by trapezoids; the oracle divides the exact pair count once)."""
+    g = load_golden("rank_metrics.npz")
+    y, p = g[f"y_{L}"], g[f"p_{L}"]
+    assert np.array_equal(np.array(O.taskr_dcg_per_list(y, p), dtype=np.float64), g[f"taskr_{L}"])
+    assert O.taskr_metric(y, p) == float(g[f"taskr_mean_{L}"])
+    for tag, pp in (("", p), ("_tied", g[f"p_tied_{L}"])):
+        auc, valid = O.auc_per_list(y, pp)
+        assert np.array_equal(np.nonzero(valid)[0], g[f"auc_lists{tag}_{L}"]) and not valid[3]
+        assert np.abs(auc[valid] - g[f"auc{tag}_{L}"]).max() <= 1e-12
+        assert abs(O.taskc_metric(y, pp) - float(g[f"taskc_mean{tag}_{L}"])) <= 1e-12
+    with pytest.raises(ZeroDivisionError):
+        O.taskc_metric(y[3:4], p[3:4])
+    # ties keep their list order: two equal scores, the first document is ranked first
+    assert O.taskr_dcg_per_list(np.array([[1., 0.]]), np.array([[.5, .5]], dtype=np.float32)) == [1 / math.log2(2) - 1 / math.log2(3)]
+    assert O.taskr_dcg_per_list(np.array([[0., 1.]]), np.array([[.5, .5]], dtype=np.float32)) == [-1 / math.log2(2) + 1 / math.log2(3)]

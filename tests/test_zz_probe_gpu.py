@@ -86,6 +86,7 @@ def test_standalone_towers_vs_torch(cls, d):
     got = {n: p.grad.clone() for n, p in m.named_parameters()}
     m.zero_grad(set_to_none=True)
     (ref * w).sum().backward()
+    gmax = max(p.grad.abs().max().item() for p in m.parameters())   # the softmax towers' bias gradient is 0 +- rounding
     for n, p in m.named_parameters():
-        assert (got[n] - p.grad).abs().max().item() <= 1e-3 * max(p.grad.abs().max().item(), 1e-6), n
+        assert (got[n] - p.grad).abs().max().item() <= 1e-3 * gmax, n
     assert (xa.grad - xb.grad).abs().max().item() <= 1e-3 * xb.grad.abs().max().item()
