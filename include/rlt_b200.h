@@ -294,6 +294,20 @@ int rlt_eval_cut(const float* probs, const float* labels, int n_lists, int seq_l
  * pyint_in[b] = 1 marks a k that was a Python int in the reference (float32 precision, run.py:135). */
 int rlt_eval_given_k(const float* labels, const int32_t* k_in, const int32_t* pyint_in, int n_lists, int seq_len,
                      int32_t* count_out, int32_t* nrel_out, double* f1_out, double* dcg_out, rlt_stream_t stream);
+/* ------------------------------------------------------------------------------------------ */
+/* Row N3 - device-resident data path.  Replaces the host-side collation of a shuffled batch by torch's DataLoader
+ * (dataloader/attncut_dataloader.py:82-87) and the two host->device copies of run.py:123-124.         */
+/* ------------------------------------------------------------------------------------------ */
+/* x_out[o] = x[index[o]] ([n_src, seq_len, n_features] float32 rows), labels_out[o] = labels[index[o]] from EITHER float32
+ * labels [n_src, seq_len] OR bit masks label_bits [n_src, ceil(seq_len/32)] (bit i%32 of word i/32 = document i is
+ * relevant), expanded to the reference's float32 {0., 1.}.  index == NULL: identity (the first n_out lists).
+ * labels_out may be NULL.  status (device int32, zeroed by the caller) |= 1 when an index is out of range. */
+int rlt_gather_lists(const float* x, const float* labels, const uint32_t* label_bits, const int64_t* index, int n_src,
+                     int n_out, int seq_len, int n_features, float* x_out, float* labels_out, int32_t* status,
+                     rlt_stream_t stream);
+/* float32 {0., 1.} labels -> bit masks (layout above).  status |= 2 when a label is neither 0. nor 1. */
+int rlt_pack_labels(const float* labels, int n_lists, int seq_len, uint32_t* label_bits, int32_t* status, rlt_stream_t stream);
+
 /* Full-list metrics of the verify scripts, one value per list:
  *   dcg_out[b]  = Metric.taskr_metric's DCG_sample (utils/metrics.py:51-57): documents ordered by descending score
  *                 (ties keep list order), +-inv_log2[i] added left to right in float64; inv_log2[i] = 1/math.log2(i+2)

@@ -234,6 +234,29 @@ def rerank_loss(scores: Tensor, labels: Tensor, margin: float = 5e-4) -> Tensor:
     return gap if gap > 0 else torch.zeros((), dtype=scores.dtype, requires_grad=True)
 
 
+def pack_labels(labels) -> np.ndarray:
+    """Bit-mask label format of row N3 (include/rlt_b200.h, rlt_pack_labels): [n, ceil(L/32)] uint32, bit i%32 of word
+    i/32 set when document i is relevant (label == 1., dataloader/attncut_dataloader.py:47)."""
+    y = np.asarray(labels)
+    n, L = y.shape
+    words = (L + 31) // 32
+    padded = np.zeros((n, words * 32), dtype=np.uint8)
+    padded[:, :L] = (y == 1)
+    return np.packbits(padded, axis=1, bitorder="little").view("<u4").reshape(n, words)
+
+
+def unpack_labels(bits, seq_len: int) -> np.ndarray:
+    b = np.ascontiguousarray(np.asarray(bits).astype("<u4")).view(np.uint8)
+    return np.unpackbits(b, axis=1, bitorder="little")[:, :seq_len].astype(np.float32)
+
+
+def loader_batches(X, y, batch_size: int, order):
+    """What `DataLoader(TensorDataset(X, y), batch_size, shuffle=True)` (attncut_dataloader.py:86-87) collates for a given
+    visiting order: consecutive slices of the order, last one partial."""
+    X, y, order = np.asarray(X), np.asarray(y), np.asarray(order)
+    return [(X[order[lo:lo + batch_size]], y[order[lo:lo + batch_size]]) for lo in range(0, len(order), batch_size)]
+
+
 def taskr_dcg_per_list(labels, predictions) -> list:
     """The DCG_sample values of Metric.taskr_metric (utils/metrics.py:51-57): documents in descending-prediction order,
     +-1/log2(i+2) accumulated left to right as Python floats.  Ties: list order (stable sort); the reference's default

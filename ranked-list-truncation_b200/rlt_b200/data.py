@@ -5,10 +5,15 @@ extra features : U(0,1)   (the two neighbour-similarity features of the AttnCut 
 label_j ~ Bernoulli(a * exp(-j/tau)), a ~ U(0.2, 0.9), tau ~ U(10, 80) per list, >= 1 relevant forced
 Returns X [n, L, F] float32 and y [n, L] float32 in {0,1}, the shapes the reference loaders yield
 (dataloader/attncut_dataloader.py:21-59, choopy_dataloader.py:21-45).
+
+Row N3: `DeviceLoader` keeps a whole split resident in HBM and replaces the torch DataLoader
+of dataloader/attncut_dataloader.py:82-87 -- same iteration protocol, same batches under the same torch seed.
 """
 from __future__ import annotations
 
 import torch
+
+from . import _lib
 
 
 def synthetic_lists(n_lists: int, seq_len: int = 300, n_features: int = 3, seed: int = 20240229,
@@ -30,3 +35,83 @@ def synthetic_lists(n_lists: int, seq_len: int = 300, n_features: int = 3, seed:
     empty = y.sum(dim=1) == 0
     y[empty, 0] = 1.0
     return x, y.contiguous()
+
+
+def shuffled_order(n: int) -> torch.Tensor:
+    """The order in which `DataLoader(TensorDataset(..), shuffle=True)` visits n items in its next epoch, consuming the
+    global CPU generator exactly as torch does: one int64 draw for the iterator's base seed
+    (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__), one for the RandomSampler's private generator
+    (sampler.py, RandomSampler.__iter__), then `randperm(n)` from that generator.  With the same `torch.manual_seed` the
+    batches therefore contain the same lists as the reference's loader (attncut_dataloader.py:86-87)."""
+    torch.empty((), dtype=torch.int64).random_()
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return torch.randperm(n, generator=g)
+
+
+class DeviceLoader:
+    """A split held in HBM once -- X [N, L, F] float32, labels [N, L] as float32 or as bit masks (`pack_labels=True`:
+    one uint32 per 32 documents) -- iterated like the reference's `data.DataLoader(TensorDataset(X, y), batch_size,
+    shuffle=True)`: `for X_b, y_b in loader` yields `[b, L, F]` / `[b, L]` float32 CUDA tensors, the last batch partial,
+    `len(loader)` batches per epoch, a new permutation every epoch.  A batch is one rlt_gather_lists launch; the only
+    host->device traffic per epoch is the permutation (8 N bytes)."""
+
+    def __init__(self, X: torch.Tensor, y: torch.Tensor, batch_size: int = 20, shuffle: bool = True,
+                 pack_labels: bool = False, device=None):
+        if X.dim() != 3 or y.dim() != 2 or X.shape[:2] != y.shape:
+            raise ValueError(f"expected X [N, L, F] and y [N, L]; got {tuple(X.shape)} and {tuple(y.shape)}")
+        if batch_size < 1:
+            raise ValueError("batch_size should be a positive integer value")
+        if not torch.cuda.is_available():
+            raise RuntimeError("DeviceLoader needs a CUDA device (rlt_b200 has no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.batch_size, self.shuffle = int(batch_size), bool(shuffle)
+        self.n_lists, self.seq_len, self.n_features = (int(v) for v in X.shape)
+        self.X = X.detach().to(self.device, torch.float32).contiguous()
+        labels = y.detach().to(self.device, torch.float32).contiguous()
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.y = self.y_bits = None
+        if pack_labels:
+            words = (self.seq_len + 31) // 32
+            self.y_bits = torch.empty(self.n_lists, words, dtype=torch.int32, device=self.device)
+            _lib.check(_lib.load().rlt_pack_labels(_lib.ptr(labels), self.n_lists, self.seq_len, _lib.ptr(self.y_bits),
+                                                   _lib.ptr(self._status), _lib.stream_ptr()), "rlt_pack_labels")
+            if int(self._status.item()) & 2:
+                raise ValueError("labels other than 0. and 1. cannot be stored as bit masks")
+        else:
+            self.y = labels
+
+    def __len__(self) -> int:
+        return (self.n_lists + self.batch_size - 1) // self.batch_size
+
+    def gather(self, index: torch.Tensor | None, n_out: int | None = None):
+        """(X[index], y[index]) as fresh contiguous CUDA tensors; `index` int64 on the device (None: the first n_out)."""
+        n_out = int(index.numel()) if index is not None else int(n_out)
+        if index is not None and (index.dtype != torch.int64 or index.device != self.device or not index.is_contiguous()):
+            raise ValueError("index must be a contiguous int64 tensor on the loader's device")
+        xb = torch.empty(n_out, self.seq_len, self.n_features, dtype=torch.float32, device=self.device)
+        yb = torch.empty(n_out, self.seq_len, dtype=torch.float32, device=self.device)
+        _lib.check(_lib.load().rlt_gather_lists(_lib.ptr(self.X), _lib.ptr(self.y), _lib.ptr(self.y_bits), _lib.ptr(index),
+                                                self.n_lists, n_out, self.seq_len, self.n_features, _lib.ptr(xb), _lib.ptr(yb),
+                                                _lib.ptr(self._status), _lib.stream_ptr()), "rlt_gather_lists")
+        return xb, yb
+
+    def check(self) -> None:
+        """Raises IndexError if any gather since the last check saw an index outside [0, N) (one host sync)."""
+        if int(self._status.item()) & 1:
+            self._status.zero_()
+            raise IndexError("DeviceLoader: list index out of range")
+
+    def __iter__(self):
+        order = (shuffled_order(self.n_lists) if self.shuffle else torch.arange(self.n_lists)).to(self.device)
+        for lo in range(0, self.n_lists, self.batch_size):
+            yield self.gather(order[lo:lo + self.batch_size])
+        self.check()                          # once per epoch, after the last batch: no per-step host sync
+
+
+def device_loaders(X_train, X_test, y_train, y_test, batch_size: int = 20, pack_labels: bool = False):
+    """The (train_loader, test_loader) pair of dataloader/attncut_dataloader.py:72-89 (both shuffled, as there) on
+    tensors the caller has already built (the reference reads them from pickles, :29-59)."""
+    return (DeviceLoader(X_train, y_train, batch_size, True, pack_labels),
+            DeviceLoader(X_test, y_test, batch_size, True, pack_labels))
