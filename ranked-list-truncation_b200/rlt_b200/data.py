@@ -50,15 +50,28 @@ def shuffled_order(n: int) -> torch.Tensor:
     return torch.randperm(n, generator=g)
 
 
+def batch_slices(n_lists: int, batch_size: int, rank: int = 0, world: int = 1, drop_uneven: bool = True):
+    """[lo, hi) slices of the epoch order that `rank` collates.  The batch is the unit of sharding (the reference attends
+    across the lists of a batch, so a batch must stay whole -- parallel.py): rank r takes batches r, r+W, r+2W, ... of the
+    order every rank derives from the same seed, without communication.  `drop_uneven` (world > 1) ends the epoch after
+    the last complete round of W batches so that every rank runs the same number of steps (and of all-reduces)."""
+    from .parallel import shard_groups
+    n_batches = (n_lists + batch_size - 1) // batch_size
+    if world > 1 and drop_uneven:
+        n_batches -= n_batches % world
+    return [(b * batch_size, min(n_lists, (b + 1) * batch_size)) for b in shard_groups(n_batches, rank, world)]
+
+
 class DeviceLoader:
     """A split held in HBM once -- X [N, L, F] float32, labels [N, L] as float32 or as bit masks (`pack_labels=True`:
     one uint32 per 32 documents) -- iterated like the reference's `data.DataLoader(TensorDataset(X, y), batch_size,
     shuffle=True)`: `for X_b, y_b in loader` yields `[b, L, F]` / `[b, L]` float32 CUDA tensors, the last batch partial,
     `len(loader)` batches per epoch, a new permutation every epoch.  A batch is one rlt_gather_lists launch; the only
-    host->device traffic per epoch is the permutation (8 N bytes)."""
+    host->device traffic per epoch is the permutation (8 N bytes).  With `world > 1` (one process per GPU) every rank
+    holds the split and collates its own batches of the common order (`batch_slices`)."""
 
     def __init__(self, X: torch.Tensor, y: torch.Tensor, batch_size: int = 20, shuffle: bool = True,
-                 pack_labels: bool = False, device=None):
+                 pack_labels: bool = False, device=None, rank: int = 0, world: int = 1, drop_uneven: bool = True):
         if X.dim() != 3 or y.dim() != 2 or X.shape[:2] != y.shape:
             raise ValueError(f"expected X [N, L, F] and y [N, L]; got {tuple(X.shape)} and {tuple(y.shape)}")
         if batch_size < 1:
@@ -67,6 +80,7 @@ class DeviceLoader:
             raise RuntimeError("DeviceLoader needs a CUDA device (rlt_b200 has no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.batch_size, self.shuffle = int(batch_size), bool(shuffle)
+        self.rank, self.world, self.drop_uneven = int(rank), int(world), bool(drop_uneven)
         self.n_lists, self.seq_len, self.n_features = (int(v) for v in X.shape)
         self.X = X.detach().to(self.device, torch.float32).contiguous()
         labels = y.detach().to(self.device, torch.float32).contiguous()
@@ -83,7 +97,7 @@ class DeviceLoader:
             self.y = labels
 
     def __len__(self) -> int:
-        return (self.n_lists + self.batch_size - 1) // self.batch_size
+        return len(batch_slices(self.n_lists, self.batch_size, self.rank, self.world, self.drop_uneven))
 
     def gather(self, index: torch.Tensor | None, n_out: int | None = None):
         """(X[index], y[index]) as fresh contiguous CUDA tensors; `index` int64 on the device (None: the first n_out)."""
@@ -105,8 +119,8 @@ class DeviceLoader:
 
     def __iter__(self):
         order = (shuffled_order(self.n_lists) if self.shuffle else torch.arange(self.n_lists)).to(self.device)
-        for lo in range(0, self.n_lists, self.batch_size):
-            yield self.gather(order[lo:lo + self.batch_size])
+        for lo, hi in batch_slices(self.n_lists, self.batch_size, self.rank, self.world, self.drop_uneven):
+            yield self.gather(order[lo:hi])
         self.check()                          # once per epoch, after the last batch: no per-step host sync
 
 
