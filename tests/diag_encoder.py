@@ -1,4 +1,5 @@
-"""Diagnostic: per-tensor gradient error of the encoder layer, tcgen05 vs SIMT backend vs float64 oracle."""
+"""Diagnostic (run by hand on a GPU box: `python tests/diag_encoder.py`; not collected by pytest): per-tensor gradient
+error of the encoder layer, tcgen05 vs SIMT backend vs float64 oracle.  Lives under tests/ because it imports oracle/."""
 import sys, ctypes, warnings
 from pathlib import Path
 import torch
