@@ -39,6 +39,13 @@ MODELS = {
     "plecut": ("PLECut", dict(seq_len=300, input_size=3, dropout=0.0, num_experts=3), 3),
     # verify_probe.py:61: the base model of the probing experiment; forward returns (experts_in, experts_o, towers)
     "probebase": ("ProbeBase", dict(seq_len=300, num_tasks=3, input_size=3, dropout=0.0, num_experts=2), 3),
+    # run.py --num_tasks 2.1 (class + cut) / 2.2 (rerank + cut); B = 5 only
+    "mtchoopy_t21": ("MtChoopy", dict(seq_len=300, num_tasks=2.1, dropout=0.0), 1),
+    "mtchoopy_t22": ("MtChoopy", dict(seq_len=300, num_tasks=2.2, dropout=0.0), 1),
+    "mtattncut_t21": ("MtAttnCut", dict(input_size=3, num_tasks=2.1, dropout=0.0), 3),
+    "mtattncut_t22": ("MtAttnCut", dict(input_size=3, num_tasks=2.2, dropout=0.0), 3),
+    "mmoecut_t21": ("MMOECut", dict(seq_len=300, num_tasks=2.1, input_size=3, dropout=0.0, num_experts=3), 3),
+    "mmoecut_t22": ("MMOECut", dict(seq_len=300, num_tasks=2.2, input_size=3, dropout=0.0, num_experts=3), 3),
 }
 
 
@@ -69,16 +76,17 @@ def build_criterion(ref_losses, name: str, metric: str):
         return ref_losses.ChoopyLoss(metric=metric)
     if name == "attncut":
         return ref_losses.DivLoss(metric=metric, div_type="js", augmented=True)
-    if name in ("mtchoopy", "mtattncut"):
-        return ref_losses.MtCutLoss(metric=metric, rerank_weight=0.5, classi_weight=0.5, num_tasks=3)
-    return ref_losses.MtCutLoss(metric=metric, num_tasks=3)
+    num_tasks = MODELS[name][1].get("num_tasks", 3)
+    if name.startswith(("mtchoopy", "mtattncut")):
+        return ref_losses.MtCutLoss(metric=metric, rerank_weight=0.5, classi_weight=0.5, num_tasks=num_tasks)
+    return ref_losses.MtCutLoss(metric=metric, num_tasks=num_tasks)
 
 
 def model_goldens(ref_models, ref_losses, only=None):
     for name, (cls_name, kwargs, feats) in MODELS.items():
         if only and name not in only:
             continue
-        for B in (5, 16):
+        for B in ((5,) if name.endswith(("_t21", "_t22")) else (5, 16)):
             torch.manual_seed(WEIGHT_SEED)
             model = getattr(ref_models, cls_name)(**kwargs)
             model.train()  # dropout = 0: train mode is deterministic and matches what run.py trains with

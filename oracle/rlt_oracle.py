@@ -604,6 +604,15 @@ FORWARDS = {
     "mtchoopy": mtchoopy_forward, "mtattncut": mtattncut_forward, "mmoecut": mmoecut_forward,
     "moecut": moecut_forward, "plecut": plecut_forward, "probebase": probebase_forward,
 }
+# the two-task variants of run.py's --num_tasks (2.1 = class + cut, 2.2 = rerank + cut; MtChoopy.py:27-32,
+# MtAttnCut.py:24-29, MMOECut.py:74-84): "<model>_t21" / "<model>_t22"
+for _base in ("mtchoopy", "mtattncut", "mmoecut"):
+    for _tag, _nt in (("t21", 2.1), ("t22", 2.2)):
+        FORWARDS[f"{_base}_{_tag}"] = (lambda sd, x, _f=FORWARDS[_base], _nt=_nt, **kw: _f(sd, x, num_tasks=_nt, **kw))
+
+
+def num_tasks_of(model_name: str) -> float:
+    return 2.1 if model_name.endswith("_t21") else 2.2 if model_name.endswith("_t22") else 3
 
 
 def criterion_for(model_name: str, metric: str = "f1", loop: bool = False, **kw):
@@ -615,7 +624,7 @@ def criterion_for(model_name: str, metric: str = "f1", loop: bool = False, **kw)
     if model_name == "attncut":
         return lambda out, y: div_loss(out, y, metric=metric, div_type=kw.get("div_type", "js"),
                                        augmented=kw.get("augmented", True), loop=loop)
-    return lambda out, y: mtcut_loss(out, y, metric=metric, num_tasks=kw.get("num_tasks", 3),
+    return lambda out, y: mtcut_loss(out, y, metric=metric, num_tasks=kw.get("num_tasks", num_tasks_of(model_name)),
                                      rerank_weight=kw.get("rerank_weight", 0.5),
                                      classi_weight=kw.get("classi_weight", 0.5), loop=loop)
 

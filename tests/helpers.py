@@ -19,7 +19,15 @@ MODEL_KW = {
     "moecut": ("MOECut", dict(seq_len=300, num_tasks=3, input_size=3, dropout=0.0)),
     "plecut": ("PLECut", dict(seq_len=300, input_size=3, dropout=0.0, num_experts=3)),
     "probebase": ("ProbeBase", dict(seq_len=300, num_tasks=3, input_size=3, dropout=0.0, num_experts=2)),
+    # run.py --num_tasks 2.1 (class + cut) / 2.2 (rerank + cut): goldens at B = 5 only
+    "mtchoopy_t21": ("MtChoopy", dict(seq_len=300, num_tasks=2.1, dropout=0.0)),
+    "mtchoopy_t22": ("MtChoopy", dict(seq_len=300, num_tasks=2.2, dropout=0.0)),
+    "mtattncut_t21": ("MtAttnCut", dict(input_size=3, num_tasks=2.1, dropout=0.0)),
+    "mtattncut_t22": ("MtAttnCut", dict(input_size=3, num_tasks=2.2, dropout=0.0)),
+    "mmoecut_t21": ("MMOECut", dict(seq_len=300, num_tasks=2.1, input_size=3, dropout=0.0, num_experts=3)),
+    "mmoecut_t22": ("MMOECut", dict(seq_len=300, num_tasks=2.2, input_size=3, dropout=0.0, num_experts=3)),
 }
+TWO_TASK = [n for n in MODEL_KW if n.endswith(("_t21", "_t22"))]
 PROBE_SEED = 4321
 
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import MODEL_KW, build_model, check_weights, grad_errors, load_golden, output_error, probe_inputs
+from helpers import MODEL_KW, TWO_TASK, build_model, check_weights, grad_errors, load_golden, output_error, probe_inputs
 from oracle import rlt_oracle as O
 
 
@@ -111,8 +111,7 @@ def test_aux_and_bicut_losses_vs_reference(L):
         assert np.abs(o.grad.numpy() - g[f"bicut_{metric}_{L}/do"]).max() <= 1e-5 * np.abs(g[f"bicut_{metric}_{L}/do"]).max()
 
 
-@pytest.mark.parametrize("B", [5, 16])
-@pytest.mark.parametrize("name", list(MODEL_KW))
+@pytest.mark.parametrize("name,B", [(n, B) for n in MODEL_KW for B in ((5,) if n in TWO_TASK else (5, 16))])
 def test_model_oracle_vs_reference(name, B):
     """Weights reproduced from the seed, oracle forward (fp32 and fp64), loss and gradients vs the reference."""
     g = load_golden(f"model_{name}_B{B}.npz")
