@@ -11,6 +11,10 @@ of dataloader/attncut_dataloader.py:82-87 -- same iteration protocol, same batch
 """
 from __future__ import annotations
 
+import pickle
+from pathlib import Path
+
+import numpy as np
 import torch
 
 from . import _lib
@@ -129,3 +133,62 @@ def device_loaders(X_train, X_test, y_train, y_test, batch_size: int = 20, pack_
     tensors the caller has already built (the reference reads them from pickles, :29-59)."""
     return (DeviceLoader(X_train, y_train, batch_size, True, pack_labels),
             DeviceLoader(X_test, y_test, batch_size, True, pack_labels))
+
+
+def rank_tensors(database, dataset_name: str = "bm25", stats: bool = True):
+    """(X_train, X_test, y_train, y_test) from the reference's pickle files, as `Rank_Dataset.data_prepare` builds them
+    (dataloader/attncut_dataloader.py:21-59 with `stats=True`: X [N, L, 3] = retrieval score + the two neighbour
+    statistics of `attncut/{name}_{split}.pkl`; dataloader/choopy_dataloader.py:21-45 with `stats=False`: X [N, L, 1]);
+    y [N, L] float32, 1. where the document id is in `gt.pkl[qid]`.  `database` is the reference's
+    `DATASET_BASE + '/' + retrieve_data` directory.  Same values as the reference (python floats rounded once to
+    float32), built through numpy instead of nested Python lists; every query of a split must have the same length."""
+    database = Path(database)
+
+    def load(name):
+        with open(database / name, "rb") as f:
+            return pickle.load(f)
+
+    gt = {key: set(docs) for key, docs in load("gt.pkl").items()}
+
+    def split(which):
+        raw = load(f"{dataset_name}_{which}.pkl")
+        extra = load(f"attncut/{dataset_name}_{which}.pkl") if stats else None
+        xs, ys = [], []
+        for key, ranked in raw.items():
+            feats = np.fromiter(ranked.values(), dtype=np.float64, count=len(ranked)).reshape(-1, 1)
+            if stats:
+                feats = np.column_stack((feats, np.asarray(extra[key], dtype=np.float64)))
+            rel = gt[key]                                            # KeyError for an unjudged query, as in the reference
+            xs.append(feats)
+            ys.append(np.fromiter((1.0 if doc in rel else 0.0 for doc in ranked), dtype=np.float32, count=len(ranked)))
+        return torch.from_numpy(np.stack(xs).astype(np.float32)), torch.from_numpy(np.stack(ys))
+
+    (x_tr, y_tr), (x_te, y_te) = split("train"), split("test")
+    return x_tr, x_te, y_tr, y_te
+
+
+def write_synthetic_pickles(database, dataset_name: str = "bm25", n_train: int = 199, n_test: int = 50, seq_len: int = 300,
+                            seed: int = 20240229) -> None:
+    """Synthetic robust04-shaped data in the reference's on-disk formats, so that the reference's
+    own loaders -- and `rank_tensors` -- can be driven without the original corpus: `{name}_{train,test}.pkl`
+    (dict qid -> dict doc_id -> score, rank order), `attncut/{name}_{train,test}.pkl` (dict qid -> list[L][2]) and `gt.pkl`
+    (dict qid -> list of relevant doc ids)."""
+    database = Path(database)
+    (database / "attncut").mkdir(parents=True, exist_ok=True)
+    x, y = synthetic_lists(n_train + n_test, seq_len, 3, seed=seed)
+    gt, q = {}, 0
+    for which, n in (("train", n_train), ("test", n_test)):
+        raw, extra = {}, {}
+        for _ in range(n):
+            qid = str(301 + q)
+            docs = [f"D{q:04d}-{j:03d}" for j in range(seq_len)]
+            raw[qid] = {d: float(v) for d, v in zip(docs, x[q, :, 0].tolist())}
+            extra[qid] = x[q, :, 1:].double().tolist()
+            gt[qid] = [d for d, r in zip(docs, y[q].tolist()) if r == 1.0] + [f"D{q:04d}-unretrieved"]
+            q += 1
+        with open(database / f"{dataset_name}_{which}.pkl", "wb") as f:
+            pickle.dump(raw, f)
+        with open(database / "attncut" / f"{dataset_name}_{which}.pkl", "wb") as f:
+            pickle.dump(extra, f)
+    with open(database / "gt.pkl", "wb") as f:
+        pickle.dump(gt, f)
