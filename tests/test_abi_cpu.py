@@ -72,3 +72,26 @@ def test_probe_modules_match_reference_layout():
     assert models.TaskR().rerank_layer[0].in_features == 128
     with pytest.raises(RuntimeError, match="no CPU"):
         models.TowerClass(d_model=256)(torch.randn(2, 40, 256))
+
+
+def test_python_call_sites_match_header_arity():
+    """The ctypes calls carry no argtypes, so a drifted argument list would only show up as garbage on the GPU: every
+    `<lib>.rlt_*(...)` call in the host package must pass exactly as many arguments as include/rlt_b200.h declares."""
+    import ast
+    import re
+    from pathlib import Path
+    text = re.sub(r"/\*.*?\*/", "", _lib.HEADER_PATH.read_text(), flags=re.S)
+    arity = {}
+    for name, params in re.findall(r"\b(rlt_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", text):
+        params = params.strip()
+        arity[name] = 0 if params in ("", "void") else params.count(",") + 1
+    assert len(arity) >= 20 and arity["rlt_rank_metrics"] == 9 and arity["rlt_gather_lists"] == 12
+    pkg = Path(_lib.__file__).resolve().parent.parent
+    checked = 0
+    for path in sorted(pkg.rglob("*.py")):
+        for node in ast.walk(ast.parse(path.read_text())):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr in arity:
+                assert not node.keywords and not any(isinstance(a, ast.Starred) for a in node.args), (path.name, node.func.attr)
+                assert len(node.args) == arity[node.func.attr], (path.name, node.lineno, node.func.attr, len(node.args))
+                checked += 1
+    assert checked >= 30, checked
