@@ -6,6 +6,8 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_gpu_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_gpu_tests.log
 tail -3 gpurun_out/${TAG}_gpu_tests.log
+# rows N3 / N4: roofline lines of the gather and rank-metric kernels (never measured in round 1)
+timeout 300 python tools/bench_data.py > gpurun_out/${TAG}_bench_data.txt 2>&1; tail -6 gpurun_out/${TAG}_bench_data.txt
 timeout 600 python bench.py --impl reference > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench.err
 timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2>> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 cat gpurun_out/${TAG}_bench_ref.json gpurun_out/${TAG}_bench.json | cut -c1-600
