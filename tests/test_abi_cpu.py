@@ -95,3 +95,13 @@ def test_python_call_sites_match_header_arity():
                 assert len(node.args) == arity[node.func.attr], (path.name, node.lineno, node.func.attr, len(node.args))
                 checked += 1
     assert checked >= 30, checked
+
+
+def test_rank_metrics_refuse_a_host_without_cuda():
+    import numpy as np
+    from utils.metrics import Metric
+    if torch.cuda.is_available():
+        pytest.skip("needs a host without CUDA")
+    for fn in (Metric.taskr_metric, Metric.taskc_metric):
+        with pytest.raises(RuntimeError, match="no CPU"):
+            fn(np.zeros((1, 4), np.float32), np.zeros((1, 4), np.float32))
