@@ -106,6 +106,22 @@ int rlt_adam_step(const unsigned long long* param_ptrs, const unsigned long long
                   float* exp_avg_sq, const long long* state_offset, const int* chunk_tensor, const int* chunk_first,
                   const int* chunk_len, int n_chunks, double lr, double beta1, double beta2, double eps,
                   double weight_decay, long long step, double grad_scale, rlt_stream_t stream);
+/* The same step with torch.optim.Adam's per-parameter bookkeeping on the DEVICE: tensor_steps [n_tensors] (int32,
+ * zero-initialised by the caller) holds each tensor's own step count -- torch keeps `state['step']` per parameter and
+ * does not touch a parameter whose `.grad` is None (no decay, no moment update, no step increment; run.py:121
+ * `optimizer.zero_grad()` resets the gradients to None every batch, and the rerank head has none while its hinge is
+ * inactive, utils/losses.py:141).  tensor_skip [n_tensors] (int32, may be NULL): non-zero = leave tensor t alone this
+ * step.  Bias corrections are evaluated per tensor from its own count; no scalar depends on the host, so the launch
+ * can be captured in a CUDA graph. */
+int rlt_adam_step_masked(const unsigned long long* param_ptrs, const unsigned long long* grad_ptrs, float* exp_avg,
+                         float* exp_avg_sq, const long long* state_offset, const int* chunk_tensor,
+                         const int* chunk_first, const int* chunk_len, int n_chunks, int n_tensors, int* tensor_steps,
+                         const int* tensor_skip, double lr, double beta1, double beta2, double eps, double weight_decay,
+                         double grad_scale, rlt_stream_t stream);
+/* tensor_skip[tensor_ids[i]] = 1 when NO group of `status` (rlt_aux_heads_loss) has its hinge bit (2) set, else 0:
+ * the Engine's device-side replacement of "param.grad is None" for the rerank-head parameters. */
+int rlt_adam_skip_from_status(const int32_t* status, int n_groups, const int* tensor_ids, int n_ids, int* tensor_skip,
+                              rlt_stream_t stream);
 /* Probe: TMA-load a [rows<=128, 32] fp32 tile of src through a TFLOAT32 tensor map and copy the
  * shared-memory image (de-swizzled) to dst.  Used once to learn whether TMA rounds or truncates. */
 int rlt_probe_tma_tf32(const float* src, float* dst, int rows, rlt_stream_t stream);
@@ -339,8 +355,10 @@ typedef struct rlt_aux_loss_desc {
   float loss_scale;
 } rlt_aux_loss_desc;
 /* zc / zr: class / rerank head LOGITS [G*S, L] (either may be NULL).  probs_c: sigmoid(zc) (optional);
- * out_r: softmax(zr) when rerank_softmax (required then).  status[g] = 1 when a group has no relevant or
- * no irrelevant document (the reference raises RuntimeError there; the wrapper does too). */
+ * out_r: softmax(zr) when rerank_softmax (required then).  status[g]: bit 0 set when a group has no relevant or
+ * no irrelevant document (the reference raises RuntimeError there; the wrapper does too); bit 1 set when the rerank
+ * hinge of the group is active (utils/losses.py:141 returns a gradient-free constant otherwise: the rerank head then
+ * has no gradient at all and torch.optim.Adam skips its parameters, see rlt_adam_step_masked). */
 int rlt_aux_heads_loss(const rlt_aux_loss_desc* desc, const float* zc, const float* zr, const float* labels,
                        float* probs_c, float* out_r, float* dzc, float* dzr, float* loss_group, int32_t* status,
                        float* loss_out, rlt_stream_t stream);

@@ -82,11 +82,61 @@ def build_criterion(ref_losses, name: str, metric: str):
     return ref_losses.MtCutLoss(metric=metric, num_tasks=num_tasks)
 
 
-def model_goldens(ref_models, ref_losses, only=None):
+BIG_BATCH = ("bicut", "choopy", "attncut", "mtchoopy", "mtattncut", "mmoecut")
+TRAJ_STEPS, TRAJ_B, TRAJ_LR, TRAJ_WD = 5, 16, 1e-3, 1e-3
+
+
+def trajectory_goldens(ref_models, ref_losses, only=None):
+    """run.py:104,120-129 for TRAJ_STEPS batches: the unmodified reference model + criterion + torch.optim.Adam(lr,
+    weight_decay) (L2 decay), one batch per step.  Stored: the batches, the loss of every step, digests of the final
+    parameters and of the total parameter displacement.  Pins multi-step behaviour (optimizer coupling, operands that
+    must follow the parameters from step to step)."""
+    for name in BIG_BATCH:
+        if only and name not in only:
+            continue
+        cls_name, kwargs, feats = MODELS[name]
+        torch.manual_seed(WEIGHT_SEED)
+        model = getattr(ref_models, cls_name)(**kwargs)
+        model.train()
+        init = {n: p.detach().clone() for n, p in model.named_parameters()}
+        torch.manual_seed(0)
+        crit = build_criterion(ref_losses, name, "f1")
+        opt = torch.optim.Adam(model.parameters(), lr=TRAJ_LR, weight_decay=TRAJ_WD)
+        rec = {"lr": np.float64(TRAJ_LR), "weight_decay": np.float64(TRAJ_WD), "steps": np.int64(TRAJ_STEPS)}
+        losses = []
+        for step in range(TRAJ_STEPS):
+            x, y = synthetic_lists(TRAJ_B, 300, feats, seed=DATA_SEED + 1000 + step, device="cpu")
+            rec[f"x{step}"], rec[f"y{step}"] = x.numpy(), y.numpy()
+            opt.zero_grad()
+            loss = crit(loss_input(model(x)), y)
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        rec["losses"] = np.array(losses, dtype=np.float64)
+        rng = np.random.default_rng(13)
+        names = []
+        for pname, p in model.named_parameters():
+            names.append(pname)
+            d = digest(p.detach() - init[pname], rng)
+            for k, v in d.items():
+                rec[f"delta/{pname}/{k}"] = v
+            rec[f"final/{pname}/val"] = p.detach().double().numpy().ravel()[d["idx"]]
+        rec["param_names"] = np.array(names)
+        np.savez_compressed(GOLDEN / f"traj_{name}.npz", **rec)
+        print(f"traj_{name}: losses={losses}")
+
+
+def model_goldens(ref_models, ref_losses, only=None, only_sizes=None):
     for name, (cls_name, kwargs, feats) in MODELS.items():
         if only and name not in only:
             continue
-        for B in ((5,) if name.endswith(("_t21", "_t22")) else (5, 16)):
+        # B = 63 / 64: the reference's real batch (run.py:307 default 63, hyper_parameter_bm25.conf:2 -> 64) for the six
+        # families of run.py's dispatch; B = 5 / 16 for everything
+        big = (63, 64) if name in BIG_BATCH else ()
+        sizes = ((5,) if name.endswith(("_t21", "_t22")) else (5, 16)) + big
+        if only_sizes:
+            sizes = tuple(b for b in sizes if b in only_sizes)
+        for B in sizes:
             torch.manual_seed(WEIGHT_SEED)
             model = getattr(ref_models, cls_name)(**kwargs)
             model.train()  # dropout = 0: train mode is deterministic and matches what run.py trains with
@@ -293,6 +343,12 @@ def main():
     ref_models, ref_losses, ref_metrics = refshim.load()
     torch.set_num_threads(8)
     only = set(sys.argv[1:])          # e.g. `python -m oracle.make_golden moecut plecut`: only those model fixtures
+    if "traj" in only:                # `python -m oracle.make_golden traj [names]`: the multi-step fixtures
+        trajectory_goldens(ref_models, ref_losses, only - {"traj"})
+        return
+    if "big" in only:                 # `python -m oracle.make_golden big [names]`: only the B = 63 / 64 fixtures
+        model_goldens(ref_models, ref_losses, (only - {"big"}) or set(BIG_BATCH), only_sizes=(63, 64))
+        return
     if only == {"rank"}:
         rank_metric_goldens(ref_metrics)
         return

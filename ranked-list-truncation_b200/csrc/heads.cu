@@ -538,7 +538,9 @@ __global__ void __launch_bounds__(256) head_dots_bwd_kernel(const float* __restr
 //   rerank: e = mean_{y==0} u - mean_{y==1} u + margin over the group; loss = max(e, 0)   (losses.py:127-141)
 //           u = zr (MtChoopy/MtAttnCut) or softmax_L(zr) (MMOECut towers; rerank_softmax = 1)
 // Writes per-group losses and the gradients dzc, dzr (scaled by the task weights and gscale).
-// status[g] = 1 if the group has no relevant or no irrelevant document (the reference raises).
+// status[g]: bit 0 = the group has no relevant or no irrelevant document (the reference raises); bit 1 = the rerank
+// hinge is active (e > 0).  While it is inactive the reference's criterion returns a constant (losses.py:141), the
+// rerank head receives NO gradient and torch's Adam skips those parameters -- FusedAdam reads this bit to do the same.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) aux_heads_kernel(const float* __restrict__ zc, const float* __restrict__ zr,
                                                         const float* __restrict__ labels, int S, int L,
@@ -612,7 +614,7 @@ __global__ void __launch_bounds__(256) aux_heads_kernel(const float* __restrict_
       }
     }
     loss_group[g] = loss;
-    if (status) status[g] = bad;
+    if (status) status[g] = bad | (active != 0.f ? 2 : 0);   // bit 0: degenerate group, bit 1: the rerank hinge is active
     bc[0] = active; bc[1] = inv_pos; bc[2] = inv_neg;
   }
   __syncthreads();

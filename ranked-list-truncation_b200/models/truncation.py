@@ -50,9 +50,6 @@ def _encoder_params(enc: nn.TransformerEncoder):
 class _Base(nn.Module):
     _dropout_p = 0.0
 
-    def _check_mode(self):
-        """Kept for the callers: every mode is supported (train-mode dropout included)."""
-
     def _p(self) -> float:
         """Dropout probability in effect: the constructor's value in train(), 0 in eval()."""
         return float(self._dropout_p) if self.training else 0.0
@@ -63,10 +60,8 @@ class _Base(nn.Module):
 
     @staticmethod
     def _heads(h, linears):
-        """logits [H, B, L] of H Linear(d, 1) heads evaluated in one pass over h."""
-        w = torch.cat([m.weight for m in linears], dim=0)
-        b = torch.cat([m.bias for m in linears], dim=0)
-        return F.HeadDots.apply(h, w, b)
+        """logits (one [B, L] tensor per head) of H Linear(d, 1) heads evaluated in one pass over h."""
+        return F.HeadDots.apply(h, *[t for m in linears for t in (m.weight, m.bias)])
 
 
 class Choopy(_Base):
@@ -81,7 +76,6 @@ class Choopy(_Base):
         self.decison_layer = _lin_softmax(d_model)
 
     def forward(self, x):
-        self._check_mode()
         h = self._encode(F.ChoopyEmbed.apply(x, self.position_encoding), self.attention_layer)
         z = self._heads(h, [self.decison_layer[0]])
         return F.SoftmaxLists.apply(z[0]).unsqueeze(2)
@@ -103,7 +97,6 @@ class MtChoopy(_Base):
         self.decison_layer = _lin_softmax(d_model)
 
     def forward(self, x):
-        self._check_mode()
         h = self._encode(F.ChoopyEmbed.apply(x, self.position_encoding), self.encoding_layer)
         return _mt_outputs(self, h)
 
@@ -133,7 +126,6 @@ class BiCut(_Base):
                                      nn.Dropout(dropout), nn.Softmax(dim=2))
 
     def forward(self, x):
-        self._check_mode()
         h = F.BiLstm.apply(x, self.bilstm.hidden_size, self.bilstm.num_layers, *self.bilstm._flat_weights)
         return F.BicutHead.apply(h, self.fc.weight, self.fc.bias, self.softmax[1].weight, self.softmax[1].bias, self._p())
 
@@ -150,7 +142,6 @@ class AttnCut(_Base):
         self.decison_layer = _lin_softmax(d_model)
 
     def forward(self, x):
-        self._check_mode()
         e = self.encoding_layer
         h = F.BiLstm.apply(x, e.hidden_size, e.num_layers, *e._flat_weights)
         h = self._encode(h, self.attention_layer)
@@ -173,10 +164,16 @@ class MtAttnCut(_Base):
         self.decison_layer = _lin_softmax(d_model)
 
     def forward(self, x):
-        self._check_mode()
         e = self.pre_encoding
         h = F.BiLstm.apply(x, e.hidden_size, e.num_layers, *e._flat_weights)
         return _mt_outputs(self, self._encode(h, self.encoding_layer))
+
+
+def _moe_towers(h, gates, towers, experts):
+    """Gate softmax, expert mixture and tower Linear(d, 1) of every tower in one kernel pass (MMOECut.py:90-105); the
+    parameters go in one by one so that a tower without gradient keeps `.grad is None` (rlt_b200.autograd.MoeGateMix)."""
+    return F.MoeGateMix.apply(h, len(towers), *gates, *[t.linear.weight for t in towers],
+                              *[t.linear.bias for t in towers], *experts)
 
 
 class _Expert(nn.Module):
@@ -226,13 +223,10 @@ class MMOECut(_Base):
             self.towers = nn.ModuleList([rer(), cut()])
 
     def forward(self, x):
-        self._check_mode()
         e = self.pre_encoding
         h = F.BiLstm.apply(x, e.hidden_size, e.num_layers, *e._flat_weights)
         experts = [self._encode(h, ex.attention_layer) for ex in self.experts]
-        w = torch.cat([t.linear.weight for t in self.towers], dim=0)
-        b = torch.cat([t.linear.bias for t in self.towers], dim=0)
-        z = F.MoeGateMix.apply(h, torch.stack(list(self.w_gates)), w, b, *experts)   # [T, B, L] tower logits
+        z = _moe_towers(h, list(self.w_gates), list(self.towers), experts)   # one [B, L] logit tensor per tower
         outs = []
         for t, tower in enumerate(self.towers):
             outs.append((torch.sigmoid(z[t]) if tower.act == "sigmoid" else F.SoftmaxLists.apply(z[t])).unsqueeze(2))
@@ -265,14 +259,11 @@ class MOECut(_Base):
             self.towers = nn.ModuleList([rer(), cut()])
 
     def forward(self, x):
-        self._check_mode()
         e = self.pre_encoding
         h = F.BiLstm.apply(x, e.hidden_size, e.num_layers, *e._flat_weights)
         experts = [self._encode(h, ex.attention_layer) for ex in self.experts]
-        w = torch.cat([t.linear.weight for t in self.towers], dim=0)
-        b = torch.cat([t.linear.bias for t in self.towers], dim=0)
         # the shared gate is presented once per tower; autograd sums the three gate gradients into the one Parameter
-        z = F.MoeGateMix.apply(h, torch.stack([self.w_gates] * len(self.towers)), w, b, *experts)
+        z = _moe_towers(h, [self.w_gates] * len(self.towers), list(self.towers), experts)
         outs = []
         for t, tower in enumerate(self.towers):
             outs.append((torch.sigmoid(z[t]) if tower.act == "sigmoid" else F.SoftmaxLists.apply(z[t])).unsqueeze(2))
@@ -305,13 +296,12 @@ class PLECut(_Base):
                                      _Tower(self.expert_hidden, "cut_layer", "softmax")])
 
     def forward(self, x):
-        self._check_mode()
         e = self.pre_encoding
         h = F.BiLstm.apply(x, e.hidden_size, e.num_layers, *e._flat_weights)
         experts = [self._encode(h, ex.attention_layer) for ex in self.experts]
         outs = []
         for tower, gate, (lo, hi) in zip(self.towers, self.w_gates, self._SUBSETS):
-            z = F.MoeGateMix.apply(h, gate.unsqueeze(0), tower.linear.weight, tower.linear.bias, *experts[lo:hi])[0]
+            z = _moe_towers(h, [gate], [tower], experts[lo:hi])[0]
             outs.append((torch.sigmoid(z) if tower.act == "sigmoid" else F.SoftmaxLists.apply(z)).unsqueeze(2))
         return outs
 
@@ -381,14 +371,11 @@ class ProbeBase(_Base):
                                      TowerCut(self.expert_hidden)])
 
     def forward(self, x):
-        self._check_mode()
         e = self.pre_encoding
         h = F.BiLstm.apply(x, e.hidden_size, e.num_layers, *e._flat_weights)
         experts = [self._encode(h, ex.attention_layer) for ex in self.experts]
         towers = list(self.towers)[:len(self.w_gates)]          # zip(towers, towers_input) of Probe.py:93
-        w = torch.cat([t.linear.weight for t in towers], dim=0)
-        b = torch.cat([t.linear.bias for t in towers], dim=0)
-        z = F.MoeGateMix.apply(h, torch.stack(list(self.w_gates)), w, b, *experts)
+        z = _moe_towers(h, list(self.w_gates), towers, experts)
         outs = []
         for t, tower in enumerate(towers):
             outs.append((torch.sigmoid(z[t]) if tower.act == "sigmoid" else F.SoftmaxLists.apply(z[t])).unsqueeze(2))

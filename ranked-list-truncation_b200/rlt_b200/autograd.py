@@ -163,39 +163,62 @@ class BicutHead(torch.autograd.Function):
 
 
 class MoeGateMix(torch.autograd.Function):
-    """MMOECut gates, mixtures and tower Linear(d,1) layers (models/MMOECut.py:90-105) -> tower logits [Tk, B, L]."""
+    """MMOECut gates, mixtures and tower Linear(d,1) layers (models/MMOECut.py:90-105).  Called as
+    `MoeGateMix.apply(h_lstm, n_towers, *gates, *tower_w, *tower_b, *experts)` (n_towers gate matrices [L*dl, E], tower
+    weights [1, d] and biases [1], then the E expert outputs); returns one logit tensor [B, L] per tower.
+
+    As for HeadDots, per-tower inputs / outputs preserve "no gradient": the gate and tower parameters of a tower whose
+    logits received no gradient (rerank tower, hinge inactive) get None, as in the reference."""
 
     @staticmethod
-    def forward(ctx, h_lstm, w_gates, tower_w, tower_b, *experts):
-        h_lstm, w_gates = _c(h_lstm), _c(w_gates.detach())
-        tower_w, tower_b = _c(tower_w.detach()), _c(tower_b.detach())
+    def forward(ctx, h_lstm, n_towers, *rest):
+        Tk = int(n_towers)
+        gates_in, tw_in, tb_in, experts = rest[:Tk], rest[Tk:2 * Tk], rest[2 * Tk:3 * Tk], rest[3 * Tk:]
+        h_lstm = _c(h_lstm)
+        w_gates = torch.stack([_c(g.detach()) for g in gates_in])
+        tower_w = torch.cat([_c(t.detach()).reshape(1, -1) for t in tw_in], dim=0)
+        tower_b = torch.cat([_c(t.detach()).reshape(1) for t in tb_in], dim=0)
         experts = [_c(e) for e in experts]
         B, L, dl = h_lstm.shape
-        Tk, J, E = w_gates.shape
+        _, J, E = w_gates.shape
         d = experts[0].shape[2]
         if J != L * dl:
             raise RuntimeError(f"w_gates expects {J} gate inputs but the LSTM output has {L}x{dl}")
+        if E != len(experts):
+            raise RuntimeError(f"gates of width {E} over {len(experts)} experts")
         desc = ops.MoeDesc(B, L, dl, d, E, Tk)
         gates = torch.empty(Tk, B, E, dtype=torch.float32, device=h_lstm.device)
         z = torch.empty(Tk, B, L, dtype=torch.float32, device=h_lstm.device)
         ops.moe_heads_fwd(desc, h_lstm, w_gates, experts, tower_w, tower_b, gates, z)
         ctx.desc = desc
+        ctx.shapes = ([t.shape for t in tw_in], [t.shape for t in tb_in])
         ctx.save_for_backward(h_lstm, w_gates, tower_w, gates, *experts)
-        return z
+        ctx.set_materialize_grads(False)
+        return tuple(z[t] for t in range(Tk))
 
     @staticmethod
-    def backward(ctx, dz):
+    def backward(ctx, *dzs):
         h_lstm, w_gates, tower_w, gates, *experts = ctx.saved_tensors
-        dz = _c(dz)
+        Tk = w_gates.shape[0]
+        if all(g is None for g in dzs):
+            return (None,) * (2 + 3 * Tk + len(experts))
+        B, L, _ = h_lstm.shape
+        dz = torch.stack([torch.zeros(B, L, dtype=torch.float32, device=h_lstm.device) if g is None else _c(g) for g in dzs])
         d_experts = [torch.empty_like(e) for e in experts]
         d_tw = torch.zeros_like(tower_w)
-        d_tb = torch.zeros(tower_w.shape[0], dtype=torch.float32, device=dz.device)
+        d_tb = torch.zeros(Tk, dtype=torch.float32, device=dz.device)
         d_wg = torch.zeros_like(w_gates)
         d_h = torch.empty_like(h_lstm)
         scratch = torch.empty_like(gates)
         ops.moe_heads_bwd(ctx.desc, h_lstm, w_gates, experts, tower_w, gates, dz, d_experts, d_tw, d_tb, d_wg, d_h, False,
                           scratch)
-        return (d_h, d_wg, d_tw, d_tb, *d_experts)
+        live = [g is not None for g in dzs]
+        tw_shapes, tb_shapes = ctx.shapes
+        return (d_h, None,
+                *[d_wg[t] if live[t] else None for t in range(Tk)],
+                *[d_tw[t].reshape(tw_shapes[t]) if live[t] else None for t in range(Tk)],
+                *[d_tb[t].reshape(tb_shapes[t]) if live[t] else None for t in range(Tk)],
+                *d_experts)
 
 
 class ChoopyEmbed(torch.autograd.Function):
@@ -223,29 +246,47 @@ class ChoopyEmbed(torch.autograd.Function):
 
 
 class HeadDots(torch.autograd.Function):
-    """H parallel Linear(d, 1) heads: returns logits [H, B, L]."""
+    """H parallel Linear(d, 1) heads evaluated in ONE pass over h.  Called as `HeadDots.apply(h, w0, b0, w1, b1, ...)`
+    with the heads' own parameters; returns H logit tensors [B, L] (one per head, views of one buffer).
+
+    Separate inputs / outputs per head keep autograd's "no gradient" information: a head whose output received no
+    gradient (the rerank head while its hinge is inactive: the reference's criterion returns a constant there,
+    utils/losses.py:141) gets `None` for its weight and bias, exactly as in the reference, so that an optimizer leaves
+    it alone for that step."""
 
     @staticmethod
-    def forward(ctx, h, w, b):
-        h, w, b = _c(h), _c(w.detach()), _c(b.detach())
+    def forward(ctx, h, *wb):
+        h = _c(h)
+        H = len(wb) // 2
+        w = torch.cat([_c(wb[2 * i].detach()).reshape(1, -1) for i in range(H)], dim=0)
+        b = torch.cat([_c(wb[2 * i + 1].detach()).reshape(1) for i in range(H)], dim=0)
         B, L, d = h.shape
-        H = w.shape[0]
         z = torch.empty(H, B, L, dtype=torch.float32, device=h.device)
         ops.head_dots_fwd(h, w, b, z, B * L, d, H)
         ctx.save_for_backward(h, w)
-        return z
+        ctx.set_materialize_grads(False)
+        ctx.wb_shapes = [t.shape for t in wb]
+        return tuple(z[i] for i in range(H))
 
     @staticmethod
-    def backward(ctx, dz):
+    def backward(ctx, *dzs):
         h, w = ctx.saved_tensors
-        dz = _c(dz)
         B, L, d = h.shape
         H = w.shape[0]
+        if all(g is None for g in dzs):
+            return (None,) * (1 + 2 * H)
+        dz = torch.stack([torch.zeros(B, L, dtype=torch.float32, device=h.device) if g is None else _c(g) for g in dzs])
         dx = torch.empty_like(h)
         dw = torch.zeros_like(w)
         db = torch.zeros(H, dtype=torch.float32, device=h.device)
         ops.head_dots_bwd(h, w, dz, dx, dw, db, B * L, d, H, False)
-        return dx, dw, db
+        out = [dx]
+        for i, g in enumerate(dzs):
+            if g is None:
+                out += [None, None]
+            else:
+                out += [dw[i].reshape(ctx.wb_shapes[2 * i]), db[i].reshape(ctx.wb_shapes[2 * i + 1])]
+        return tuple(out)
 
 
 class SoftmaxLists(torch.autograd.Function):
@@ -311,11 +352,17 @@ class AuxHeadsLoss(torch.autograd.Function):
         ops.aux_heads_loss(pc, zr, labels, n_groups=1, group_size=B, seq_len=L, rerank_softmax=False, class_probs=True,
                            margin=margin, class_weight=class_weight, rerank_weight=rerank_weight, dzc=dpc, dzr=dzr,
                            loss_group=loss_group, status=status, loss_out=loss)
-        if rerank_out is not None and int(status.item()) != 0:
-            # reference utils/losses.py:138 returns torch.tensor(0, requires_grad=True) -> RuntimeError
-            raise RuntimeError("Only Tensors of floating point and complex dtype can require gradients")
+        hinge_active = False
+        if rerank_out is not None:
+            st = int(status.item())     # the reference syncs here too (two .item() calls, utils/losses.py:136-137)
+            if st & 1:
+                # reference utils/losses.py:138 returns torch.tensor(0, requires_grad=True) -> RuntimeError
+                raise RuntimeError("Only Tensors of floating point and complex dtype can require gradients")
+            hinge_active = bool(st & 2)
+        # hinge inactive: the reference's RerankLoss returns a constant zero leaf (losses.py:141) -- the rerank output
+        # gets NO gradient (None), not a zero one, so the heads behind it keep `.grad is None`
         grads = [dpc.reshape(class_p.shape) if class_p is not None else None,
-                 dzr.reshape(rerank_out.shape) if rerank_out is not None else None]
+                 dzr.reshape(rerank_out.shape) if (rerank_out is not None and hinge_active) else None]
         ctx.grads = grads
         return loss
 

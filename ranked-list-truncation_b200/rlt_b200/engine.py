@@ -89,8 +89,13 @@ class Engine:
         self.kind = type(model).__name__.lower()
         if self.kind not in KINDS:
             raise NotImplementedError(f"Engine: unknown model family {type(model).__name__}")
-        if getattr(model, "num_tasks", 3) != 3:
-            raise NotImplementedError("Engine: only num_tasks == 3 is wired (the nn.Module path handles 2.1 / 2.2)")
+        # run.py:327 `--num_tasks` is a float: 3 (class + rerank + cut), 2.1 (class + cut), 2.2 (rerank + cut);
+        # MtChoopy.py:30-32, MtAttnCut.py:27-29, MMOECut.py:69-84, losses.py:181-191
+        self.num_tasks = getattr(model, "num_tasks", 3) if self.kind in ("mtchoopy", "mtattncut", "mmoecut") else 3
+        if self.kind == "mmoecut":      # the reference MMOECut keeps no num_tasks attribute: read it off the towers
+            self.num_tasks = 3 if len(model.towers) == 3 else (2.1 if model.towers[0].act == "sigmoid" else 2.2)
+        if self.num_tasks not in (3, 2.1, 2.2):
+            raise NotImplementedError(f"Engine: num_tasks must be 3, 2.1 or 2.2 (got {self.num_tasks})")
         self.G, self.S, self.L = n_groups, group_size, seq_len
         self.B = n_groups * group_size
         self.T = self.B * seq_len
@@ -159,7 +164,9 @@ class Engine:
         if k in ("choopy", "attncut"):
             self.head_mods = [model.decison_layer[0]]
         elif k in ("mtchoopy", "mtattncut"):
-            self.head_mods = [model.classi[0], model.rerank, model.decison_layer[0]]
+            self.head_mods = {3: [model.classi[0], model.rerank, model.decison_layer[0]],
+                              2.1: [model.classi[0], model.decison_layer[0]],
+                              2.2: [model.rerank, model.decison_layer[0]]}[self.num_tasks]
         elif k == "mmoecut":
             self.head_mods = [t.linear for t in model.towers]
             self.w_gate_params = list(model.w_gates)
@@ -181,6 +188,9 @@ class Engine:
             if training:
                 self.d_fc = torch.empty_like(self.fc_out)
         self.H = 2 if k == "bicut" else len(self.head_mods)
+        # which logit rows feed the auxiliary criteria (None = task absent)
+        self.i_class = 0 if self.num_tasks in (3, 2.1) else None
+        self.i_rerank = {3: 1, 2.1: None, 2.2: 0}[self.num_tasks]
         self.d_head = self.fc_out.shape[1] if k == "bicut" else self.d
         self.head_w = torch.empty(self.H, self.d_head, **f32)
         self.head_b = torch.empty(self.H, **f32)
@@ -192,6 +202,17 @@ class Engine:
         self.loss_group = torch.empty(self.G, **f32)
         self.status = torch.zeros(self.G, dtype=torch.int32, device=self.dev)
         self.loss = torch.zeros((), **f32)
+        # torch.optim.Adam leaves a parameter without gradient alone; the rerank head has none while its hinge is
+        # inactive (losses.py:141).  adam_skip[t] (device, one int32 per parameter in named_params order) is raised for
+        # the rerank head's parameters by the criterion when no group's hinge is active; FusedAdam.for_engine reads it.
+        self.adam_skip = torch.zeros(len(self.named_params), dtype=torch.int32, device=self.dev)
+        self._rerank_param_ids = None
+        if self.i_rerank is not None and k in ("mtchoopy", "mtattncut", "mmoecut"):
+            index = {id(p): i for i, (_, p) in enumerate(self.named_params)}
+            owned = [self.head_mods[self.i_rerank].weight, self.head_mods[self.i_rerank].bias]
+            if k == "mmoecut":
+                owned.append(self.w_gate_params[self.i_rerank])
+            self._rerank_param_ids = torch.tensor([index[id(p)] for p in owned], dtype=torch.int32, device=self.dev)
         self.refresh()
 
     # ------------------------------------------------------------------------------------------
@@ -199,7 +220,9 @@ class Engine:
         return self.grads[self._by_id[id(p)]]
 
     def refresh(self):
-        """Gather small stacked operands from the module parameters (call after every optimizer step)."""
+        """Gather the small stacked operands (head weights, MMOECut gates) from the module parameters.  Called at the
+        start of every forward, so whoever steps the parameters (FusedAdam, a torch optimizer, load_state_dict) is
+        seen by the next step; the copies are a few launches over < 3 MB and are part of the timed step."""
         with torch.no_grad():
             if self.kind == "bicut":
                 self.head_w.copy_(self.head_mods[0].weight)
@@ -216,6 +239,7 @@ class Engine:
     def _forward(self, x, train=False):
         from .autograd import fresh_seed
         k = self.kind
+        self.refresh()      # the stacked head / gate operands follow the parameters (an optimizer may have stepped them)
         if self.lstm is None:
             ops.choopy_embed_fwd(x, self.pe.detach(), self.front)
         else:
@@ -252,11 +276,15 @@ class Engine:
                      loss_per_list=self.loss_per_list, loss_out=self.loss, grad_scale=1.0 / B, loss_scale=1.0 / B)
         if k == "attncut":
             return
-        ops.aux_heads_loss(self.z[0], self.z[1], y, n_groups=G, group_size=self.S, seq_len=self.L,
-                           rerank_softmax=(k == "mmoecut"), class_weight=self.classi_weight,
-                           rerank_weight=self.rerank_weight, grad_scale=1.0 / G, loss_scale=1.0 / G,
-                           out_r=self.rerank_probs if k == "mmoecut" else None, dzc=self.dz[0], dzr=self.dz[1],
+        ic, ir = self.i_class, self.i_rerank
+        ops.aux_heads_loss(None if ic is None else self.z[ic], None if ir is None else self.z[ir], y, n_groups=G,
+                           group_size=self.S, seq_len=self.L, rerank_softmax=(k == "mmoecut"),
+                           class_weight=self.classi_weight, rerank_weight=self.rerank_weight, grad_scale=1.0 / G,
+                           loss_scale=1.0 / G, out_r=self.rerank_probs if (k == "mmoecut" and ir is not None) else None,
+                           dzc=None if ic is None else self.dz[ic], dzr=None if ir is None else self.dz[ir],
                            loss_group=self.loss_group, status=self.status, loss_out=self.loss, accumulate=True)
+        if self._rerank_param_ids is not None:
+            ops.adam_skip_from_status(self.status, self._rerank_param_ids, self.adam_skip)
 
     def train_step(self, x, y):
         """Forward + criterion + backward.  Gradients land in self.grad_bucket (zeroed first), the scalar

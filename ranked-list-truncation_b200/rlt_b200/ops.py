@@ -329,3 +329,9 @@ def bicut_loss(u, labels, *, input_kind=0, metric_nci=False, alpha=0.65, r=0.097
                          loss_scale)
     check(lib().rlt_bicut_loss(C.byref(desc), ptr(u), ptr(labels), ptr(probs_out), ptr(grad), ptr(loss_per_list),
                                ptr(loss_out), stream_ptr()), "rlt_bicut_loss")
+
+
+def adam_skip_from_status(status, tensor_ids, tensor_skip):
+    """tensor_skip[tensor_ids] = 1 when no group's rerank hinge is active (status bit 1 of rlt_aux_heads_loss), else 0."""
+    check(lib().rlt_adam_skip_from_status(ptr(status), int(status.numel()), ptr(tensor_ids), int(tensor_ids.numel()),
+                                          ptr(tensor_skip), stream_ptr()), "rlt_adam_skip_from_status")

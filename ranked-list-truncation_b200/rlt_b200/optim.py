@@ -18,7 +18,7 @@ from .ops import lib
 
 class FusedAdam:
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False, *,
-                 maximize=False, grads=None, grad_scale=1.0):
+                 maximize=False, grads=None, grad_scale=1.0, skip=None):
         """params: iterable of CUDA fp32 parameters (e.g. `model.parameters()`).  grads (optional): one gradient
         tensor per parameter (views of an Engine's bucket: `FusedAdam.for_engine`); default: `param.grad` at step
         time.  grad_scale: factor applied to the gradient first (1/world after a SUM all-reduce)."""
@@ -58,39 +58,51 @@ class FusedAdam:
         self._n_chunks = len(ct)
         self._param_ptrs = torch.tensor([p.data_ptr() for p in self.params], dtype=torch.int64, device=dev)
         self._grad_key, self._grad_ptrs = None, None
+        self.tensor_steps = torch.zeros(len(self.params), **i32)       # torch: state[p]['step'], per parameter
+        self._ext_skip = skip
+        self._skip_key, self._skip = None, None
 
     @classmethod
     def for_engine(cls, engine, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
         """Step the Engine's parameters straight from its flat gradient bucket (after the all-reduce)."""
         params = [p for _, p in engine.named_params]
         grads = [engine.grads[n] for n, _ in engine.named_params]
-        return cls(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grads=grads, grad_scale=grad_scale)
+        return cls(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grads=grads, grad_scale=grad_scale,
+                   skip=engine.adam_skip)
 
     def _grads(self):
+        """(device table of gradient addresses, device skip flags or None)."""
         gs = self._fixed_grads if self._fixed_grads is not None else [p.grad for p in self.params]
         for g, p in zip(gs, self.params):
-            if g is None:
-                raise RuntimeError("FusedAdam.step: a parameter has no gradient (torch.optim.Adam would skip it; the "
-                                   "truncation models produce a gradient for every parameter)")
-            if not (g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and g.numel() == p.numel()):
+            if g is not None and not (g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and g.numel() == p.numel()):
                 raise RuntimeError("FusedAdam.step: gradients must be contiguous float32 CUDA tensors")
-        key = tuple(g.data_ptr() for g in gs)
+        dev = self.params[0].device
+        key = tuple(0 if g is None else g.data_ptr() for g in gs)
         if key != self._grad_key:       # autograd may re-allocate .grad after zero_grad(set_to_none=True)
-            self._grad_ptrs = torch.tensor(key, dtype=torch.int64, device=self.params[0].device)
+            self._grad_ptrs = torch.tensor(key, dtype=torch.int64, device=dev)
             self._grad_key = key
-        return self._grad_ptrs
+        if self._ext_skip is not None:
+            return self._grad_ptrs, self._ext_skip
+        skip_key = tuple(g is None for g in gs)
+        if not any(skip_key):
+            return self._grad_ptrs, None
+        if skip_key != self._skip_key:
+            self._skip = torch.tensor([int(v) for v in skip_key], dtype=torch.int32, device=dev)
+            self._skip_key = skip_key
+        return self._grad_ptrs, self._skip
 
     @torch.no_grad()
     def step(self):
-        gp = self._grads()
+        gp, skip = self._grads()
         self.step_count += 1
         d = self.defaults
-        check(lib().rlt_adam_step(ptr(self._param_ptrs), ptr(gp), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                                  ptr(self._state_offset), ptr(self._chunk_tensor), ptr(self._chunk_first),
-                                  ptr(self._chunk_len), C.c_int(self._n_chunks), C.c_double(d["lr"]),
-                                  C.c_double(d["betas"][0]), C.c_double(d["betas"][1]), C.c_double(d["eps"]),
-                                  C.c_double(d["weight_decay"]), C.c_longlong(self.step_count),
-                                  C.c_double(self.grad_scale), stream_ptr()), "rlt_adam_step")
+        check(lib().rlt_adam_step_masked(ptr(self._param_ptrs), ptr(gp), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                         ptr(self._state_offset), ptr(self._chunk_tensor), ptr(self._chunk_first),
+                                         ptr(self._chunk_len), C.c_int(self._n_chunks), C.c_int(len(self.params)),
+                                         ptr(self.tensor_steps), ptr(skip), C.c_double(d["lr"]),
+                                         C.c_double(d["betas"][0]), C.c_double(d["betas"][1]), C.c_double(d["eps"]),
+                                         C.c_double(d["weight_decay"]), C.c_double(self.grad_scale), stream_ptr()),
+              "rlt_adam_step_masked")
 
     def zero_grad(self, set_to_none=True):
         if self._fixed_grads is not None:
@@ -107,11 +119,15 @@ class FusedAdam:
         return self.exp_avg[o:o + p.numel()].view_as(p), self.exp_avg_sq[o:o + p.numel()].view_as(p)
 
     def state_dict(self):
-        return {"step": self.step_count, "defaults": dict(self.defaults), "exp_avg": self.exp_avg.clone(),
-                "exp_avg_sq": self.exp_avg_sq.clone()}
+        return {"step": self.step_count, "tensor_steps": self.tensor_steps.clone(), "defaults": dict(self.defaults),
+                "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone()}
 
     def load_state_dict(self, sd):
         self.step_count = int(sd["step"])
+        if "tensor_steps" in sd:
+            self.tensor_steps.copy_(sd["tensor_steps"])
+        else:
+            self.tensor_steps.fill_(self.step_count)
         self.defaults.update(sd["defaults"])
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])

@@ -122,3 +122,30 @@ def test_fused_adam_from_engine_bucket():
     for (n, q), ref in zip(eng.named_params, p):
         d = np.abs(q.detach().cpu().numpy() - ref).max()
         assert d <= 2e-7 * np.abs(ref).max() + 1e-9, (n, d)
+
+
+@pytest.mark.gpu
+def test_fused_adam_skips_parameters_without_gradient_like_torch():
+    """torch.optim.Adam leaves a parameter whose .grad is None untouched (no L2 decay, no moment decay) and counts its
+    steps separately (state['step'] per parameter).  run.py:121 resets gradients to None every batch and the rerank
+    head has none while its hinge is inactive (utils/losses.py:141), so the reference freezes it for those batches."""
+    from rlt_b200.optim import FusedAdam
+    torch.manual_seed(3)
+    shapes = [(7, 5), (300,), (4097,), (1,)]
+    pa = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = FusedAdam(pa, lr=1e-2, weight_decay=1e-2)
+    ob = torch.optim.Adam(pb, lr=1e-2, weight_decay=1e-2)
+    present = [(1, 1, 1, 1), (1, 0, 1, 0), (1, 0, 0, 1), (1, 1, 1, 0), (0, 1, 1, 1)]
+    for step, mask in enumerate(present):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            g = torch.randn_like(a) if mask[i] else None
+            a.grad = g
+            b.grad = None if g is None else g.clone()
+        oa.step()
+        ob.step()
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            d = (a - b).abs().max().item()
+            assert d <= 4e-7 * (step + 1) * b.abs().max().item() + 1e-9, (step, i, d)
+    assert oa.tensor_steps.tolist() == [4, 3, 4, 3]
+    assert [int(ob.state[p]["step"]) for p in pb] == [4, 3, 4, 3]

@@ -134,7 +134,7 @@ def test_aux_heads_and_bicut_loss_kernels(L):
                            loss_group=lg, status=st, loss_out=loss)
         assert abs(loss.item() - float(g[f"rerank_{tag}_{L}/loss"])) <= 1e-6
         assert np.abs(dzr.cpu().numpy() - g[f"rerank_{tag}_{L}/ds"].reshape(B, L)).max() <= 1e-8
-        assert st.item() == 0
+        assert st.item() == (2 if tag == "active" else 0)        # bit 1: the hinge is active
     # class head: BCE on sigmoid(z) vs torch, both input conventions
     zc = torch.randn(B, L, device="cuda") * 3
     ref = torch.nn.functional.binary_cross_entropy(torch.sigmoid(zc.double()), y.double()).item()

@@ -1,12 +1,15 @@
 """GPU parity of the two-task variants run.py's `--num_tasks` selects (2.1 = class + cut, 2.2 = rerank + cut;
 MtChoopy.py:27-32, MtAttnCut.py:24-29, MMOECut.py:74-84, losses.py:180-191) against goldens from the unmodified reference.
-Same tolerances as the three-task tests (test_lstm_models_gpu.py).  Added after round 1's GPU budget was spent: the
-oracle side is pinned on CPU (test_oracle_golden.py), this file had not yet run on a B200 when it was committed."""
+Same tolerances as the three-task tests (test_lstm_models_gpu.py), except where the emulated-TF32 floor of a fixture
+(tests/tf32_floor.py, re-derived on the CPU by test_tf32_floor_cpu.py) already exceeds the contract: MtAttnCut 2.2,
+whose gradient is dominated by the token-uniform rerank hinge.  Measured on B200 (round 2, tools/diag_two_task.py):
+rel_max 2.3e-4 / 1.2e-3 (MtAttnCut 2.1 / 2.2), 2.0e-4 (MtChoopy 2.2), 1.8e-4 / 3.9e-4 (MMOECut 2.1 / 2.2)."""
 import numpy as np
 import pytest
 import torch
 
 from helpers import MODEL_KW, TWO_TASK, build_model, check_weights, grad_errors, load_golden, output_error
+from tf32_floor import bounds
 
 pytestmark = pytest.mark.gpu
 
@@ -38,4 +41,5 @@ def test_two_task_variants_vs_reference_golden(name):
     loss.backward()
     named = {n: (p.grad if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
     rel_l2, rel_max, rel_norm = grad_errors(named, g)
-    assert rel_l2 <= 2e-3 and rel_max <= 1e-3, (name, rel_l2, rel_max, rel_norm)
+    l2_bound, max_bound = bounds(f"{name}_B5")
+    assert rel_l2 <= l2_bound and rel_max <= max_bound, (name, rel_l2, rel_max, rel_norm)
