@@ -166,14 +166,14 @@ def reward_matrix(labels: Tensor, metric: str) -> Tensor:
     dt = labels.dtype
     if metric == "f1":
         c = torch.cumsum(labels, dim=1)
-        k = torch.arange(1, L + 1, dtype=dt).unsqueeze(0)
+        k = torch.arange(1, L + 1, dtype=dt, device=labels.device).unsqueeze(0)
         n_rel = labels.sum(dim=1, keepdim=True)
         prec = c / k
         rec = torch.where(n_rel != 0, c / torch.where(n_rel != 0, n_rel, torch.ones_like(n_rel)), torch.zeros_like(c))
         den = prec + rec
         return torch.where(den != 0, prec * rec * 2 / torch.where(den != 0, den, torch.ones_like(den)),
                            torch.zeros_like(den))
-    coef = torch.tensor(DCG_COEF[:L], dtype=torch.float32).to(dt).unsqueeze(0)
+    coef = torch.tensor(DCG_COEF[:L], dtype=torch.float32).to(dt).to(labels.device).unsqueeze(0)
     sign = torch.where(labels == 1., torch.ones_like(labels), -torch.ones_like(labels))
     return torch.cumsum(sign / coef, dim=1)
 

@@ -317,13 +317,12 @@ int rlt_bilstm_fwd(const rlt_bilstm_desc* d, const rlt_bilstm_weights* w, const 
     float* sv = saved ? saved + (l == 0 ? sl.s0 : sl.s1) : nullptr;
     time_begin(TAG_LSTM, stream);
     if (tc) {
-      static bool attr = false;
-      if (!attr) {
+      static DeviceOnce attr;
+      if (attr.first()) {
         RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             int(LstmUmFwdSmem::TOTAL)));
         RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             int(LstmUmFwdSmem::TOTAL)));
-        attr = true;
       }
       LstmInProj inp{};
       const dim3 grid((B + U_TILE - 1) / U_TILE, 2);
@@ -372,11 +371,10 @@ int rlt_bilstm_bwd(const rlt_bilstm_desc* d, const rlt_bilstm_weights* w, const 
       RLT_TRY(grad_scale(dout, size_t(T) * 2 * H, amax, scale, 6, stream));
       // bias gradients (column sums of dA) are accumulated by the recurrence itself
       RLT_CHECK_CUDA(cudaMemsetAsync(colsum_scratch, 0, 2 * G4 * sizeof(float), stream));
-      static bool attr = false;
-      if (!attr) {
+      static DeviceOnce attr;
+      if (attr.first()) {
         RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             int(LstmUmBwdSmem::TOTAL)));
-        attr = true;
       }
       lstm_um_bwd_kernel<<<dim3((B + U_TILE - 1) / U_TILE, 2), U_THREADS, LstmUmBwdSmem::TOTAL, stream>>>(
           dout, sv, w->w_hh[l][0], w->w_hh[l][1], scale, dA, colsum_scratch, B, L);

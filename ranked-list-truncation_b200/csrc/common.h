@@ -40,6 +40,14 @@ void note_launch();
   } while (0)
 
 int num_sms();
+// Per-device one-time setup (cudaFuncSetAttribute / occupancy queries are per device): `static DeviceOnce once;
+// if (once.first()) {...}` runs the body once for every device a process uses.
+struct DeviceOnce {
+  bool done[64] = {};
+  int value[64] = {};
+  int dev() const { int d = 0; return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) ? d : 0; }
+  bool first() { const int d = dev(); if (done[d]) return false; done[d] = true; return true; }
+};
 
 // In-situ kernel timing: when the "time_tag" option equals `tag`, the launch is bracketed by CUDA events on
 // its own stream; rlt_timing_read() sums the elapsed times.  Tags name the GEMM call sites of the encoder.

@@ -207,14 +207,22 @@ int colsum(const float* src, float* out, int T, int C, cudaStream_t stream) {
 // each other at that position.  qkv is [T, 3d] (q | k | v), token t = (g*S + s)*L + l.
 // Two threads per query row split the keys; online softmax in registers; lse saved for backward.
 // ------------------------------------------------------------------------------------------
-template <int DH>
+// attn_mask(): keep-and-scale factor of attention probability (query i, key j) of a work item -- the same element
+// numbering as the tensor-core kernels (attention_mma.cuh) and the rlt_dropout_mask test hook.
+__device__ __forceinline__ float attn_mask(const DropCfg& drop, uint64_t item, int S, int i, int j) {
+  const uint64_t e = (item * uint64_t(S) + uint64_t(i)) * uint64_t(S) + uint64_t(j & ~1);
+  return drop_factor(drop_bits(drop.seed, DROP_ATTN, e), j & 1, drop.thr, drop.scale);
+}
+
+template <int DH, bool kDrop>
 __global__ void __launch_bounds__(128) attn_lists_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ o,
                                                              float* __restrict__ lse, int S, int L, int d,
-                                                             int n_head, float scale) {
+                                                             int n_head, float scale, DropCfg drop) {
   extern __shared__ float sm[];
   float* sK = sm;                 // [S][DH+1]
   float* sV = sm + S * (DH + 1);  // [S][DH+1]
   const int l = blockIdx.x, g = blockIdx.y, h = blockIdx.z;
+  const uint64_t item = (uint64_t(g) * L + l) * n_head + h;   // work-item number of the dropout hash (head fastest)
   const size_t tok0 = (size_t(g) * S) * L + l;  // token of list s: tok0 + s*L
   const int ld = 3 * d;
   for (int i = threadIdx.x; i < S * (DH / 4); i += blockDim.x) {
@@ -253,10 +261,11 @@ __global__ void __launch_bounds__(128) attn_lists_fwd_kernel(const float* __rest
       const float mn = fmaxf(m, sc);
       const float corr = __expf(m - mn);  // exp(-inf) = 0 on the first key
       const float p = __expf(sc - mn);
-      den = den * corr + p;
+      den = den * corr + p;                                   // the row sum stays undropped
+      const float pd = kDrop ? p * attn_mask(drop, item, S, ii, j) : p;
       const float* vr = sV + j * (DH + 1);
 #pragma unroll
-      for (int c = 0; c < DH; ++c) acc[c] = fmaf(acc[c], corr, p * vr[c]);
+      for (int c = 0; c < DH; ++c) acc[c] = fmaf(acc[c], corr, pd * vr[c]);
       m = mn;
     }
     // merge the two halves of the row (partner = lane ^ 1)
@@ -287,11 +296,11 @@ __global__ void __launch_bounds__(128) attn_lists_fwd_kernel(const float* __rest
 
 // Backward: dqkv from (qkv, o, lse, do).  Phase A: thread pair per query row -> dQ.  Phase B: thread pair
 // per key row -> dK, dV (scores recomputed; no atomics).
-template <int DH>
+template <int DH, bool kDrop>
 __global__ void __launch_bounds__(128) attn_lists_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ o,
                                                              const float* __restrict__ lse, const float* __restrict__ d_o,
                                                              float* __restrict__ dqkv, int S, int L, int d, int n_head,
-                                                             float scale) {
+                                                             float scale, DropCfg drop) {
   extern __shared__ float sm[];
   constexpr int P = DH + 1;
   float* sQ = sm;            // [S][P]  (q * scale)
@@ -301,6 +310,7 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_kernel(const float* __rest
   float* sL = sG + S * P;    // lse  [S]
   float* sD = sL + S;        // D_i = dO_i . O_i  [S]
   const int l = blockIdx.x, g = blockIdx.y, h = blockIdx.z;
+  const uint64_t item = (uint64_t(g) * L + l) * n_head + h;
   const size_t tok0 = (size_t(g) * S) * L + l;
   const int ld = 3 * d;
   for (int i = threadIdx.x; i < S * (DH / 4); i += blockDim.x) {
@@ -347,6 +357,7 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_kernel(const float* __rest
       float sc = 0.f, dp = 0.f;
 #pragma unroll
       for (int c = 0; c < DH; ++c) { sc = fmaf(qr[c], kr[c], sc); dp = fmaf(gr[c], vr[c], dp); }
+      if (kDrop) dp *= attn_mask(drop, item, S, ii, j);      // d(attn) = mask/(1-p) * d(dropped attn)
       const float ds = __expf(sc - li) * (dp - Di);
 #pragma unroll
       for (int c = 0; c < DH; ++c) acc[c] = fmaf(ds, kr[c], acc[c]);
@@ -379,9 +390,11 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_kernel(const float* __rest
 #pragma unroll
       for (int c = 0; c < DH; ++c) { sc = fmaf(qr[c], kr[c], sc); dp = fmaf(gr[c], vr[c], dp); }
       const float p = __expf(sc - sL[i]);
-      const float ds = p * (dp - sD[i]);
+      const float mk = kDrop ? attn_mask(drop, item, S, i, jj) : 1.f;
+      const float ds = p * (dp * mk - sD[i]);
+      const float pd = p * mk;                                // dV sees the dropped probabilities
 #pragma unroll
-      for (int c = 0; c < DH; ++c) { ak[c] = fmaf(ds, qr[c], ak[c]); av[c] = fmaf(p, gr[c], av[c]); }
+      for (int c = 0; c < DH; ++c) { ak[c] = fmaf(ds, qr[c], ak[c]); av[c] = fmaf(pd, gr[c], av[c]); }
     }
     float* outk = dqkv + (tok0 + size_t(jj) * L) * ld + d + h * DH;
     float* outv = outk + d;
@@ -406,18 +419,17 @@ template <int DH, int NT, bool kDrop, bool kFull>
 static int attention_fwd_launch(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head, float scale,
                                 cudaStream_t stream, DropCfg drop) {
   const size_t smem = size_t(2) * 3 * NT * 8 * (DH + 4) * sizeof(float);
-  static bool attr_set = false;
-  static int per_sm = 0;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_pipe_kernel<DH, NT, kDrop, kFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_fwd_pipe_kernel<DH, NT, kDrop, kFull>, 128, smem));
-    if (per_sm < 1) per_sm = 1;
-    attr_set = true;
+    int per_sm_q = 0;
+    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_q, attn_lists_fwd_pipe_kernel<DH, NT, kDrop, kFull>, 128, smem));
+    attr_set.value[attr_set.dev()] = per_sm_q < 1 ? 1 : per_sm_q;
   }
   const long long n_items = (long long)G * L * n_head;
   RLT_REQUIRE(n_items < (1ll << 31) && size_t(S) * L * 3 * d < (size_t(1) << 32), RLT_UNSUPPORTED_SHAPE,
               "attention: %lld work items / group span exceed the 32-bit index range", n_items);
-  long long grid = (long long)num_sms() * per_sm;
+  long long grid = (long long)num_sms() * attr_set.value[attr_set.dev()];
   if (grid > n_items) grid = n_items;
   time_begin(TAG_ATTN_FWD, stream);
   attn_lists_fwd_pipe_kernel<DH, NT, kDrop, kFull><<<int(grid), 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, int(n_items), drop);
@@ -442,18 +454,17 @@ static int attention_bwd_launch(const float* qkv, const float* lse, const float*
   constexpr size_t kPS = size_t(2) * NT * 8 * (NT * 8) * sizeof(float);
   constexpr int kBufs = (2 * kBuf + kPS <= 110 * 1024) ? 2 : 1;
   constexpr size_t smem = kBufs * kBuf + kPS;
-  static bool attr_set = false;
-  static int per_sm = 0;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_pipe_kernel<DH, NT, kDrop, kBufs, kFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_lists_bwd_pipe_kernel<DH, NT, kDrop, kBufs, kFull>, 128, smem));
-    if (per_sm < 1) per_sm = 1;
-    attr_set = true;
+    int per_sm_q = 0;
+    RLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_q, attn_lists_bwd_pipe_kernel<DH, NT, kDrop, kBufs, kFull>, 128, smem));
+    attr_set.value[attr_set.dev()] = per_sm_q < 1 ? 1 : per_sm_q;
   }
   const long long n_items = (long long)G * L * n_head;
   RLT_REQUIRE(n_items < (1ll << 31) && size_t(S) * L * 3 * d < (size_t(1) << 32), RLT_UNSUPPORTED_SHAPE,
               "attention: %lld work items / group span exceed the 32-bit index range", n_items);
-  long long grid = (long long)num_sms() * per_sm;
+  long long grid = (long long)num_sms() * attr_set.value[attr_set.dev()];
   if (grid > n_items) grid = n_items;
   time_begin(TAG_ATTN_BWD, stream);
   attn_lists_bwd_pipe_kernel<DH, NT, kDrop, kBufs, kFull><<<int(grid), 128, smem, stream>>>(qkv, lse, d_o, dqkv, S, L, d, n_head, scale, int(n_items), drop);
@@ -487,16 +498,18 @@ static int attention_fwd(const float* qkv, float* o, float* lse, int G, int S, i
     RLT_AF(64);
 #undef RLT_AF
   }
-  RLT_REQUIRE(drop.thr == 0, RLT_UNSUPPORTED_SHAPE, "attention: dropout needs the tensor-core path (S <= 128, head dim 16/32/64)");
   const dim3 grid(L, G, n_head);
   const size_t smem = size_t(2) * S * (dh + 1) * sizeof(float);
   RLT_REQUIRE(smem <= 200 * 1024, RLT_UNSUPPORTED_SHAPE, "attention: group of %d lists does not fit in shared memory", S);
 #define RLT_ATTN_FWD(DH)                                                                                        \
   do {                                                                                                          \
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_kernel<DH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        int(smem)));                                                            \
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         int(smem)));                                                            \
     time_begin(TAG_ATTN_FWD, stream);                                                                           \
-    attn_lists_fwd_kernel<DH><<<grid, 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale);               \
+    if (drop.thr) attn_lists_fwd_kernel<DH, true><<<grid, 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, drop); \
+    else attn_lists_fwd_kernel<DH, false><<<grid, 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, drop);         \
     time_end(TAG_ATTN_FWD, stream);                                                                             \
   } while (0)
   if (dh == 16) RLT_ATTN_FWD(16);
@@ -527,10 +540,13 @@ static int attention_bwd(const float* qkv, const float* o, const float* lse, con
   RLT_REQUIRE(smem <= 200 * 1024, RLT_UNSUPPORTED_SHAPE, "attention bwd: group of %d lists does not fit in shared memory", S);
 #define RLT_ATTN_BWD(DH)                                                                                        \
   do {                                                                                                          \
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_kernel<DH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        int(smem)));                                                            \
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         int(smem)));                                                            \
     time_begin(TAG_ATTN_BWD, stream);                                                                           \
-    attn_lists_bwd_kernel<DH><<<grid, 128, smem, stream>>>(qkv, o, lse, d_o, dqkv, S, L, d, n_head, scale);    \
+    if (drop.thr) attn_lists_bwd_kernel<DH, true><<<grid, 128, smem, stream>>>(qkv, o, lse, d_o, dqkv, S, L, d, n_head, scale, drop); \
+    else attn_lists_bwd_kernel<DH, false><<<grid, 128, smem, stream>>>(qkv, o, lse, d_o, dqkv, S, L, d, n_head, scale, drop);         \
     time_end(TAG_ATTN_BWD, stream);                                                                             \
   } while (0)
   if (dh == 16) RLT_ATTN_BWD(16);

@@ -207,11 +207,10 @@ static int launch_tn_ef(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, i
   const int tiles_m = (M + Cfg::BM - 1) / Cfg::BM, tiles_n = N / BN;
   const int b_res = (g_b_resident != 0 && BN >= 128 && size_t(num_kb) * Cfg::B_BYTES <= size_t(Cfg::RES_B_BYTES) &&
                      tiles_m >= 2 * (grid / tiles_n)) ? 1 : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, OP, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         int(Cfg::SMEM_BYTES)));
-    attr_set = true;
   }
   time_begin(ep.tag, stream);
   gemm_tn_kernel<BN, OP, EF><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep, b_res);
@@ -311,10 +310,9 @@ static int launch_f16out(const __half* A, int lda, const __half* B, int ldb, int
   tmGate = tmOut;
   if (ep.gate_h != nullptr)
     RLT_TRY(make_tmap_any(&tmGate, ep.gate_h, 2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, ep.ldo, 32, false, 32, CU_TENSOR_MAP_SWIZZLE_64B));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16out_kernel<BN, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
-    attr_set = true;
   }
   const int tiles_m = (M + Cfg::BM - 1) / Cfg::BM, tiles_n = N / Cfg::BN;
   RLT_REQUIRE(tiles_n <= num_sms(), RLT_UNSUPPORTED_SHAPE, "gemm: N=%d needs more column blocks than there are SMs", N);
@@ -364,11 +362,10 @@ static int launch_dw_impl(const void* A, int lda, const void* B, int ldb, int T,
     RLT_TRY(make_tmap(&tmA, static_cast<const float*>(A), T, M, lda, Cfg::BT, tma_rounds(), true));
     RLT_TRY(make_tmap(&tmB, static_cast<const float*>(B), T, N, ldb, Cfg::BT, tma_rounds(), true));
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     RLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_dw_kernel<BN, kF16, kColsum>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         int(Cfg::SMEM_BYTES)));
-    attr_set = true;
   }
   const int tiles = ((M + Cfg::BM - 1) / Cfg::BM) * (N / BN);
   const int num_tb = (T + Cfg::BT - 1) / Cfg::BT;
@@ -434,10 +431,9 @@ int ffn_bwd_fused(const __half* du16, const __half* w2th, const __half* hh, __ha
   RLT_TRY(make_tmap_h(&tmW2, w2th, f, d, d, Cfg::BN));
   RLT_TRY(make_tmap_h(&tmH, hh, T, f, f, Cfg::BM));
   RLT_TRY(make_tmap_any(&tmDH, dh16, 2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, T, f, f, 32, false, 32, CU_TENSOR_MAP_SWIZZLE_64B));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     RLT_CHECK_CUDA(cudaFuncSetAttribute(ffn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
-    attr_set = true;
   }
   const int tiles_m = (T + Cfg::BM - 1) / Cfg::BM, tiles_n = f / Cfg::BN;
   int walkers = num_sms() / tiles_n;

@@ -14,10 +14,34 @@ def _buf(nbytes: int, device) -> torch.Tensor:
     return torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
 
 
+_seed_gen = None
+_seed_gen_key = None
+
+
 def fresh_seed() -> int:
-    """Seed of one forward call's dropout masks, drawn from torch's default (host) generator so that
-    torch.manual_seed() makes runs repeatable.  The same seed is handed to the backward kernels."""
-    return int(torch.randint(0, 2 ** 62, (1,)).item())
+    """Seed of one forward call's dropout masks.  Drawn from a PRIVATE host generator seeded from
+    `torch.initial_seed()` (so `torch.manual_seed()` still makes runs repeatable) plus the data-parallel rank (so
+    replicas draw different masks).  torch's global CPU generator is left alone: the reference's dropout runs on the
+    CUDA Philox stream and never consumes it, so a DataLoader / `DeviceLoader.shuffled_order` under the same
+    `torch.manual_seed` keeps producing the reference's batches in every epoch.  The same seed is handed to the
+    backward kernels."""
+    global _seed_gen, _seed_gen_key
+    rank = 0
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank = torch.distributed.get_rank()
+    key = (torch.initial_seed(), rank)
+    if _seed_gen is None or _seed_gen_key != key:
+        _seed_gen = torch.Generator()
+        _seed_gen.manual_seed((key[0] * 1000003 + 7919 * rank + 12345) % (2 ** 63 - 1))
+        _seed_gen_key = key
+    return int(torch.randint(0, 2 ** 62, (1,), generator=_seed_gen).item())
+
+
+def reset_dropout_seed() -> None:
+    """Restart the private dropout-seed stream from `torch.initial_seed()` (it restarts by itself whenever
+    `torch.manual_seed` is given a NEW value; call this to replay a run under the same seed)."""
+    global _seed_gen_key
+    _seed_gen_key = None
 
 
 def _c(t: torch.Tensor) -> torch.Tensor:

@@ -107,6 +107,8 @@ class Engine:
             raise RuntimeError("Engine: the model must live on a CUDA device (no CPU path)")
         self.dev = p0.device
         f32 = dict(dtype=torch.float32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            ops.ensure_tables()         # eager: never inside a later CUDA-graph capture
 
         # ---- parameters and the flat gradient bucket (one all-reduce payload)
         self.named_params = list(model.named_parameters())

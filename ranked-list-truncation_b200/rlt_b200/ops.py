@@ -82,7 +82,9 @@ def _require(t: torch.Tensor, name: str):
 
 
 def ensure_tables():
-    """Upload the DCG tables to the current device once."""
+    """Upload the DCG tables to the current device once.  The upload is a synchronous copy (complete on return, so
+    ordered before any later launch on any stream); Engine.__init__ and the criterion modules call this eagerly so that
+    the first call never falls inside a CUDA-graph capture."""
     dev = torch.cuda.current_device()
     if dev in _tables_on:
         return
