@@ -146,6 +146,9 @@ typedef struct rlt_encoder_desc {
   float ln_eps;        /* 1e-5                                                                       */
   float dropout_p;     /* train-mode dropout probability (0 = eval / no dropout)                     */
   uint64_t dropout_seed;
+  int32_t inference;   /* 1 = forward only (torch.no_grad / eval, run.py:166-167): nothing is kept for a backward --
+                          the FFN hidden never leaves the chip                                             */
+  int32_t reserved;
 } rlt_encoder_desc;
 
 /* nn.TransformerEncoderLayer parameters in state_dict order (all fp32 device pointers). */
@@ -164,6 +167,18 @@ typedef struct rlt_encoder_weights {
   const float* norm2_b;
 } rlt_encoder_weights;
 
+/* The feed-forward block of one encoder layer as ONE kernel (csrc/ffn_fwd_fused.cuh; what rlt_encoder_layer_fwd runs for
+ * d_model 128 without dropout): out = LayerNorm(y + relu(y W1^T + b1) W2^T + b2), torch TransformerEncoderLayer._ff_block
+ * + norm2 (models/Choopy.py:11 etc., dim_feedforward 2048).  y16 / w1_h / w2_h: fp16 copies of y [T, d], linear1.weight
+ * [d_ff, d] and linear2.weight [d, d_ff] (row-major); y: the fp32 residual.  Optional outputs (NULL = forward only):
+ * u2 [T, d] pre-norm sum, stats [T, 2] (mean, rstd), h_out [T, d_ff] fp16 hidden.  d must be 128, d_ff % 128 == 0,
+ * d_ff <= 2048; RLT_UNSUPPORTED_SHAPE otherwise. */
+/* Tools only: device buffer of 64 x 16 int64 that the next rlt_ffn_fused_fwd launches fill with clock64 stamps of the first
+ * CTA pair's MMA thread and first epilogue warp (NULL switches the timeline off, the default). */
+int rlt_ffn_fused_set_timeline(long long* device_buffer);
+int rlt_ffn_fused_fwd(const void* y16, const float* y, const void* w1_h, const float* b1, const void* w2_h, const float* b2,
+                      const float* gamma, const float* beta, float* out, float* u2, float* stats, void* h_out, int n_tokens,
+                      int d_model, int d_ff, float ln_eps, rlt_stream_t stream);
 /* gradient accumulators, same shapes; the backward ADDS into them (zero them or pass .grad). */
 typedef struct rlt_encoder_grads {
   float* in_proj_w;

@@ -75,6 +75,11 @@ int colsum(const float* src, float* out, int T, int C, cudaStream_t stream);   /
 // fp16-operand variants (tensor-core backend only): C = A[M,K] B[N,K]^T and C += alpha * alpha_ptr[0] * A[T,M]^T B[T,N]
 int gemm_tn_h(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const EpiParams& ep,
               cudaStream_t stream);
+bool ffn_fwd_fused_ok(int d, int f);
+void ffn_fwd_set_timeline(long long* dev_buf);
+int ffn_fwd_fused(const __half* y16, const float* y, const __half* w1h, const float* b1, const __half* w2h, const float* b2,
+                  const float* gamma, const float* beta, float* out, float* u2, float* stats, __half* h_out, int T, int d,
+                  int f, float eps, cudaStream_t stream, int tag);
 bool ffn_bwd_fused_ok(int d, int f);
 int ffn_bwd_fused(const __half* du16, const __half* w2th, const __half* hh, __half* dh16, int T, int d, int f, float alpha,
                   const float* scale, float* db1, float* dW2, cudaStream_t stream, int tag);

@@ -648,6 +648,24 @@ int rlt_colsum(const float* src, float* out, int n_rows, int n_cols, rlt_stream_
   return colsum(src, out, n_rows, n_cols, static_cast<cudaStream_t>(stream));
 }
 
+int rlt_ffn_fused_fwd(const void* y16, const float* y, const void* w1_h, const float* b1, const void* w2_h, const float* b2,
+                      const float* gamma, const float* beta, float* out, float* u2, float* stats, void* h_out, int n_tokens,
+                      int d_model, int d_ff, float ln_eps, rlt_stream_t stream) {
+  RLT_REQUIRE(y16 && y && w1_h && b1 && w2_h && b2 && gamma && beta && out && n_tokens > 0, RLT_INVALID_ARG,
+              "rlt_ffn_fused_fwd: null pointer or empty problem");
+  RLT_REQUIRE(ffn_fwd_fused_ok(d_model, d_ff), RLT_UNSUPPORTED_SHAPE,
+              "rlt_ffn_fused_fwd: d_model=%d d_ff=%d (needs d_model 128, d_ff a multiple of 128 up to 2048, tensor-core backend)",
+              d_model, d_ff);
+  return ffn_fwd_fused(static_cast<const __half*>(y16), y, static_cast<const __half*>(w1_h), b1,
+                       static_cast<const __half*>(w2_h), b2, gamma, beta, out, u2, stats, static_cast<__half*>(h_out),
+                       n_tokens, d_model, d_ff, ln_eps, static_cast<cudaStream_t>(stream), TAG_FFN_FUSED);
+}
+
+int rlt_ffn_fused_set_timeline(long long* device_buffer) {
+  ffn_fwd_set_timeline(device_buffer);
+  return RLT_OK;
+}
+
 size_t rlt_encoder_layer_saved_bytes(const rlt_encoder_desc* e) {
   if (check_desc(e) != RLT_OK) return 0;
   return saved_layout(*e).total * sizeof(float);
@@ -695,6 +713,19 @@ int rlt_encoder_layer_fwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
                          h16 ? y16 : nullptr));
   __half* w1h = w1th + size_t(d) * f;
   __half* w2th = w1h + size_t(d) * f;
+  if (h16 && drop.thr == 0 && ffn_fwd_fused_ok(d, f)) {
+    // the whole feed-forward block + LayerNorm2 in one kernel (ffn_fwd_fused.cuh): the hidden stays on chip; in
+    // training it is written once for the backward, which also needs the transposed fp16 weight copies
+    const bool keep = e->inference == 0;
+    RLT_TRY(convert_f16(w->lin1_w, w1h, size_t(d) * f, nullptr, stream));
+    RLT_TRY(convert_f16(w->lin2_w, w2h, size_t(d) * f, nullptr, stream));
+    if (keep) {
+      RLT_TRY(transpose_f16(w->lin2_w, w2th, d, f, stream));                   // [d, f] -> [f, d] (backward dH)
+      RLT_TRY(transpose_f16(w->lin1_w, w1th, f, d, stream));                   // [f, d] -> [d, f] (backward dY)
+    }
+    return ffn_fwd_fused(y16, sv + sl.y, w1h, w->lin1_b, w2h, w->lin2_b, w->norm2_w, w->norm2_b, out, keep ? sv + sl.u2 : nullptr,
+                         keep ? sv + sl.st2 : nullptr, keep ? hh : nullptr, T, d, f, e->ln_eps, stream, TAG_FFN_FUSED);
+  }
   // h = relu(y W1^T + b1)
   ep = EpiParams{}; ep.alpha = 1.f; ep.ldo = f; ep.bias = w->lin1_b; ep.relu = 1; ep.tag = TAG_FFN1;
   ep.drop = drop; ep.drop_site = DROP_FFN;       // the stored hidden is the DROPPED one (its sign pattern gates the backward)

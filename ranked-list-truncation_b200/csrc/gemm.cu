@@ -14,6 +14,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_f16out.cuh"
 #include "ffn_bwd_fused.cuh"
+#include "ffn_fwd_fused.cuh"
 
 namespace rlt {
 
@@ -42,6 +43,7 @@ static int g_gemm_backend = env_int("RLT_GEMM_BACKEND", 0);
 static int g_tma_round = env_int("RLT_TMA_ROUND", 1);
 static int g_b_resident = env_int("RLT_B_RESIDENT", 1);
 static int g_ffn_bwd_fused = env_int("RLT_FFN_BWD_FUSED", 1);   // one-pass dH / dW2 / db1 kernel (d_model 128)
+static int g_ffn_fwd_fused = env_int("RLT_FFN_FWD_FUSED", 1);   // fused FFN1 + ReLU + FFN2 + residual + LayerNorm2 (cta_group::2)
 static int g_dw_colsum = env_int("RLT_DW_COLSUM", 1);         // bias-gradient column sums as an extra MMA of the weight-gradient GEMM
 static int g_f16out_tma = env_int("RLT_F16OUT_TMA", 1);     // copy-engine epilogue kernel for the fp16-output GEMMs   // gemm_tn: keep the CTA's B slice in shared memory when it fits
 
@@ -444,6 +446,57 @@ int ffn_bwd_fused(const __half* du16, const __half* w2th, const __half* hh, __ha
   return RLT_OK;
 }
 
+static long long* g_ffn_dbg = nullptr;      // device buffer for the kernel's timeline (rlt_ffn_fused_set_timeline; tools only)
+void ffn_fwd_set_timeline(long long* dev_buf) { g_ffn_dbg = dev_buf; }
+// Fused FFN forward (ffn_fwd_fused.cuh): out = LN2(y + relu(y W1^T + b1) W2^T + b2), hidden on chip.
+bool ffn_fwd_fused_ok(int d, int f) {
+  return g_ffn_fwd_fused != 0 && gemm_backend() == 0 && d == 128 && f % FfnFwdCfg<128>::CH == 0 && f <= FfnFwdCfg<128>::MAX_F;
+}
+int ffn_fwd_fused(const __half* y16, const float* y, const __half* w1h, const float* b1, const __half* w2h, const float* b2,
+                  const float* gamma, const float* beta, float* out, float* u2, float* stats, __half* h_out, int T, int d,
+                  int f, float eps, cudaStream_t stream, int tag) {
+  RLT_REQUIRE(ffn_fwd_fused_ok(d, f), RLT_UNSUPPORTED_SHAPE, "ffn_fwd_fused: d=%d f=%d unsupported", d, f);
+  using Cfg = FfnFwdCfg<128>;
+  CUtensorMap tmY, tmW1, tmW2, tmH;
+  RLT_TRY(make_tmap_h(&tmY, y16, T, d, d, Cfg::BM));
+  tmH = tmY;       // placeholder when the hidden is not saved (never dereferenced then)
+  if (h_out != nullptr)
+    RLT_TRY(make_tmap_any(&tmH, h_out, 2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, T, f, f, 32, false, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  RLT_TRY(make_tmap_h(&tmW1, w1h, f, d, d, Cfg::CH / 2));
+  RLT_TRY(make_tmap_h(&tmW2, w2h, d, f, f, d / 2));
+  static DeviceOnce once;
+  if (once.first()) {
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
+    // how many CTA pairs the device can hold at once (a GPC with an odd number of free SMs leaves one unpaired)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(num_sms() / 2 * 2));
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, ffn_fwd_kernel<128>, &cfg) != cudaSuccess || n_clusters < 1) {
+      (void)cudaGetLastError();
+      n_clusters = num_sms() / 2;
+    }
+    once.value[once.dev()] = n_clusters;
+  }
+  const int n_tiles = (T + 2 * Cfg::BM - 1) / (2 * Cfg::BM);
+  int pairs = once.value[once.dev()];
+  if (pairs > n_tiles) pairs = n_tiles;
+  FfnFwdParams prm;
+  prm.y = y; prm.b1 = b1; prm.b2 = b2; prm.gamma = gamma; prm.beta = beta; prm.out = out; prm.u2 = u2; prm.stats = stats;
+  prm.h_out = h_out; prm.T = T; prm.F = f; prm.eps = eps;
+  prm.dbg = g_ffn_dbg;
+  TimeScope scope(tag, stream);
+  ffn_fwd_kernel<128><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmY, tmW1, tmW2, tmH, prm);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+
 int gemm_dw_h(const __half* A, int lda, const __half* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,
               const float* alpha_ptr, cudaStream_t stream, int tag) {
   TimeScope scope(tag, stream);
@@ -694,6 +747,7 @@ int rlt_set_option(const char* key, int value) {
   if (strcmp(key, "b_resident") == 0) { g_b_resident = value; return RLT_OK; }
   if (strcmp(key, "f16out_tma") == 0) { g_f16out_tma = value; return RLT_OK; }
   if (strcmp(key, "ffn_bwd_fused") == 0) { g_ffn_bwd_fused = value; return RLT_OK; }
+  if (strcmp(key, "ffn_fwd_fused") == 0) { g_ffn_fwd_fused = value; return RLT_OK; }
   if (strcmp(key, "dw_colsum") == 0) { g_dw_colsum = value; return RLT_OK; }
   return set_error(RLT_INVALID_ARG, "rlt_set_option: unknown option '%s'", key);
 }
@@ -704,6 +758,7 @@ int rlt_get_option(const char* key) {
   if (strcmp(key, "b_resident") == 0) return g_b_resident;
   if (strcmp(key, "f16out_tma") == 0) return g_f16out_tma;
   if (strcmp(key, "ffn_bwd_fused") == 0) return g_ffn_bwd_fused;
+  if (strcmp(key, "ffn_fwd_fused") == 0) return g_ffn_fwd_fused;
   if (strcmp(key, "dw_colsum") == 0) return g_dw_colsum;
   if (strcmp(key, "time_tag") == 0) return g_time_tag;
   if (strcmp(key, "lstm_backend") == 0) return lstm_backend();

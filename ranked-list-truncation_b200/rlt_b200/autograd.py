@@ -68,10 +68,11 @@ class EncoderStack(torch.autograd.Function):
         if B % n_groups:
             raise RuntimeError(f"batch of {B} lists is not divisible into {n_groups} attention groups")
         dropout_p = float(dropout_p)
-        descs = [ops.encoder_desc(n_groups, B // n_groups, L, d, n_head, d_ff, ln_eps, dropout_p,
-                                  fresh_seed() if dropout_p > 0 else 0) for _ in range(n_layers)]   # one mask set per layer
-        desc = descs[0]
         need_grad = any(ctx.needs_input_grad)
+        descs = [ops.encoder_desc(n_groups, B // n_groups, L, d, n_head, d_ff, ln_eps, dropout_p,
+                                  fresh_seed() if dropout_p > 0 else 0, inference=not need_grad)
+                 for _ in range(n_layers)]   # one mask set per layer
+        desc = descs[0]
         saved_bytes = ops.encoder_saved_bytes(desc)
         if saved_bytes == 0:
             raise ops._lib.RltError("encoder: " + ops._lib.load().rlt_last_error().decode())

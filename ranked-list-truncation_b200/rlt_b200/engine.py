@@ -35,6 +35,8 @@ class _EncStack:
         self.n_head = l0.self_attn.num_heads
         self.desc = ops.encoder_desc(eng.G, eng.S, eng.L, self.d, l0.self_attn.num_heads, l0.linear1.out_features,
                                      l0.norm1.eps)
+        self.desc_infer = ops.encoder_desc(eng.G, eng.S, eng.L, self.d, l0.self_attn.num_heads, l0.linear1.out_features,
+                                           l0.norm1.eps, inference=True)
         self.desc_first = ops.encoder_desc(eng.G, eng.S, eng.L, self.d, l0.self_attn.num_heads,
                                            l0.linear1.out_features, l0.norm1.eps, accumulate_dx=accumulate_dx)
         layers = _enc_layers(enc)
@@ -60,10 +62,11 @@ class _EncStack:
         p_saved = self.p
         if not train:
             self.p = 0.0
+        desc = self.desc if train else self.desc_infer      # forward only: nothing is kept, the FFN hidden stays on chip
         for i in range(self.n):
             self.seeds[i] = fresh_seed() if self.p > 0 else 0
-            self._set_drop(self.desc, i)
-            ops.encoder_layer_fwd(self.desc, self.w[i], cur, self.outs[i], self.saved[i if self.training else 0])
+            self._set_drop(desc, i)
+            ops.encoder_layer_fwd(desc, self.w[i], cur, self.outs[i], self.saved[i if self.training else 0])
             cur = self.outs[i]
         self.p = p_saved
         return cur

@@ -24,7 +24,8 @@ LOSS_KINDS = {"choopy": 0, "raml": 1, "kl": 2, "js": 3}
 class EncoderDesc(C.Structure):
     _fields_ = [("n_groups", C.c_int32), ("group_size", C.c_int32), ("seq_len", C.c_int32), ("d_model", C.c_int32),
                 ("n_head", C.c_int32), ("d_ff", C.c_int32), ("attend_axis", C.c_int32), ("accumulate_dx", C.c_int32),
-                ("ln_eps", C.c_float), ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64)]
+                ("ln_eps", C.c_float), ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("inference", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 ENCODER_PARAM_ORDER = ("self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight",
@@ -99,9 +100,9 @@ def ensure_tables():
 # encoder layer
 # ----------------------------------------------------------------------------------------------
 def encoder_desc(n_groups, group_size, seq_len, d_model, n_head, d_ff=2048, ln_eps=1e-5, dropout_p=0.0, seed=0,
-                 accumulate_dx=False):
+                 accumulate_dx=False, inference=False):
     return EncoderDesc(n_groups, group_size, seq_len, d_model, n_head, d_ff, 0, int(accumulate_dx), ln_eps, dropout_p,
-                       seed)
+                       seed, int(inference), 0)
 
 
 def encoder_ptrs(tensors) -> EncoderPtrs:
@@ -131,6 +132,15 @@ def encoder_layer_bwd(desc, weights, grads, x, saved, d_out, d_x, workspace):
                                       ptr(d_x), ptr(workspace),
                                       C.c_size_t(workspace.numel() * workspace.element_size()), stream_ptr()),
           "rlt_encoder_layer_bwd")
+
+
+def ffn_fused_fwd(y16, y, w1_h, b1, w2_h, b2, gamma, beta, out, u2=None, stats=None, h_out=None, eps=1e-5):
+    """out = LayerNorm(y + relu(y W1^T + b1) W2^T + b2) in one kernel (rlt_ffn_fused_fwd).  y16 / w1_h / w2_h: fp16."""
+    T, d = y.shape
+    f = w1_h.shape[0]
+    check(lib().rlt_ffn_fused_fwd(ptr(y16), ptr(y), ptr(w1_h), ptr(b1), ptr(w2_h), ptr(b2), ptr(gamma), ptr(beta), ptr(out),
+                                  ptr(u2), ptr(stats), ptr(h_out), int(T), int(d), int(f), C.c_float(eps), stream_ptr()),
+          "rlt_ffn_fused_fwd")
 
 
 # ----------------------------------------------------------------------------------------------

@@ -138,3 +138,45 @@ def test_fused_backward_paths_match_unfused(S, L, G):
         e = (a - b).abs().max().item()
         tol = 5e-4 if n == "self_attn.in_proj_bias" else 2e-5      # in_proj_bias: exact fp32 sums vs a TF32-operand product
         assert e <= tol * scale, (n, e, scale)
+
+
+@pytest.mark.parametrize("S,L,G", [(5, 40, 1), (64, 20, 2), (63, 9, 1), (16, 300, 1), (64, 300, 3), (1, 1, 1), (3, 171, 1)])
+def test_fused_ffn_forward_matches_the_three_kernel_path(S, L, G):
+    """ffn_fwd_kernel (FFN1 + ReLU + FFN2 + residual + LayerNorm2 in one cta_group::2 kernel, hidden in tensor memory)
+    against the path it replaces (FFN1 GEMM -> fp16 hidden in HBM -> FFN2 GEMM -> LayerNorm kernel): same fp16
+    operands, fp32 accumulation in tensor memory, only the summation order of the LayerNorm statistics differs.
+    Token counts include partial 256-token tiles, a single token, and several tiles per CTA pair; the saved hidden /
+    pre-norm sum / statistics are checked through the (unchanged) backward."""
+    from rlt_b200 import _lib, ops
+    from rlt_b200.autograd import EncoderStack
+    d, n_head = 128, 8
+    sd = _layer_sd(d, n_head, seed=3)
+    torch.manual_seed(11 + S)
+    x = torch.randn(G * S, L, d)
+    dy = torch.randn(G * S, L, d) * 0.01
+
+    def run(fused, grad=True):
+        _lib.set_option("ffn_fwd_fused", fused)
+        try:
+            params = [sd[n].cuda().requires_grad_(grad) for n in ops.ENCODER_PARAM_ORDER]
+            xc = x.cuda().requires_grad_(grad)
+            out = EncoderStack.apply(xc, n_head, G, 1e-5, 0.0, *params)
+            if not grad:
+                return [out.detach().double().cpu()]
+            (out * dy.cuda()).sum().backward()
+            return [out.detach().double().cpu()] + [p.grad.double().cpu() for p in params] + [xc.grad.double().cpu()]
+        finally:
+            _lib.set_option("ffn_fwd_fused", 1)
+
+    ref = run(0)
+    new = run(1)
+    names = ["out"] + list(ops.ENCODER_PARAM_ORDER) + ["dx"]
+    for n, a, b in zip(names, ref, new):
+        scale = a.abs().max().item() + 1e-30
+        e = (a - b).abs().max().item()
+        # the output itself at fp32 rounding; the gradients pass through TF32 / fp16 operand rounding downstream, where a
+        # last-bit difference of an activation can move an operand by one TF32 ulp (2^-11)
+        assert e <= (2e-5 if n == "out" else 5e-4) * scale, (n, e, scale)
+    # forward only (torch.no_grad / eval): the hidden is not written at all, the output is the same
+    inf = run(1, grad=False)[0]
+    assert (inf - new[0]).abs().max().item() <= 1e-6 * new[0].abs().max().item()
