@@ -168,10 +168,10 @@ typedef struct rlt_encoder_weights {
 } rlt_encoder_weights;
 
 /* The feed-forward block of one encoder layer as ONE kernel (csrc/ffn_fwd_fused.cuh; what rlt_encoder_layer_fwd runs for
- * d_model 128 without dropout): out = LayerNorm(y + relu(y W1^T + b1) W2^T + b2), torch TransformerEncoderLayer._ff_block
+ * d_model 128 / 256 without dropout): out = LayerNorm(y + relu(y W1^T + b1) W2^T + b2), torch TransformerEncoderLayer._ff_block
  * + norm2 (models/Choopy.py:11 etc., dim_feedforward 2048).  y16 / w1_h / w2_h: fp16 copies of y [T, d], linear1.weight
  * [d_ff, d] and linear2.weight [d, d_ff] (row-major); y: the fp32 residual.  Optional outputs (NULL = forward only):
- * u2 [T, d] pre-norm sum, stats [T, 2] (mean, rstd), h_out [T, d_ff] fp16 hidden.  d must be 128, d_ff % 128 == 0,
+ * u2 [T, d] pre-norm sum, stats [T, 2] (mean, rstd), h_out [T, d_ff] fp16 hidden.  d must be 128 or 256, d_ff % 128 == 0,
  * d_ff <= 2048; RLT_UNSUPPORTED_SHAPE otherwise. */
 /* Tools only: device buffer of 64 x 16 int64 that the next rlt_ffn_fused_fwd launches fill with clock64 stamps of the first
  * CTA pair's MMA thread and first epilogue warp (NULL switches the timeline off, the default). */

@@ -654,7 +654,7 @@ int rlt_ffn_fused_fwd(const void* y16, const float* y, const void* w1_h, const f
   RLT_REQUIRE(y16 && y && w1_h && b1 && w2_h && b2 && gamma && beta && out && n_tokens > 0, RLT_INVALID_ARG,
               "rlt_ffn_fused_fwd: null pointer or empty problem");
   RLT_REQUIRE(ffn_fwd_fused_ok(d_model, d_ff), RLT_UNSUPPORTED_SHAPE,
-              "rlt_ffn_fused_fwd: d_model=%d d_ff=%d (needs d_model 128, d_ff a multiple of 128 up to 2048, tensor-core backend)",
+              "rlt_ffn_fused_fwd: d_model=%d d_ff=%d (needs d_model 128 or 256, d_ff a multiple of 128 up to 2048, tensor-core backend)",
               d_model, d_ff);
   return ffn_fwd_fused(static_cast<const __half*>(y16), y, static_cast<const __half*>(w1_h), b1,
                        static_cast<const __half*>(w2_h), b2, gamma, beta, out, u2, stats, static_cast<__half*>(h_out),

@@ -354,12 +354,17 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
           // training: the hidden is saved -- written once by the copy engine (per-warp staging tile -> TMA store; per-thread
           // global stores of 32 rows 4 KB apart cost the LSU one cycle per row and instruction: measured +1 ms per launch);
           // rows beyond T are clipped by the tensor map
-          static_assert(SC == 32, "the staging tile is [32 rows x 32 columns]");
           if (lane == 0) tma_store_wait_read<0>();             // the previous store of this warp has drained its staging tile
           __syncwarp();
+          if constexpr (SC == 32) {            // [32 rows x 32 columns] fp16, 64-byte rows, SWIZZLE_64B
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            *reinterpret_cast<uint4*>(st_out + lane * 64 + ((q4 ^ sw) << 4)) = make_uint4(hp[4 * q4], hp[4 * q4 + 1], hp[4 * q4 + 2], hp[4 * q4 + 3]);
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<uint4*>(st_out + lane * 64 + ((q4 ^ sw) << 4)) = make_uint4(hp[4 * q4], hp[4 * q4 + 1], hp[4 * q4 + 2], hp[4 * q4 + 3]);
+          } else {                             // [32 rows x 16 columns] fp16, 32-byte rows, no swizzle
+#pragma unroll
+            for (int q4 = 0; q4 < 2; ++q4)
+              *reinterpret_cast<uint4*>(st_out + lane * 32 + (q4 << 4)) = make_uint4(hp[4 * q4], hp[4 * q4 + 1], hp[4 * q4 + 2], hp[4 * q4 + 3]);
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -390,54 +395,31 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       // cycles per tile for residual + out, a third of the kernel); instead global memory is accessed with 8 rows x 64
       // contiguous bytes per instruction and the block is turned between the two layouts through the warp's 2 KB staging
       // tile, 16 columns at a time.
-      static_assert(ZC == 32, "Z epilogue: 32 columns per warp");
+      // d = 256: a warp owns 64 columns = two such blocks; the pre-norm sums go back to tensor memory (the Z columns are
+      // free once read) instead of staying in 64 registers.
+      constexpr int NB = ZC / 32;
       const long long row_base = (long long)tile * 2 * Cfg::BM + (long long)rank * Cfg::BM + quarter * 32;
       const int crow = lane >> 2, cu = lane & 3;                   // coalesced side: row 8 i + crow, 16-byte unit cu
-      float4 rq[2][4];
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {                              // issued before waiting for the last MMA2
-          const long long rg = row_base + 8 * i + crow;
-          rq[h][i] = rg < p.T ? __ldg(reinterpret_cast<const float4*>(p.y + size_t(rg) * D + cq * ZC + 16 * h + 4 * cu))
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      mbar_wait(z_full, tt & 1);
-      tc_fence_after();
-      float uv[ZC];
-      tmem_ld32(lane_tmem + Cfg::COL_Z + cq * ZC, uv);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_cluster(z_empty_r);                            // Z is in registers: the next tile may accumulate
-        tma_store_wait_read<0>();                                  // (training) the last hidden store has left the staging tile
-      }
-      __syncwarp();
-      // coalesced-side / row-side addresses inside the staging tile (64-byte rows, 16-byte units XOR-swizzled)
+      // coalesced-side addresses inside the staging tile (64-byte rows, 16-byte units XOR-swizzled)
       uint32_t c_off[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int rr = 8 * i + crow;
         c_off[i] = uint32_t(rr * 64 + ((cu ^ ((rr >> 1) & 3)) << 4));
       }
-      float s = 0.f;
+      float4 rq[2][4];
+      auto load_residual = [&](int zb) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(st_out + c_off[i]) = rq[h][i];
-        __syncwarp();
-#pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(st_out + lane * 64 + ((u4 ^ sw) << 4));
-          const float* b2v = sVec + cq * ZC + 16 * h + 4 * u4;
-          float* dstv = uv + 16 * h + 4 * u4;
-          dstv[0] += b2v[0] + t4.x; dstv[1] += b2v[1] + t4.y; dstv[2] += b2v[2] + t4.z; dstv[3] += b2v[3] + t4.w;
-          s += (dstv[0] + dstv[1]) + (dstv[2] + dstv[3]);
-        }
-        __syncwarp();
-      }
+          for (int i = 0; i < 4; ++i) {
+            const long long rg = row_base + 8 * i + crow;
+            rq[h][i] = rg < p.T ? __ldg(reinterpret_cast<const float4*>(p.y + size_t(rg) * D + cq * ZC + 32 * zb + 16 * h + 4 * cu))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+      };
       // a [32 x 32] block of this warp from registers (thread = row) to global memory through the staging tile
-      auto store_block = [&](float* gbase, const float (&val)[ZC]) {
+      auto store_block = [&](float* gbase, const float (&val)[32], int zb) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -449,32 +431,81 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
           for (int i = 0; i < 4; ++i) {
             const long long rg = row_base + 8 * i + crow;
             const float4 t4 = *reinterpret_cast<const float4*>(st_out + c_off[i]);
-            if (rg < p.T) *reinterpret_cast<float4*>(gbase + size_t(rg) * D + cq * ZC + 16 * h + 4 * cu) = t4;
+            if (rg < p.T) *reinterpret_cast<float4*>(gbase + size_t(rg) * D + cq * ZC + 32 * zb + 16 * h + 4 * cu) = t4;
           }
           __syncwarp();
         }
       };
-      if (p.u2 != nullptr) store_block(p.u2, uv);
+      load_residual(0);                                            // issued before waiting for the last MMA2
+      mbar_wait(z_full, tt & 1);
+      tc_fence_after();
+      float uv[32];
+      float s = 0.f;
+#pragma unroll
+      for (int zb = 0; zb < NB; ++zb) {
+        if (zb > 0) load_residual(zb);
+        tmem_ld32(lane_tmem + Cfg::COL_Z + cq * ZC + 32 * zb, uv);
+        if (zb == 0) {
+          if constexpr (NB == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(z_empty_r);         // Z is in registers: the next tile may accumulate
+          }
+          if (lane == 0) tma_store_wait_read<0>();                 // (training) the last hidden store has left the staging tile
+          __syncwarp();
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(st_out + c_off[i]) = rq[h][i];
+          __syncwarp();
+#pragma unroll
+          for (int u4 = 0; u4 < 4; ++u4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(st_out + lane * 64 + ((u4 ^ sw) << 4));
+            const float* b2v = sVec + cq * ZC + 32 * zb + 16 * h + 4 * u4;
+            float* dstv = uv + 16 * h + 4 * u4;
+            dstv[0] += b2v[0] + t4.x; dstv[1] += b2v[1] + t4.y; dstv[2] += b2v[2] + t4.z; dstv[3] += b2v[3] + t4.w;
+            s += (dstv[0] + dstv[1]) + (dstv[2] + dstv[3]);
+          }
+          __syncwarp();
+        }
+        if (p.u2 != nullptr) store_block(p.u2, uv, zb);
+        if constexpr (NB > 1) tmem_st32f(lane_tmem + Cfg::COL_Z + cq * ZC + 32 * zb, uv);
+      }
+      if constexpr (NB > 1) tmem_st_wait();
       // row statistics across the four column quarters (warps quarter, quarter + 4, ...): two-pass like torch
       red0[cq * 32 + lane] = s;
       asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
       const float mu = (red0[lane] + red0[32 + lane] + red0[64 + lane] + red0[96 + lane]) * (1.f / D);
       float q = 0.f;
 #pragma unroll
-      for (int c = 0; c < ZC; ++c) {
-        uv[c] -= mu;
-        q += uv[c] * uv[c];
+      for (int zb = 0; zb < NB; ++zb) {
+        if constexpr (NB > 1) tmem_ld32(lane_tmem + Cfg::COL_Z + cq * ZC + 32 * zb, uv);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float dlt = uv[c] - mu;
+          q += dlt * dlt;
+        }
       }
       red1[cq * 32 + lane] = q;
       asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
       const float rstd = rsqrtf((red1[lane] + red1[32 + lane] + red1[64 + lane] + red1[96 + lane]) * (1.f / D) + p.eps);
-      {
-        const float* gm = sVec + D + cq * ZC;
-        const float* bt = sVec + 2 * D + cq * ZC;
 #pragma unroll
-        for (int c = 0; c < ZC; ++c) uv[c] = uv[c] * rstd * gm[c] + bt[c];
+      for (int zb = 0; zb < NB; ++zb) {
+        if constexpr (NB > 1) tmem_ld32(lane_tmem + Cfg::COL_Z + cq * ZC + 32 * zb, uv);
+        const float* gm = sVec + D + cq * ZC + 32 * zb;
+        const float* bt = sVec + 2 * D + cq * ZC + 32 * zb;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) uv[c] = (uv[c] - mu) * rstd * gm[c] + bt[c];
+        if constexpr (NB > 1) {
+          if (zb == NB - 1) {                                      // the scratch use of the Z columns is over
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(z_empty_r);
+          }
+        }
+        store_block(p.out, uv, zb);
       }
-      store_block(p.out, uv);
       if (p.stats != nullptr && cq == 0 && live) {
         p.stats[2 * size_t(row)] = mu;
         p.stats[2 * size_t(row) + 1] = rstd;

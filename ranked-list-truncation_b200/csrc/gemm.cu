@@ -450,23 +450,24 @@ static long long* g_ffn_dbg = nullptr;      // device buffer for the kernel's ti
 void ffn_fwd_set_timeline(long long* dev_buf) { g_ffn_dbg = dev_buf; }
 // Fused FFN forward (ffn_fwd_fused.cuh): out = LN2(y + relu(y W1^T + b1) W2^T + b2), hidden on chip.
 bool ffn_fwd_fused_ok(int d, int f) {
-  return g_ffn_fwd_fused != 0 && gemm_backend() == 0 && d == 128 && f % FfnFwdCfg<128>::CH == 0 && f <= FfnFwdCfg<128>::MAX_F;
+  return g_ffn_fwd_fused != 0 && gemm_backend() == 0 && (d == 128 || d == 256) && f % 128 == 0 && f <= FfnFwdCfg<128>::MAX_F;
 }
-int ffn_fwd_fused(const __half* y16, const float* y, const __half* w1h, const float* b1, const __half* w2h, const float* b2,
-                  const float* gamma, const float* beta, float* out, float* u2, float* stats, __half* h_out, int T, int d,
-                  int f, float eps, cudaStream_t stream, int tag) {
-  RLT_REQUIRE(ffn_fwd_fused_ok(d, f), RLT_UNSUPPORTED_SHAPE, "ffn_fwd_fused: d=%d f=%d unsupported", d, f);
-  using Cfg = FfnFwdCfg<128>;
+template <int D>
+static int ffn_fwd_fused_launch(const __half* y16, const float* y, const __half* w1h, const float* b1, const __half* w2h,
+                                const float* b2, const float* gamma, const float* beta, float* out, float* u2, float* stats,
+                                __half* h_out, int T, int f, float eps, cudaStream_t stream, int tag) {
+  using Cfg = FfnFwdCfg<D>;
   CUtensorMap tmY, tmW1, tmW2, tmH;
-  RLT_TRY(make_tmap_h(&tmY, y16, T, d, d, Cfg::BM));
+  RLT_TRY(make_tmap_h(&tmY, y16, T, D, D, Cfg::BM));
+  RLT_TRY(make_tmap_h(&tmW1, w1h, f, D, D, Cfg::CH / 2));
+  RLT_TRY(make_tmap_h(&tmW2, w2h, D, f, f, D / 2));
   tmH = tmY;       // placeholder when the hidden is not saved (never dereferenced then)
-  if (h_out != nullptr)
-    RLT_TRY(make_tmap_any(&tmH, h_out, 2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, T, f, f, 32, false, 32, CU_TENSOR_MAP_SWIZZLE_64B));
-  RLT_TRY(make_tmap_h(&tmW1, w1h, f, d, d, Cfg::CH / 2));
-  RLT_TRY(make_tmap_h(&tmW2, w2h, d, f, f, d / 2));
+  if (h_out != nullptr)      // per-warp [32 rows x CH/4 columns] fp16 tiles: 64-byte rows swizzled, 32-byte rows plain
+    RLT_TRY(make_tmap_any(&tmH, h_out, 2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, T, f, f, 32, false, Cfg::CH / 4,
+                          Cfg::CH / 4 == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE));
   static DeviceOnce once;
   if (once.first()) {
-    RLT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
     // how many CTA pairs the device can hold at once (a GPC with an odd number of free SMs leaves one unpaired)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(num_sms() / 2 * 2));
@@ -478,7 +479,7 @@ int ffn_fwd_fused(const __half* y16, const float* y, const __half* w1h, const fl
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int n_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&n_clusters, ffn_fwd_kernel<128>, &cfg) != cudaSuccess || n_clusters < 1) {
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, ffn_fwd_kernel<D>, &cfg) != cudaSuccess || n_clusters < 1) {
       (void)cudaGetLastError();
       n_clusters = num_sms() / 2;
     }
@@ -492,9 +493,17 @@ int ffn_fwd_fused(const __half* y16, const float* y, const __half* w1h, const fl
   prm.h_out = h_out; prm.T = T; prm.F = f; prm.eps = eps;
   prm.dbg = g_ffn_dbg;
   TimeScope scope(tag, stream);
-  ffn_fwd_kernel<128><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmY, tmW1, tmW2, tmH, prm);
+  ffn_fwd_kernel<D><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmY, tmW1, tmW2, tmH, prm);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
+}
+int ffn_fwd_fused(const __half* y16, const float* y, const __half* w1h, const float* b1, const __half* w2h, const float* b2,
+                  const float* gamma, const float* beta, float* out, float* u2, float* stats, __half* h_out, int T, int d,
+                  int f, float eps, cudaStream_t stream, int tag) {
+  RLT_REQUIRE(ffn_fwd_fused_ok(d, f), RLT_UNSUPPORTED_SHAPE, "ffn_fwd_fused: d=%d f=%d unsupported", d, f);
+  if (d == 128)
+    return ffn_fwd_fused_launch<128>(y16, y, w1h, b1, w2h, b2, gamma, beta, out, u2, stats, h_out, T, f, eps, stream, tag);
+  return ffn_fwd_fused_launch<256>(y16, y, w1h, b1, w2h, b2, gamma, beta, out, u2, stats, h_out, T, f, eps, stream, tag);
 }
 
 int gemm_dw_h(const __half* A, int lda, const __half* B, int ldb, int T, int M, int N, float* C, int ldc, float alpha,

@@ -140,8 +140,9 @@ def test_fused_backward_paths_match_unfused(S, L, G):
         assert e <= tol * scale, (n, e, scale)
 
 
+@pytest.mark.parametrize("d,n_head", [(128, 8), (256, 4)])
 @pytest.mark.parametrize("S,L,G", [(5, 40, 1), (64, 20, 2), (63, 9, 1), (16, 300, 1), (64, 300, 3), (1, 1, 1), (3, 171, 1)])
-def test_fused_ffn_forward_matches_the_three_kernel_path(S, L, G):
+def test_fused_ffn_forward_matches_the_three_kernel_path(S, L, G, d, n_head):
     """ffn_fwd_kernel (FFN1 + ReLU + FFN2 + residual + LayerNorm2 in one cta_group::2 kernel, hidden in tensor memory)
     against the path it replaces (FFN1 GEMM -> fp16 hidden in HBM -> FFN2 GEMM -> LayerNorm kernel): same fp16
     operands, fp32 accumulation in tensor memory, only the summation order of the LayerNorm statistics differs.
@@ -149,7 +150,6 @@ def test_fused_ffn_forward_matches_the_three_kernel_path(S, L, G):
     pre-norm sum / statistics are checked through the (unchanged) backward."""
     from rlt_b200 import _lib, ops
     from rlt_b200.autograd import EncoderStack
-    d, n_head = 128, 8
     sd = _layer_sd(d, n_head, seed=3)
     torch.manual_seed(11 + S)
     x = torch.randn(G * S, L, d)

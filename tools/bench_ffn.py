@@ -13,7 +13,7 @@ from rlt_b200 import ops  # noqa: E402
 
 def main():
     T = int(sys.argv[1]) if len(sys.argv) > 1 else 4096 * 300
-    d, f = 128, 2048
+    d, f = (int(sys.argv[2]) if len(sys.argv) > 2 else 128), 2048
     pk = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm, tfs = pk.get("hbm_gbs", 6650.0), pk.get("bf16_tflops_sustained", 1400.0)
     g = torch.Generator(device="cuda").manual_seed(1)
