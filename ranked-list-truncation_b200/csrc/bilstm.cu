@@ -222,6 +222,15 @@ static LstmSaved lstm_saved(const rlt_bilstm_desc& d) {
   return s;
 }
 // workspace (floats): P / dA [T, 1024] | dY0 [T, 256] | WT [4][128*512] | bias scratch [1024]
+// lists per CTA of the tcgen05 recurrence: 32 while 2 * ceil(B / 32) CTAs still fit in one wave, else 64
+static int g_lstm_tile = 0;          // 0 = automatic (rlt_set_option("lstm_tile", 32 | 64) pins it: A/B measurements, tests)
+void set_lstm_tile(int v) { g_lstm_tile = (v == 32 || v == 64) ? v : 0; }
+int get_lstm_tile() { return g_lstm_tile; }
+static int lstm_tile(int B) {
+  if (g_lstm_tile != 0) return g_lstm_tile;
+  return 2 * ((B + 31) / 32) <= num_sms() ? 32 : 64;
+}
+
 static size_t lstm_ws_floats(const rlt_bilstm_desc& d) {
   const size_t T = size_t(d.n_lists) * d.seq_len;
   return T * 2 * G4 + T * 2 * H + 4 * size_t(H) * G4 + 2 * G4 + 256;
@@ -319,22 +328,23 @@ int rlt_bilstm_fwd(const rlt_bilstm_desc* d, const rlt_bilstm_weights* w, const 
     if (tc) {
       static DeviceOnce attr;
       if (attr.first()) {
-        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            int(LstmUmFwdSmem::TOTAL)));
-        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            int(LstmUmFwdSmem::TOTAL)));
+        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_fwd_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LstmUmFwdSmem<64>::TOTAL)));
+        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_fwd_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LstmUmFwdSmem<64>::TOTAL)));
+        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_fwd_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LstmUmFwdSmem<32>::TOTAL)));
+        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_fwd_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LstmUmFwdSmem<32>::TOTAL)));
       }
       LstmInProj inp{};
-      const dim3 grid((B + U_TILE - 1) / U_TILE, 2);
       if (fused_in) {
         inp.x = x; inp.F = F;
         for (int dir = 0; dir < 2; ++dir) { inp.w_ih[dir] = w->w_ih[0][dir]; inp.b_ih[dir] = w->b_ih[0][dir]; inp.b_hh[dir] = w->b_hh[0][dir]; }
-        lstm_um_fwd_kernel<true><<<grid, U_THREADS, LstmUmFwdSmem::TOTAL, stream>>>(nullptr, inp, w->w_hh[l][0], w->w_hh[l][1],
-                                                                                   out, sv, B, L);
-      } else {
-        lstm_um_fwd_kernel<false><<<grid, U_THREADS, LstmUmFwdSmem::TOTAL, stream>>>(P, inp, w->w_hh[l][0], w->w_hh[l][1], out,
-                                                                                    sv, B, L);
       }
+      const float* Pin = fused_in ? nullptr : P;
+#define RLT_LSTM_FWD(FUSED, TILE_)                                                                                       \
+  lstm_um_fwd_kernel<FUSED, TILE_><<<dim3((B + TILE_ - 1) / TILE_, 2), U_THREADS, LstmUmFwdSmem<TILE_>::TOTAL, stream>>>( \
+      Pin, inp, w->w_hh[l][0], w->w_hh[l][1], out, sv, B, L)
+      if (lstm_tile(B) == 32) { if (fused_in) RLT_LSTM_FWD(true, 32); else RLT_LSTM_FWD(false, 32); }
+      else { if (fused_in) RLT_LSTM_FWD(true, 64); else RLT_LSTM_FWD(false, 64); }
+#undef RLT_LSTM_FWD
     } else {
       lstm_rec_fwd_kernel<<<dim3(B, 2), H, 0, stream>>>(P, WT + (l * 2) * size_t(H) * G4, WT + (l * 2 + 1) * size_t(H) * G4,
                                                         out, sv, L);
@@ -373,11 +383,15 @@ int rlt_bilstm_bwd(const rlt_bilstm_desc* d, const rlt_bilstm_weights* w, const 
       RLT_CHECK_CUDA(cudaMemsetAsync(colsum_scratch, 0, 2 * G4 * sizeof(float), stream));
       static DeviceOnce attr;
       if (attr.first()) {
-        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            int(LstmUmBwdSmem::TOTAL)));
+        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LstmUmBwdSmem<64>::TOTAL)));
+        RLT_CHECK_CUDA(cudaFuncSetAttribute(lstm_um_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LstmUmBwdSmem<32>::TOTAL)));
       }
-      lstm_um_bwd_kernel<<<dim3((B + U_TILE - 1) / U_TILE, 2), U_THREADS, LstmUmBwdSmem::TOTAL, stream>>>(
-          dout, sv, w->w_hh[l][0], w->w_hh[l][1], scale, dA, colsum_scratch, B, L);
+      if (lstm_tile(B) == 32)
+        lstm_um_bwd_kernel<32><<<dim3((B + 31) / 32, 2), U_THREADS, LstmUmBwdSmem<32>::TOTAL, stream>>>(
+            dout, sv, w->w_hh[l][0], w->w_hh[l][1], scale, dA, colsum_scratch, B, L);
+      else
+        lstm_um_bwd_kernel<64><<<dim3((B + 63) / 64, 2), U_THREADS, LstmUmBwdSmem<64>::TOTAL, stream>>>(
+            dout, sv, w->w_hh[l][0], w->w_hh[l][1], scale, dA, colsum_scratch, B, L);
     } else {
       lstm_rec_bwd_kernel<<<dim3(B, 2), H, 0, stream>>>(dout, sv, w->w_hh[l][0], w->w_hh[l][1], dA, L);
     }

@@ -100,6 +100,8 @@ int pow2_scale(const unsigned int* amax_bits, float* scale, int target, cudaStre
 int gemm_backend();
 // 0 = persistent tcgen05 LSTM recurrence (default), 1 = plain validation kernels (also forced by gemm_backend 1)
 int lstm_backend();
+void set_lstm_tile(int v);
+int get_lstm_tile();
 void set_lstm_backend(int v);
 // true when the TMA tensor maps are encoded as TFLOAT32 (TMA rounds fp32->tf32 while loading), so
 // producers need not materialise rounded operand copies.

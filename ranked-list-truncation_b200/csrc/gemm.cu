@@ -751,6 +751,7 @@ int rlt_set_option(const char* key, int value) {
   if (key == nullptr) return set_error(RLT_INVALID_ARG, "rlt_set_option: null key");
   if (strcmp(key, "time_tag") == 0) { g_time_tag = value; return RLT_OK; }
   if (strcmp(key, "lstm_backend") == 0) { set_lstm_backend(value); return RLT_OK; }
+  if (strcmp(key, "lstm_tile") == 0) { set_lstm_tile(value); return RLT_OK; }
   if (strcmp(key, "gemm_backend") == 0) { g_gemm_backend = value; return RLT_OK; }
   if (strcmp(key, "tma_round") == 0) { g_tma_round = value; return RLT_OK; }
   if (strcmp(key, "b_resident") == 0) { g_b_resident = value; return RLT_OK; }
@@ -771,6 +772,7 @@ int rlt_get_option(const char* key) {
   if (strcmp(key, "dw_colsum") == 0) return g_dw_colsum;
   if (strcmp(key, "time_tag") == 0) return g_time_tag;
   if (strcmp(key, "lstm_backend") == 0) return lstm_backend();
+  if (strcmp(key, "lstm_tile") == 0) return get_lstm_tile();
   return set_error(RLT_INVALID_ARG, "rlt_get_option: unknown option '%s'", key);
 }
 
