@@ -167,6 +167,13 @@ typedef struct rlt_encoder_weights {
   const float* norm2_b;
 } rlt_encoder_weights;
 
+/* Cross-list multi-head attention core of one encoder layer, forward (what rlt_encoder_layer_fwd runs between the QKV
+ * projection and the output projection; torch functional.multi_head_attention_forward with the reference's layout, SURVEY
+ * section 0): qkv [G*S*L, 3d] (q | k | v, token = (g*S + s)*L + l), o [G*S*L, d], lse [G*S*L, n_head] (natural-log
+ * log-sum-exp of the scaled scores, may be NULL).  For every group g, position l and head h the S lists attend to each
+ * other.  Head dim 16 and S <= 64 run on tcgen05 (csrc/attention_tc.cuh), other shapes on the mma.sync / generic kernels. */
+int rlt_attention_lists_fwd(const float* qkv, float* o, float* lse, int n_groups, int group_size, int seq_len, int d_model,
+                            int n_head, rlt_stream_t stream);
 /* The feed-forward block of one encoder layer as ONE kernel (csrc/ffn_fwd_fused.cuh; what rlt_encoder_layer_fwd runs for
  * d_model 128 / 256 without dropout): out = LayerNorm(y + relu(y W1^T + b1) W2^T + b2), torch TransformerEncoderLayer._ff_block
  * + norm2 (models/Choopy.py:11 etc., dim_feedforward 2048).  y16 / w1_h / w2_h: fp16 copies of y [T, d], linear1.weight

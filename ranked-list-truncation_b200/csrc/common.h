@@ -75,6 +75,9 @@ int colsum(const float* src, float* out, int T, int C, cudaStream_t stream);   /
 // fp16-operand variants (tensor-core backend only): C = A[M,K] B[N,K]^T and C += alpha * alpha_ptr[0] * A[T,M]^T B[T,N]
 int gemm_tn_h(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const EpiParams& ep,
               cudaStream_t stream);
+bool attention_fwd_tc_ok(int S, int dh);
+int attention_fwd_tc(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head, float scale,
+                     cudaStream_t stream, int tag);
 bool ffn_fwd_fused_ok(int d, int f);
 void ffn_fwd_set_timeline(long long* dev_buf);
 int ffn_fwd_fused(const __half* y16, const float* y, const __half* w1h, const float* b1, const __half* w2h, const float* b2,

@@ -489,6 +489,8 @@ static int attention_fwd(const float* qkv, float* o, float* lse, int G, int S, i
                          cudaStream_t stream, DropCfg drop) {
   const int dh = d / n_head;
   const float scale = 1.0f / sqrtf(float(dh));
+  if (drop.thr == 0 && attention_fwd_tc_ok(S, dh))       // tcgen05 path (attention_tc.cuh): head dim 16, groups of <= 64 lists
+    return attention_fwd_tc(qkv, o, lse, G, S, L, d, n_head, scale, stream, TAG_ATTN_FWD);
   if (attention_mma_ok(S, dh)) {
 #define RLT_AF(DH_)                                                                                            \
   return S <= 64 ? attention_fwd_mma<DH_, 8>(qkv, o, lse, G, S, L, d, n_head, scale, stream, drop)            \
@@ -659,6 +661,14 @@ int rlt_ffn_fused_fwd(const void* y16, const float* y, const void* w1_h, const f
   return ffn_fwd_fused(static_cast<const __half*>(y16), y, static_cast<const __half*>(w1_h), b1,
                        static_cast<const __half*>(w2_h), b2, gamma, beta, out, u2, stats, static_cast<__half*>(h_out),
                        n_tokens, d_model, d_ff, ln_eps, static_cast<cudaStream_t>(stream), TAG_FFN_FUSED);
+}
+
+int rlt_attention_lists_fwd(const float* qkv, float* o, float* lse, int n_groups, int group_size, int seq_len, int d_model,
+                            int n_head, rlt_stream_t stream) {
+  RLT_REQUIRE(qkv && o && n_groups > 0 && group_size > 0 && seq_len > 0 && n_head > 0 && d_model % n_head == 0, RLT_INVALID_ARG,
+              "rlt_attention_lists_fwd: bad arguments");
+  return attention_fwd(qkv, o, lse, n_groups, group_size, seq_len, d_model, n_head, static_cast<cudaStream_t>(stream),
+                       DropCfg{0, 0, 1.f});
 }
 
 int rlt_ffn_fused_set_timeline(long long* device_buffer) {

@@ -15,6 +15,7 @@
 #include "gemm_f16out.cuh"
 #include "ffn_bwd_fused.cuh"
 #include "ffn_fwd_fused.cuh"
+#include "attention_tc.cuh"
 
 namespace rlt {
 
@@ -44,6 +45,7 @@ static int g_tma_round = env_int("RLT_TMA_ROUND", 1);
 static int g_b_resident = env_int("RLT_B_RESIDENT", 1);
 static int g_ffn_bwd_fused = env_int("RLT_FFN_BWD_FUSED", 1);   // one-pass dH / dW2 / db1 kernel (d_model 128)
 static int g_ffn_fwd_fused = env_int("RLT_FFN_FWD_FUSED", 1);   // fused FFN1 + ReLU + FFN2 + residual + LayerNorm2 (cta_group::2)
+static int g_attn_tc = env_int("RLT_ATTN_TC", 1);               // tcgen05 attention forward (head dim 16, groups <= 64 lists)
 static int g_dw_colsum = env_int("RLT_DW_COLSUM", 1);         // bias-gradient column sums as an extra MMA of the weight-gradient GEMM
 static int g_f16out_tma = env_int("RLT_F16OUT_TMA", 1);     // copy-engine epilogue kernel for the fp16-output GEMMs   // gemm_tn: keep the CTA's B slice in shared memory when it fits
 
@@ -446,8 +448,48 @@ int ffn_bwd_fused(const __half* du16, const __half* w2th, const __half* hh, __ha
   return RLT_OK;
 }
 
-static long long* g_ffn_dbg = nullptr;      // device buffer for the kernel's timeline (rlt_ffn_fused_set_timeline; tools only)
+static long long* g_ffn_dbg = nullptr;      // device buffer for a kernel timeline (rlt_ffn_fused_set_timeline; tools only)
 void ffn_fwd_set_timeline(long long* dev_buf) { g_ffn_dbg = dev_buf; }
+// ------------------------------------------------------------------------------------------
+// tcgen05 attention forward (attention_tc.cuh)
+// ------------------------------------------------------------------------------------------
+// 3-D fp32 tensor map over a [n_lists, L, width] row-major tensor: dims (width, L, n_lists), box (box_w, 1, 64 lists)
+static int make_tmap_lists3d(CUtensorMap* out, const float* base, int width, int L, long long n_lists, int box_w) {
+  EncodeTiledFn fn = encode_fn();
+  RLT_REQUIRE(fn != nullptr, RLT_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from the driver");
+  RLT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (width * 4) % 16 == 0, RLT_INVALID_ARG,
+              "TMA operand must be 16-byte aligned with a row pitch that is a multiple of 16 bytes");
+  const cuuint64_t dims[3] = {cuuint64_t(width), cuuint64_t(L), cuuint64_t(n_lists)};
+  const cuuint64_t strides[2] = {cuuint64_t(width) * 4, cuuint64_t(L) * cuuint64_t(width) * 4};
+  const cuuint32_t box[3] = {cuuint32_t(box_w), 1u, 64u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RLT_REQUIRE(r == CUDA_SUCCESS, RLT_CUDA_ERROR, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", int(r));
+  return RLT_OK;
+}
+bool attention_fwd_tc_ok(int S, int dh) { return g_attn_tc != 0 && gemm_backend() == 0 && dh == 16 && S <= 64; }
+int attention_fwd_tc(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head, float scale,
+                     cudaStream_t stream, int tag) {
+  using Cfg = AttnTcCfg<16>;
+  RLT_REQUIRE(attention_fwd_tc_ok(S, d / n_head), RLT_UNSUPPORTED_SHAPE, "attention_fwd_tc: S=%d dh=%d unsupported", S, d / n_head);
+  CUtensorMap tmQKV, tmO;
+  RLT_TRY(make_tmap_lists3d(&tmQKV, qkv, 3 * d, L, (long long)G * S, 16));
+  RLT_TRY(make_tmap_lists3d(&tmO, o, d, L, (long long)G * S, 16));
+  static DeviceOnce once;
+  if (once.first())
+    RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
+  const long long n_super = (long long)G * ((L + 1) / 2);
+  long long grid = num_sms();
+  if (grid > n_super) grid = n_super;
+  TimeScope scope(tag, stream);
+  attn_lists_fwd_tc_kernel<16><<<int(grid), Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQKV, tmO, o, lse, G, S, L, d, n_head,
+                                                                                    scale * 1.4426950408889634f, g_ffn_dbg);
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+
 // Fused FFN forward (ffn_fwd_fused.cuh): out = LN2(y + relu(y W1^T + b1) W2^T + b2), hidden on chip.
 bool ffn_fwd_fused_ok(int d, int f) {
   return g_ffn_fwd_fused != 0 && gemm_backend() == 0 && (d == 128 || d == 256) && f % 128 == 0 && f <= FfnFwdCfg<128>::MAX_F;
@@ -758,6 +800,7 @@ int rlt_set_option(const char* key, int value) {
   if (strcmp(key, "f16out_tma") == 0) { g_f16out_tma = value; return RLT_OK; }
   if (strcmp(key, "ffn_bwd_fused") == 0) { g_ffn_bwd_fused = value; return RLT_OK; }
   if (strcmp(key, "ffn_fwd_fused") == 0) { g_ffn_fwd_fused = value; return RLT_OK; }
+  if (strcmp(key, "attn_tc") == 0) { g_attn_tc = value; return RLT_OK; }
   if (strcmp(key, "dw_colsum") == 0) { g_dw_colsum = value; return RLT_OK; }
   return set_error(RLT_INVALID_ARG, "rlt_set_option: unknown option '%s'", key);
 }
@@ -769,6 +812,7 @@ int rlt_get_option(const char* key) {
   if (strcmp(key, "f16out_tma") == 0) return g_f16out_tma;
   if (strcmp(key, "ffn_bwd_fused") == 0) return g_ffn_bwd_fused;
   if (strcmp(key, "ffn_fwd_fused") == 0) return g_ffn_fwd_fused;
+  if (strcmp(key, "attn_tc") == 0) return g_attn_tc;
   if (strcmp(key, "dw_colsum") == 0) return g_dw_colsum;
   if (strcmp(key, "time_tag") == 0) return g_time_tag;
   if (strcmp(key, "lstm_backend") == 0) return lstm_backend();

@@ -134,6 +134,16 @@ def encoder_layer_bwd(desc, weights, grads, x, saved, d_out, d_x, workspace):
           "rlt_encoder_layer_bwd")
 
 
+def attention_lists_fwd(qkv, n_groups, group_size, seq_len, d_model, n_head, want_lse=True):
+    """Cross-list attention core (rlt_attention_lists_fwd): qkv [G*S*L, 3d] -> (o [G*S*L, d], lse [G*S*L, n_head])."""
+    T = n_groups * group_size * seq_len
+    o = torch.empty(T, d_model, dtype=torch.float32, device=qkv.device)
+    lse = torch.empty(T, n_head, dtype=torch.float32, device=qkv.device) if want_lse else None
+    check(lib().rlt_attention_lists_fwd(ptr(qkv), ptr(o), ptr(lse), int(n_groups), int(group_size), int(seq_len), int(d_model),
+                                        int(n_head), stream_ptr()), "rlt_attention_lists_fwd")
+    return o, lse
+
+
 def ffn_fused_fwd(y16, y, w1_h, b1, w2_h, b2, gamma, beta, out, u2=None, stats=None, h_out=None, eps=1e-5):
     """out = LayerNorm(y + relu(y W1^T + b1) W2^T + b2) in one kernel (rlt_ffn_fused_fwd).  y16 / w1_h / w2_h: fp16."""
     T, d = y.shape
