@@ -126,6 +126,44 @@ def trajectory_goldens(ref_models, ref_losses, only=None):
         print(f"traj_{name}: losses={losses}")
 
 
+def positions_goldens(ref_models, ref_losses):
+    """attend = "positions" (the papers' intent; attend_axis = 1 of rlt_encoder_desc): the UNMODIFIED
+    reference module with its encoder applied to the transposed tensor -- `enc(x.transpose(0, 1)).transpose(0, 1)` -- which
+    makes torch attend within each list.  Only the encoder attribute's forward is wrapped; parameters, heads and
+    criterion are the reference's.  Choopy / MtChoopy at B = 5 (head dim 16)."""
+    for name, attr in (("choopy", "attention_layer"), ("mtchoopy", "encoding_layer")):
+        cls_name, kwargs, feats = MODELS[name]
+        torch.manual_seed(WEIGHT_SEED)
+        model = getattr(ref_models, cls_name)(**kwargs)
+        model.train()
+        enc = getattr(model, attr)
+        orig = enc.forward
+        enc.forward = lambda x, _f=orig: _f(x.transpose(0, 1)).transpose(0, 1)
+        B = 5
+        x, y = synthetic_lists(B, 300, feats, seed=DATA_SEED + B, device="cpu")
+        out = model(x)
+        torch.manual_seed(0)
+        crit = build_criterion(ref_losses, name, "f1")
+        loss = crit(loss_input(out), y)
+        loss.backward()
+        rng = np.random.default_rng(7)
+        rec = {"x": x.numpy(), "y": y.numpy(), "loss": np.float64(loss.item())}
+        outs = flat_outputs(out)
+        for i, o in enumerate(outs):
+            store_output(rec, f"out{i}", o, rng)
+        rec["n_out"] = np.int64(len(outs))
+        names = []
+        for pname, p in model.named_parameters():
+            names.append(pname)
+            for k, v in digest(p.grad if p.grad is not None else torch.zeros_like(p), rng).items():
+                rec[f"grad/{pname}/{k}"] = v
+            rec[f"wsum/{pname}"] = np.float64(p.detach().double().sum().item())
+            rec[f"wabs/{pname}"] = np.float64(p.detach().double().abs().sum().item())
+        rec["param_names"] = np.array(names)
+        np.savez_compressed(GOLDEN / f"model_{name}_positions_B{B}.npz", **rec)
+        print(f"model_{name}_positions_B{B}: loss={loss.item():.8f}")
+
+
 def model_goldens(ref_models, ref_losses, only=None, only_sizes=None):
     for name, (cls_name, kwargs, feats) in MODELS.items():
         if only and name not in only:
@@ -343,6 +381,9 @@ def main():
     ref_models, ref_losses, ref_metrics = refshim.load()
     torch.set_num_threads(8)
     only = set(sys.argv[1:])          # e.g. `python -m oracle.make_golden moecut plecut`: only those model fixtures
+    if "positions" in only:           # `python -m oracle.make_golden positions`: attend-within-a-list fixtures
+        positions_goldens(ref_models, ref_losses)
+        return
     if "traj" in only:                # `python -m oracle.make_golden traj [names]`: the multi-step fixtures
         trajectory_goldens(ref_models, ref_losses, only - {"traj"})
         return

@@ -217,13 +217,17 @@ __device__ __forceinline__ float attn_mask(const DropCfg& drop, uint64_t item, i
 template <int DH, bool kDrop>
 __global__ void __launch_bounds__(128) attn_lists_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ o,
                                                              float* __restrict__ lse, int S, int L, int d,
-                                                             int n_head, float scale, DropCfg drop) {
+                                                             int n_head, float scale, DropCfg drop, int group_tokens) {
+  // Token of attended element s of work item (l, g): g * group_tokens + l + s * L, where the caller passes
+  //   attend across lists (reference):  S = lists per group, L = seq_len (stride between lists), group_tokens = S * seq_len,
+  //                                     gridDim.x = seq_len positions;
+  //   attend within a list:             S = seq_len, L = 1 (consecutive tokens), group_tokens = seq_len, gridDim.x = 1.
   extern __shared__ float sm[];
   float* sK = sm;                 // [S][DH+1]
   float* sV = sm + S * (DH + 1);  // [S][DH+1]
   const int l = blockIdx.x, g = blockIdx.y, h = blockIdx.z;
-  const uint64_t item = (uint64_t(g) * L + l) * n_head + h;   // work-item number of the dropout hash (head fastest)
-  const size_t tok0 = (size_t(g) * S) * L + l;  // token of list s: tok0 + s*L
+  const uint64_t item = (uint64_t(g) * gridDim.x + l) * n_head + h;   // work-item number of the dropout hash (head fastest)
+  const size_t tok0 = size_t(g) * group_tokens + l;  // token of element s: tok0 + s*L
   const int ld = 3 * d;
   for (int i = threadIdx.x; i < S * (DH / 4); i += blockDim.x) {
     const int s = i / (DH / 4), c = (i % (DH / 4)) * 4;
@@ -300,7 +304,7 @@ template <int DH, bool kDrop>
 __global__ void __launch_bounds__(128) attn_lists_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ o,
                                                              const float* __restrict__ lse, const float* __restrict__ d_o,
                                                              float* __restrict__ dqkv, int S, int L, int d, int n_head,
-                                                             float scale, DropCfg drop) {
+                                                             float scale, DropCfg drop, int group_tokens) {
   extern __shared__ float sm[];
   constexpr int P = DH + 1;
   float* sQ = sm;            // [S][P]  (q * scale)
@@ -310,8 +314,8 @@ __global__ void __launch_bounds__(128) attn_lists_bwd_kernel(const float* __rest
   float* sL = sG + S * P;    // lse  [S]
   float* sD = sL + S;        // D_i = dO_i . O_i  [S]
   const int l = blockIdx.x, g = blockIdx.y, h = blockIdx.z;
-  const uint64_t item = (uint64_t(g) * L + l) * n_head + h;
-  const size_t tok0 = (size_t(g) * S) * L + l;
+  const uint64_t item = (uint64_t(g) * gridDim.x + l) * n_head + h;
+  const size_t tok0 = size_t(g) * group_tokens + l;       // see attn_lists_fwd_kernel
   const int ld = 3 * d;
   for (int i = threadIdx.x; i < S * (DH / 4); i += blockDim.x) {
     const int s = i / (DH / 4), c = (i % (DH / 4)) * 4;
@@ -486,12 +490,17 @@ static int attention_bwd_mma(const float* qkv, const float* o, const float* lse,
 static bool attention_mma_ok(int S, int dh) { return gemm_backend() == 0 && S <= 128 && (dh == 16 || dh == 32 || dh == 64); }
 
 static int attention_fwd(const float* qkv, float* o, float* lse, int G, int S, int L, int d, int n_head,
-                         cudaStream_t stream, DropCfg drop) {
+                         cudaStream_t stream, DropCfg drop, int attend_axis = 0) {
   const int dh = d / n_head;
   const float scale = 1.0f / sqrtf(float(dh));
-  if (drop.thr == 0 && attention_fwd_tc_ok(S, dh))       // tcgen05 path (attention_tc.cuh): head dim 16, groups of <= 64 lists
+  // attend_axis 1 (attention WITHIN each list, the batch_first behaviour the reference does not have): every list is its
+  // own group of seq_len consecutive tokens; the generic kernels below take it as (S = seq_len, stride 1)
+  const int n_lists = G * S, seq_len = L;
+  int group_tokens = S * L, grid_x = L;
+  if (attend_axis == 1) { G = n_lists; S = seq_len; L = 1; group_tokens = seq_len; grid_x = 1; }
+  if (attend_axis == 0 && drop.thr == 0 && attention_fwd_tc_ok(S, dh))       // tcgen05 path (attention_tc.cuh): head dim 16, groups of <= 64 lists
     return attention_fwd_tc(qkv, o, lse, G, S, L, d, n_head, scale, stream, TAG_ATTN_FWD);
-  if (attention_mma_ok(S, dh)) {
+  if (attend_axis == 0 && attention_mma_ok(S, dh)) {
 #define RLT_AF(DH_)                                                                                            \
   return S <= 64 ? attention_fwd_mma<DH_, 8>(qkv, o, lse, G, S, L, d, n_head, scale, stream, drop)            \
                  : attention_fwd_mma<DH_, 16>(qkv, o, lse, G, S, L, d, n_head, scale, stream, drop)
@@ -500,9 +509,11 @@ static int attention_fwd(const float* qkv, float* o, float* lse, int G, int S, i
     RLT_AF(64);
 #undef RLT_AF
   }
-  const dim3 grid(L, G, n_head);
+  RLT_REQUIRE(G <= 65535, RLT_UNSUPPORTED_SHAPE, "attention: %d groups exceed gridDim.y", G);
+  const dim3 grid(grid_x, G, n_head);
   const size_t smem = size_t(2) * S * (dh + 1) * sizeof(float);
-  RLT_REQUIRE(smem <= 200 * 1024, RLT_UNSUPPORTED_SHAPE, "attention: group of %d lists does not fit in shared memory", S);
+  RLT_REQUIRE(smem <= 200 * 1024, RLT_UNSUPPORTED_SHAPE,
+              "attention: %d attended elements of head dim %d do not fit in shared memory", S, dh);
 #define RLT_ATTN_FWD(DH)                                                                                        \
   do {                                                                                                          \
     RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_kernel<DH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -510,8 +521,8 @@ static int attention_fwd(const float* qkv, float* o, float* lse, int G, int S, i
     RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_fwd_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         int(smem)));                                                            \
     time_begin(TAG_ATTN_FWD, stream);                                                                           \
-    if (drop.thr) attn_lists_fwd_kernel<DH, true><<<grid, 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, drop); \
-    else attn_lists_fwd_kernel<DH, false><<<grid, 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, drop);         \
+    if (drop.thr) attn_lists_fwd_kernel<DH, true><<<grid, 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, drop, group_tokens); \
+    else attn_lists_fwd_kernel<DH, false><<<grid, 128, smem, stream>>>(qkv, o, lse, S, L, d, n_head, scale, drop, group_tokens);         \
     time_end(TAG_ATTN_FWD, stream);                                                                             \
   } while (0)
   if (dh == 16) RLT_ATTN_FWD(16);
@@ -525,10 +536,13 @@ static int attention_fwd(const float* qkv, float* o, float* lse, int G, int S, i
 }
 
 static int attention_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int G,
-                         int S, int L, int d, int n_head, cudaStream_t stream, DropCfg drop) {
+                         int S, int L, int d, int n_head, cudaStream_t stream, DropCfg drop, int attend_axis = 0) {
   const int dh = d / n_head;
   const float scale = 1.0f / sqrtf(float(dh));
-  if (attention_mma_ok(S, dh)) {
+  const int n_lists = G * S, seq_len = L;
+  int group_tokens = S * L, grid_x = L;
+  if (attend_axis == 1) { G = n_lists; S = seq_len; L = 1; group_tokens = seq_len; grid_x = 1; }
+  if (attend_axis == 0 && attention_mma_ok(S, dh)) {
 #define RLT_AB(DH_)                                                                                                  \
   return S <= 64 ? attention_bwd_mma<DH_, 8>(qkv, o, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream, drop)       \
                  : attention_bwd_mma<DH_, 16>(qkv, o, lse, d_o, dqkv, G, S, L, d, n_head, scale, stream, drop)
@@ -537,9 +551,12 @@ static int attention_bwd(const float* qkv, const float* o, const float* lse, con
     RLT_AB(64);
 #undef RLT_AB
   }
-  const dim3 grid(L, G, n_head);
+  RLT_REQUIRE(G <= 65535, RLT_UNSUPPORTED_SHAPE, "attention bwd: %d groups exceed gridDim.y", G);
+  const dim3 grid(grid_x, G, n_head);
   const size_t smem = (size_t(4) * S * (dh + 1) + 2 * S) * sizeof(float);
-  RLT_REQUIRE(smem <= 200 * 1024, RLT_UNSUPPORTED_SHAPE, "attention bwd: group of %d lists does not fit in shared memory", S);
+  RLT_REQUIRE(smem <= 200 * 1024, RLT_UNSUPPORTED_SHAPE,
+              "attention bwd: %d attended elements of head dim %d do not fit in shared memory (attend_axis = 1 is built for "
+              "head dims up to 32 at seq_len 300)", S, dh);
 #define RLT_ATTN_BWD(DH)                                                                                        \
   do {                                                                                                          \
     RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_kernel<DH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -547,8 +564,8 @@ static int attention_bwd(const float* qkv, const float* o, const float* lse, con
     RLT_CHECK_CUDA(cudaFuncSetAttribute(attn_lists_bwd_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         int(smem)));                                                            \
     time_begin(TAG_ATTN_BWD, stream);                                                                           \
-    if (drop.thr) attn_lists_bwd_kernel<DH, true><<<grid, 128, smem, stream>>>(qkv, o, lse, d_o, dqkv, S, L, d, n_head, scale, drop); \
-    else attn_lists_bwd_kernel<DH, false><<<grid, 128, smem, stream>>>(qkv, o, lse, d_o, dqkv, S, L, d, n_head, scale, drop);         \
+    if (drop.thr) attn_lists_bwd_kernel<DH, true><<<grid, 128, smem, stream>>>(qkv, o, lse, d_o, dqkv, S, L, d, n_head, scale, drop, group_tokens); \
+    else attn_lists_bwd_kernel<DH, false><<<grid, 128, smem, stream>>>(qkv, o, lse, d_o, dqkv, S, L, d, n_head, scale, drop, group_tokens);         \
     time_end(TAG_ATTN_BWD, stream);                                                                             \
   } while (0)
   if (dh == 16) RLT_ATTN_BWD(16);
@@ -629,8 +646,8 @@ static int check_desc(const rlt_encoder_desc* e) {
   RLT_REQUIRE(e->n_head > 0 && e->d_model % e->n_head == 0, RLT_INVALID_ARG, "encoder: n_head %d does not divide d_model",
               e->n_head);
   RLT_REQUIRE(e->d_ff > 0 && e->d_ff % 32 == 0, RLT_UNSUPPORTED_SHAPE, "encoder: d_ff %d must be a multiple of 32", e->d_ff);
-  RLT_REQUIRE(e->attend_axis == 0, RLT_UNSUPPORTED_SHAPE,
-              "encoder: attend_axis=1 (attention within a list) is not implemented; the reference attends across lists");
+  RLT_REQUIRE(e->attend_axis == 0 || e->attend_axis == 1, RLT_INVALID_ARG,
+              "encoder: attend_axis %d (0 = across the lists of a group, as the reference; 1 = within each list)", e->attend_axis);
   RLT_REQUIRE(e->dropout_p >= 0.f && e->dropout_p < 1.f, RLT_INVALID_ARG, "encoder: dropout_p %f outside [0, 1)", e->dropout_p);
   RLT_REQUIRE(e->dropout_p == 0.f || (gemm_backend() == 0 && e->d_ff % 128 == 0 && e->d_model % 128 == 0), RLT_UNSUPPORTED_SHAPE,
               "encoder: train-mode dropout runs on the tensor-core backend only (the validation kernels have no dropout)");
@@ -709,7 +726,7 @@ int rlt_encoder_layer_fwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   ep.out = sv + sl.qkv; ep.ldo = 3 * d; ep.bias = w->in_proj_b; ep.tag = TAG_QKV;
   RLT_TRY(gemm_tn(x, d, w->in_proj_w, d, T, 3 * d, d, ep, stream));
   RLT_TRY(attention_fwd(sv + sl.qkv, sv + sl.o, sv + sl.lse, e->n_groups, e->group_size, e->seq_len, d, e->n_head,
-                        stream, drop));
+                        stream, drop, e->attend_axis));
   // u1 = x + drop(o Wo^T + b_o) ; y = LN1(u1)
   ep = EpiParams{}; ep.alpha = 1.f; ep.out = sv + sl.u1; ep.ldo = d; ep.bias = w->out_proj_b; ep.residual = x; ep.tag = TAG_OUT_PROJ;
   ep.drop = drop; ep.drop_site = DROP_AFTER_ATTN;
@@ -850,7 +867,7 @@ int rlt_encoder_layer_bwd(const rlt_encoder_desc* e, const rlt_encoder_weights* 
   // attention backward -> dQKV
   float* d_qkv = wide;
   RLT_TRY(attention_bwd(sv + sl.qkv, sv + sl.o, sv + sl.lse, d_o, d_qkv, e->n_groups, e->group_size, e->seq_len, d,
-                        e->n_head, stream, drop));
+                        e->n_head, stream, drop, e->attend_axis));
   // db_in += colsum(dQKV) ; dWin += dQKV^T x ; dX = dU1 + dQKV Win
   RLT_TRY(gemm_dw(d_qkv, 3 * d, x, d, T, 3 * d, d, gw->in_proj_w, d, 1.f, stream, 0, gw->in_proj_b));
   ep = EpiParams{}; ep.alpha = 1.f; ep.out = d_x; ep.ldo = d; ep.residual = d_u; ep.accumulate = e->accumulate_dx ? 1 : 0;

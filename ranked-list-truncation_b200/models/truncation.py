@@ -49,6 +49,12 @@ def _encoder_params(enc: nn.TransformerEncoder):
 
 class _Base(nn.Module):
     _dropout_p = 0.0
+    # Which axis the encoder layers attend over.  "lists" (default) is what the reference computes: its
+    # nn.TransformerEncoderLayer is built without batch_first and fed [B, L, d], so the B lists of a forward call attend to
+    # each other at every position.  "positions" is the papers' intent -- the L positions of each list
+    # attend to each other -- and equals `enc(x.transpose(0, 1)).transpose(0, 1)` on the reference module.  Set it on an
+    # instance (`model.attend = "positions"`); parameters, state_dict and everything else are unchanged.
+    attend = "lists"
 
     def _p(self) -> float:
         """Dropout probability in effect: the constructor's value in train(), 0 in eval()."""
@@ -56,7 +62,10 @@ class _Base(nn.Module):
 
     def _encode(self, x, enc: nn.TransformerEncoder):
         layer0 = enc.layers[0]
-        return F.EncoderStack.apply(x, layer0.self_attn.num_heads, 1, layer0.norm1.eps, self._p(), *_encoder_params(enc))
+        if self.attend not in ("lists", "positions"):
+            raise ValueError(f"attend must be 'lists' or 'positions', got {self.attend!r}")
+        fn = F.EncoderStack if self.attend == "lists" else F.EncoderStackWithin
+        return fn.apply(x, layer0.self_attn.num_heads, 1, layer0.norm1.eps, self._p(), *_encoder_params(enc))
 
     @staticmethod
     def _heads(h, linears):

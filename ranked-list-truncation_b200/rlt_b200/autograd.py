@@ -56,10 +56,16 @@ def _c(t: torch.Tensor) -> torch.Tensor:
 
 class EncoderStack(torch.autograd.Function):
     """nn.TransformerEncoder (a stack of post-norm layers) on [B, L, d]; the B lists of the call form ONE
-    attention group, as in the reference (no batch_first)."""
+    attention group, as in the reference (no batch_first).  `EncoderStackWithin` is the same stack with attention
+    WITHIN each list (attend_axis = 1: `enc(x.transpose(0, 1)).transpose(0, 1)` on the reference module)."""
+    ATTEND_AXIS = 0
 
     @staticmethod
     def forward(ctx, x, n_head, n_groups, ln_eps, dropout_p, *params):
+        return EncoderStack._forward(ctx, 0, x, n_head, n_groups, ln_eps, dropout_p, *params)
+
+    @staticmethod
+    def _forward(ctx, attend_axis, x, n_head, n_groups, ln_eps, dropout_p, *params):
         x = _c(x)
         B, L, d = x.shape
         n_layers = len(params) // 12
@@ -70,7 +76,8 @@ class EncoderStack(torch.autograd.Function):
         dropout_p = float(dropout_p)
         need_grad = any(ctx.needs_input_grad)
         descs = [ops.encoder_desc(n_groups, B // n_groups, L, d, n_head, d_ff, ln_eps, dropout_p,
-                                  fresh_seed() if dropout_p > 0 else 0, inference=not need_grad)
+                                  fresh_seed() if dropout_p > 0 else 0, inference=not need_grad,
+                                  attend_axis=attend_axis)
                  for _ in range(n_layers)]   # one mask set per layer
         desc = descs[0]
         saved_bytes = ops.encoder_saved_bytes(desc)
@@ -116,6 +123,15 @@ class EncoderStack(torch.autograd.Function):
             cur = d_x
         ctx.saved_bufs = ctx.layer_inputs = None
         return (cur, None, None, None, None, *grads)
+
+
+class EncoderStackWithin(EncoderStack):
+    """The encoder stack with attention within each list (the L positions of a list attend to each other)."""
+    ATTEND_AXIS = 1
+
+    @staticmethod
+    def forward(ctx, x, n_head, n_groups, ln_eps, dropout_p, *params):
+        return EncoderStack._forward(ctx, 1, x, n_head, n_groups, ln_eps, dropout_p, *params)
 
 
 class BiLstm(torch.autograd.Function):

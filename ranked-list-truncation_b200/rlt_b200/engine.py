@@ -33,12 +33,14 @@ class _EncStack:
         l0 = enc.layers[0]
         self.d = l0.linear1.in_features
         self.n_head = l0.self_attn.num_heads
+        axis = 1 if getattr(eng.model, "attend", "lists") == "positions" else 0     # models._Base.attend
         self.desc = ops.encoder_desc(eng.G, eng.S, eng.L, self.d, l0.self_attn.num_heads, l0.linear1.out_features,
-                                     l0.norm1.eps)
+                                     l0.norm1.eps, attend_axis=axis)
         self.desc_infer = ops.encoder_desc(eng.G, eng.S, eng.L, self.d, l0.self_attn.num_heads, l0.linear1.out_features,
-                                           l0.norm1.eps, inference=True)
+                                           l0.norm1.eps, inference=True, attend_axis=axis)
         self.desc_first = ops.encoder_desc(eng.G, eng.S, eng.L, self.d, l0.self_attn.num_heads,
-                                           l0.linear1.out_features, l0.norm1.eps, accumulate_dx=accumulate_dx)
+                                           l0.linear1.out_features, l0.norm1.eps, accumulate_dx=accumulate_dx,
+                                           attend_axis=axis)
         layers = _enc_layers(enc)
         self.n = len(layers)
         self.w = [ops.encoder_ptrs([p.detach() for p in lw]) for lw in layers]

@@ -100,9 +100,11 @@ def ensure_tables():
 # encoder layer
 # ----------------------------------------------------------------------------------------------
 def encoder_desc(n_groups, group_size, seq_len, d_model, n_head, d_ff=2048, ln_eps=1e-5, dropout_p=0.0, seed=0,
-                 accumulate_dx=False, inference=False):
-    return EncoderDesc(n_groups, group_size, seq_len, d_model, n_head, d_ff, 0, int(accumulate_dx), ln_eps, dropout_p,
-                       seed, int(inference), 0)
+                 accumulate_dx=False, inference=False, attend_axis=0):
+    """attend_axis 0: the lists of a group attend to each other per position (what the reference computes: no batch_first);
+    1: the positions of each list attend to each other (the papers' intent)."""
+    return EncoderDesc(n_groups, group_size, seq_len, d_model, n_head, d_ff, int(attend_axis), int(accumulate_dx), ln_eps,
+                       dropout_p, seed, int(inference), 0)
 
 
 def encoder_ptrs(tensors) -> EncoderPtrs:

@@ -185,3 +185,18 @@ def test_rank_metrics_vs_reference(L):
     # ties keep their list order: two equal scores, the first document is ranked first
     assert O.taskr_dcg_per_list(np.array([[1., 0.]]), np.array([[.5, .5]], dtype=np.float32)) == [1 / math.log2(2) - 1 / math.log2(3)]
     assert O.taskr_dcg_per_list(np.array([[0., 1.]]), np.array([[.5, .5]], dtype=np.float32)) == [-1 / math.log2(2) + 1 / math.log2(3)]
+
+
+@pytest.mark.parametrize("name", ["choopy", "mtchoopy"])
+def test_oracle_positions_mode_matches_transposed_reference(name):
+    """attend='positions' of the oracle against the unmodified reference with its encoder applied to the transposed
+    tensor (tests/golden/model_*_positions_B5.npz)."""
+    g = load_golden(f"model_{name}_positions_B5.npz")
+    model = build_model(name)
+    sd = {k: v.detach().double() for k, v in model.state_dict().items()}
+    x = torch.from_numpy(g["x"]).double()
+    out = getattr(O, name + "_forward")(sd, x, attend="positions")
+    outs = out if isinstance(out, (list, tuple)) else [out]
+    for i, o in enumerate(outs):
+        ref = g[f"out{i}"]
+        assert np.abs(o.numpy() - ref).max() <= 2e-5 * np.abs(ref).max(), (name, i)

@@ -1,0 +1,86 @@
+"""attend = "positions" (rlt_encoder_desc.attend_axis = 1): attention WITHIN each list -- the papers' intent, which the
+reference does not compute because it builds nn.TransformerEncoderLayer without batch_first.
+Goldens: the unmodified reference module with its encoder applied to the transposed tensor
+(`enc(x.transpose(0, 1)).transpose(0, 1)`, `python -m oracle.make_golden positions`).  The default ("lists") stays the
+reference's behaviour and is what every other test checks."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_model, check_weights, grad_errors, load_golden, output_error
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["choopy", "mtchoopy"])
+def test_attention_within_lists_vs_transposed_reference_golden(name):
+    from utils import losses
+    g = load_golden(f"model_{name}_positions_B5.npz")
+    model = build_model(name)
+    check_weights(model, g)
+    model.attend = "positions"
+    model = model.cuda().train()
+    x, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    out = model(x)
+    outs = out if isinstance(out, list) else [out]
+    for i, o in enumerate(outs):
+        err, ref_max = output_error(o, g, f"out{i}")
+        assert err <= 1e-3 * ref_max, (name, i, err, ref_max)
+    torch.manual_seed(0)
+    crit = (losses.ChoopyLoss(metric="f1") if name == "choopy" else
+            losses.MtCutLoss(metric="f1", rerank_weight=0.5, classi_weight=0.5, num_tasks=3)).cuda()
+    loss = crit(out, y)
+    ref_loss = float(g["loss"])
+    assert abs(loss.item() - ref_loss) <= 1e-3 * max(abs(ref_loss), 1e-2), (loss.item(), ref_loss)
+    loss.backward()
+    named = {n: (p.grad if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
+    rel_l2, rel_max, _ = grad_errors(named, g)
+    assert rel_l2 <= 2e-3 and rel_max <= 1e-3, (name, rel_l2, rel_max)
+    # the two modes differ by O(1): the default must NOT reproduce this golden
+    model.attend = "lists"
+    with torch.no_grad():
+        o2 = model(x)
+    o2 = o2[-1] if isinstance(o2, list) else o2
+    ref_last = g[f"out{len(outs) - 1}"]
+    assert np.abs(o2.cpu().numpy() - ref_last).max() > 1e-2 * np.abs(ref_last).max()
+
+
+def test_attend_within_lists_is_independent_of_the_batch():
+    """With attention inside a list, a list's output no longer depends on which lists share its forward call."""
+    model = build_model("choopy")
+    model.attend = "positions"
+    model = model.cuda().eval()
+    g = load_golden("model_choopy_positions_B5.npz")
+    x = torch.from_numpy(g["x"]).cuda()
+    with torch.no_grad():
+        a = model(x)[0:1]
+        b = model(x[0:1])
+    assert (a - b).abs().max().item() <= 1e-6 * a.abs().max().item()
+
+
+def test_head_dim_64_at_300_positions_is_refused_for_the_backward():
+    from models.truncation import _encoder_params
+    from rlt_b200.autograd import EncoderStackWithin
+    enc = torch.nn.TransformerEncoder(torch.nn.TransformerEncoderLayer(d_model=256, nhead=4, dropout=0.0), 1,
+                                      enable_nested_tensor=False).cuda()
+    params = _encoder_params(enc)
+    x = torch.randn(2, 300, 256, device="cuda", requires_grad=True)
+    out = EncoderStackWithin.apply(x, 4, 1, 1e-5, 0.0, *params)          # forward fits (156 KB of K / V)
+    with pytest.raises(RuntimeError, match="do not fit in shared memory"):
+        out.sum().backward()
+
+
+def test_engine_follows_the_models_attend_mode():
+    from utils import losses
+    from rlt_b200.engine import Engine
+    g = load_golden("model_choopy_positions_B5.npz")
+    model = build_model("choopy")
+    model.attend = "positions"
+    model = model.cuda().train()
+    x, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    eng = Engine(model, n_groups=1, group_size=5, seq_len=300)
+    loss = eng.train_step(x, y)
+    ref_loss = float(g["loss"])
+    assert abs(loss.item() - ref_loss) <= 1e-3 * max(abs(ref_loss), 1e-2), (loss.item(), ref_loss)
+    rel_l2, rel_max, _ = grad_errors({n: eng.grads[n] for n, _ in model.named_parameters()}, g)
+    assert rel_l2 <= 2e-3 and rel_max <= 1e-3, (rel_l2, rel_max)
