@@ -311,9 +311,16 @@ def measure_heads(c, steps: int):
         if L == 300:
             grad = torch.empty_like(z)
             lpl = torch.empty(n, device=c.dev)
-            for kind, metric, tau in (("choopy", "f1", 1.0), ("js", "f1", 0.85), ("js", "dcg", 0.85), ("raml", "f1", 0.95),
-                                      ("raml", "dcg", 0.95)):
-                fn = lambda: ops.cut_loss(z, y, loss_kind=kind, metric=metric, tau=tau, grad=grad, loss_per_list=lpl)  # noqa: E731
+            bits = ops.pack_labels(y)
+            words = bits.shape[1]
+            for kind, metric, tau, packed in (("choopy", "f1", 1.0, False), ("js", "f1", 0.85, False), ("js", "dcg", 0.85, False),
+                                              ("raml", "f1", 0.95, False), ("raml", "dcg", 0.95, False),
+                                              ("choopy", "f1", 1.0, True), ("js", "f1", 0.85, True)):
+                if packed:      # labels as the bit masks of rlt_pack_labels: 8 L + 4 ceil(L/32) + 4 bytes per list
+                    fn = lambda: ops.cut_loss(z, None, label_bits=bits, loss_kind=kind, metric=metric, tau=tau, grad=grad,  # noqa: E731
+                                              loss_per_list=lpl)
+                else:
+                    fn = lambda: ops.cut_loss(z, y, loss_kind=kind, metric=metric, tau=tau, grad=grad, loss_per_list=lpl)  # noqa: E731
                 for _ in range(2):
                     fn()
                 _barrier(c)
@@ -324,10 +331,12 @@ def measure_heads(c, steps: int):
                 _barrier(c)
                 k = max(3, steps // 2)
                 t = _max_over_ranks(c, e0.elapsed_time(e1)) * 1e-3
-                nbytes = n * k * (12 * L + 4)
-                out[f"k3_{kind}_{metric}"] = {"what": "softmax + reward + loss + d/dlogits (rlt_cut_loss)", "seq_len": L,
-                                              "lists_per_s": n * k * c.world / t, "gbs_per_gpu": nbytes / t / 1e9,
-                                              "frac": nbytes / t / 1e9 / hbm}
+                nbytes = n * k * ((8 * L + 4 * words + 4) if packed else (12 * L + 4))
+                out[f"k3_{kind}_{metric}" + ("_bits" if packed else "")] = {
+                    "what": "softmax + reward + loss + d/dlogits (" + ("rlt_cut_loss_bits, labels as bit masks" if packed else "rlt_cut_loss") + ")",
+                    "seq_len": L, "lists_per_s": n * k * c.world / t, "gbs_per_gpu": nbytes / t / 1e9,
+                    "frac": nbytes / t / 1e9 / hbm}
+            del bits
             del grad, lpl
         del z, y
         torch.cuda.empty_cache()

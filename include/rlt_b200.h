@@ -316,6 +316,10 @@ typedef struct rlt_cut_loss_desc {
  * loss_out: device scalar (optional; deterministic single-CTA reduction of loss_per_list). */
 int rlt_cut_loss(const rlt_cut_loss_desc* desc, const float* in, const float* labels, float* probs_out, float* grad,
                  float* loss_per_list, float* loss_out, rlt_stream_t stream);
+/* The same criteria with the labels as the bit masks of rlt_pack_labels ([n_lists, ceil(seq_len/32)] words): 8 L + L/8
+ * bytes of traffic per list instead of 12 L.  Logits in (input_kind 0), even seq_len, 8-byte aligned float arrays. */
+int rlt_cut_loss_bits(const rlt_cut_loss_desc* desc, const float* in, const uint32_t* label_bits, float* probs_out, float* grad,
+                      float* loss_per_list, float* loss_out, rlt_stream_t stream);
 /* Upload the DCG coefficient tables built on the host with math.log(j+2, 2) (utils/metrics.py:7). */
 int rlt_set_dcg_tables(const float* coef32_host, const double* term64_host, int n);
 

@@ -110,4 +110,10 @@ void set_lstm_backend(int v);
 // producers need not materialise rounded operand copies.
 bool tma_rounds();
 
+// cut_loss_pair.cu: the packed K3 kernels (logits in, even L, 8-byte aligned rows); labels as floats or rlt_pack_labels words
+bool cut_loss_pair_ok(int L, const void* in, const void* labels, const void* probs_out, const void* grad);
+int cut_loss_pair_launch(const rlt_cut_loss_desc* c, const float* in, const void* labels, bool bits, float* probs_out, float* grad,
+                         float* loss_per_list, cudaStream_t stream);
+int cut_loss_pair_set_rcoef(const float* rc_host, int n);
+
 }  // namespace rlt

@@ -10,34 +10,16 @@
 #include <type_traits>
 
 #include "common.h"
+#include "warp_utils.cuh"
 
 namespace rlt {
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ float warp_incl_scan(float v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const float t = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v += t;
-  }
-  return v;
-}
 
 // float32-rounded math.log(j+2, 2) (Metric_for_Loss.dcg builds torch.tensor(DCG_coef_300[:k]), reference
 // utils/metrics.py:7,97) — uploaded once by the host from the Python-side table so that it is the SAME
 // table, not a device log2.
 __device__ float g_dcg_coef32[1024];
 // float32(1) / coef32 (correctly rounded on the host): (+-1) / coef of the reference without a device division
-__device__ float g_dcg_rcoef32[1024];
+__device__ __align__(16) float g_dcg_rcoef32[1024];
 // float64 1/math.log(j+2, 2) for Metric.dcg (utils/metrics.py:26-38)
 __device__ double g_dcg_term64[1024];
 
@@ -825,6 +807,7 @@ int rlt_set_dcg_tables(const float* coef32_host, const double* term64_host, int 
     float rc[1024];
     for (int i = 0; i < n; ++i) rc[i] = 1.0f / coef32_host[i];   // IEEE float32 division on the host
     RLT_CHECK_CUDA(cudaMemcpyToSymbol(g_dcg_rcoef32, rc, sizeof(float) * n));
+    RLT_TRY(cut_loss_pair_set_rcoef(rc, n));
   }
   RLT_CHECK_CUDA(cudaMemcpyToSymbol(g_dcg_term64, term64_host, sizeof(double) * n));
   return RLT_OK;
@@ -865,6 +848,15 @@ int rlt_cut_loss(const rlt_cut_loss_desc* c, const float* in, const float* label
               "rlt_cut_loss: input_kind %d / loss_kind %d out of range", c->input_kind, c->loss_kind);
   const int cfg = c->input_kind * 8 + c->loss_kind * 2 + (c->metric_dcg ? 1 : 0);
   const float tau = c->tau, gscale = c->grad_scale;
+  if (c->input_kind == 0 && cut_loss_pair_ok(L, in, labels, probs_out, grad)) {      // the packed kernel (cut_loss_pair.cu)
+    RLT_TRY(cut_loss_pair_launch(c, in, labels, false, probs_out, grad, loss_per_list, stream));
+    RLT_CHECK_LAUNCH();
+    if (loss_out != nullptr) {
+      reduce_scale_kernel<<<1, 256, 0, stream>>>(loss_per_list, B, c->loss_scale, loss_out, c->accumulate_loss);
+      RLT_CHECK_LAUNCH();
+    }
+    return RLT_OK;
+  }
   auto launch = [&](auto ni) {
     constexpr int NI = decltype(ni)::value;
     switch (cfg) {

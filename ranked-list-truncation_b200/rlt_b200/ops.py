@@ -306,13 +306,32 @@ def softmax_lists_bwd(p, dp, dz, n_lists, seq_len):
 
 
 def cut_loss(inp, labels, *, loss_kind, metric="f1", tau=1.0, input_kind=0, probs_out=None, grad=None,
-             loss_per_list=None, loss_out=None, grad_scale=1.0, loss_scale=1.0, accumulate=False):
+             loss_per_list=None, loss_out=None, grad_scale=1.0, loss_scale=1.0, accumulate=False, label_bits=None):
+    """labels: [B, L] float32 -- or None with label_bits = the [B, ceil(L/32)] int32 / uint32 words of pack_labels
+    (rlt_cut_loss_bits: logits in, even L)."""
     ensure_tables()
-    n_lists, seq_len = labels.shape
+    n_lists, seq_len = inp.shape[0], inp.shape[1]
     desc = CutLossDesc(n_lists, seq_len, input_kind, LOSS_KINDS[loss_kind] if isinstance(loss_kind, str) else loss_kind,
                        0 if metric == "f1" else 1, int(accumulate), tau, grad_scale, loss_scale)
+    if label_bits is not None:
+        if label_bits.shape != (n_lists, (seq_len + 31) // 32) or label_bits.element_size() != 4:
+            raise ValueError(f"label_bits must be [{n_lists}, {(seq_len + 31) // 32}] 32-bit words")
+        check(lib().rlt_cut_loss_bits(C.byref(desc), ptr(inp), ptr(label_bits), ptr(probs_out), ptr(grad), ptr(loss_per_list),
+                                      ptr(loss_out), stream_ptr()), "rlt_cut_loss_bits")
+        return
     check(lib().rlt_cut_loss(C.byref(desc), ptr(inp), ptr(labels), ptr(probs_out), ptr(grad), ptr(loss_per_list),
                              ptr(loss_out), stream_ptr()), "rlt_cut_loss")
+
+
+def pack_labels(labels, check_binary=True):
+    """[B, L] float32 0./1. labels -> [B, ceil(L/32)] int32 bit masks (bit j%32 of word j//32 = label j), rlt_pack_labels."""
+    n_lists, seq_len = labels.shape
+    bits = torch.empty(n_lists, (seq_len + 31) // 32, dtype=torch.int32, device=labels.device)
+    status = torch.zeros(1, dtype=torch.int32, device=labels.device)
+    check(lib().rlt_pack_labels(ptr(labels), n_lists, seq_len, ptr(bits), ptr(status), stream_ptr()), "rlt_pack_labels")
+    if check_binary and int(status.item()) & 2:
+        raise ValueError("labels other than 0. and 1. cannot be stored as bit masks")
+    return bits
 
 
 def reward_matrix(labels, rewards, metric="f1"):

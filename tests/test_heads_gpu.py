@@ -42,6 +42,77 @@ def test_cut_loss_kernel_vs_reference_golden(kind, metric, L):
 
 
 @pytest.mark.parametrize("L", [300, 40])
+@pytest.mark.parametrize("metric", ["f1", "dcg"])
+@pytest.mark.parametrize("kind", list(KINDS))
+def test_cut_loss_from_label_bit_masks_vs_reference_golden(kind, metric, L):
+    """rlt_cut_loss_bits (labels as the words of rlt_pack_labels) against the same reference goldens, and bit-identical
+    to the float-label call: both run the packed kernel of cut_loss_pair.cuh, only the label fetch differs."""
+    from rlt_b200 import ops
+    g = load_golden("losses.npz")
+    y = torch.from_numpy(g[f"y_{L}"]).cuda()
+    z = torch.from_numpy(g[f"z_{L}"]).cuda().reshape(y.shape).contiguous()
+    B = y.shape[0]
+    lk, tau = KINDS[kind]
+    key = f"{kind}_{metric}_{L}"
+    bits = ops.pack_labels(y)
+    out = {}
+    for fmt in ("bits", "float"):
+        grad, per, loss, probs = torch.empty_like(z), torch.empty(B, device="cuda"), torch.empty((), device="cuda"), torch.empty_like(z)
+        ops.cut_loss(z, y if fmt == "float" else None, label_bits=bits if fmt == "bits" else None, loss_kind=lk, metric=metric,
+                     tau=tau, probs_out=probs, grad=grad, loss_per_list=per, loss_out=loss, grad_scale=1.0 / B, loss_scale=1.0 / B)
+        out[fmt] = (grad, per, loss, probs)
+    grad, per, loss, probs = out["bits"]
+    ref_loss = float(g[key + "/loss"])
+    assert abs(loss.item() - ref_loss) <= 2e-5 * max(1.0, abs(ref_loss)), (loss.item(), ref_loss)
+    ref = g[key + "/dz"].reshape(B, L)
+    err = np.abs(grad.cpu().numpy() - ref).max()
+    assert err <= 2e-4 * max(np.abs(ref).max(), 1e-6), (err, np.abs(ref).max())
+    if metric == "f1":     # DCG: the sign is applied by a select instead of a multiply -- same values, checked to 1 ulp below
+        for a, b in zip(out["bits"], out["float"]):
+            assert torch.equal(a, b)
+    else:
+        for a, b in zip(out["bits"], out["float"]):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-9)
+
+
+def test_cut_loss_odd_length_and_probability_input_keep_the_scalar_kernel():
+    """The packed kernel needs even L and logits: L = 301 and input_kind = 1 go through cut_loss_kernel and agree with the
+    oracle's float64 loss; rlt_cut_loss_bits refuses an odd length instead of falling back."""
+    from rlt_b200 import ops
+    torch.manual_seed(4)
+    B, L = 7, 301
+    z = torch.randn(B, L, device="cuda")
+    y = (torch.rand(B, L, device="cuda") < 0.15).float()
+    p64 = torch.softmax(z.double().cpu(), dim=1)
+    y64 = y.cpu().double()
+    for kind, (lk, tau) in KINDS.items():
+        for metric in ("f1", "dcg"):
+            per, loss = torch.empty(B, device="cuda"), torch.empty((), device="cuda")
+            ops.cut_loss(z, y, loss_kind=lk, metric=metric, tau=tau, loss_per_list=per, loss_out=loss, loss_scale=1.0 / B)
+            ref = (O.choopy_loss(p64, y64, metric) if lk == "choopy" else
+                   O.attncut_loss(p64, y64, metric, tau) if lk == "raml" else O.div_loss(p64, y64, metric, tau, lk))
+            assert abs(loss.item() - float(ref)) <= 2e-5 * max(1.0, abs(float(ref))), (kind, metric, loss.item(), float(ref))
+    # ... and an even length of another size class (NP = 8) through the packed kernel, floats and bit masks
+    L2 = 500
+    z2 = torch.randn(B, L2, device="cuda")
+    y2 = (torch.rand(B, L2, device="cuda") < 0.1).float()
+    p2 = torch.softmax(z2.double().cpu(), dim=1)
+    for kind, (lk, tau) in KINDS.items():
+        for metric in ("f1", "dcg"):
+            ref = (O.choopy_loss(p2, y2.cpu().double(), metric) if lk == "choopy" else
+                   O.attncut_loss(p2, y2.cpu().double(), metric, tau) if lk == "raml" else
+                   O.div_loss(p2, y2.cpu().double(), metric, tau, lk))
+            for bits in (None, ops.pack_labels(y2)):
+                per, loss = torch.empty(B, device="cuda"), torch.empty((), device="cuda")
+                ops.cut_loss(z2, y2 if bits is None else None, label_bits=bits, loss_kind=lk, metric=metric, tau=tau,
+                             loss_per_list=per, loss_out=loss, loss_scale=1.0 / B)
+                assert abs(loss.item() - float(ref)) <= 2e-5 * max(1.0, abs(float(ref))), (kind, metric, loss.item(), float(ref))
+    with pytest.raises(RuntimeError):
+        ops.cut_loss(z, None, label_bits=ops.pack_labels(y), loss_kind="js", metric="f1", tau=0.85,
+                     loss_per_list=torch.empty(B, device="cuda"))
+
+
+@pytest.mark.parametrize("L", [300, 40])
 def test_reward_matrix_kernel(L):
     from rlt_b200 import ops
     g = load_golden("losses.npz")

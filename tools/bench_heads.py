@@ -37,11 +37,17 @@ def main():
         if L <= 320:
             grad = torch.empty_like(z)
             lpl = torch.empty(n, device="cuda")
-            for kind, metric in (("choopy", "f1"), ("js", "f1"), ("js", "dcg"), ("raml", "dcg")):
+            bits = ops.pack_labels(y)
+            for kind, metric in (("choopy", "f1"), ("js", "f1"), ("js", "dcg"), ("raml", "f1"), ("raml", "dcg"), ("kl", "f1")):
                 t = timeit(lambda: ops.cut_loss(z, y, loss_kind=kind, metric=metric, tau=0.85, grad=grad, loss_per_list=lpl))
                 b = n * (12 * L + 4)
                 print(f"K3 cut_loss {kind:6s}/{metric:3s} L={L:4d} n={n}: {t*1e3:7.3f} ms  {n/t/1e6:8.1f} M lists/s  {b/t/1e9:7.0f} GB/s  "
                       f"{b/t/1e9/peak:.2f} of copy peak")
+                t = timeit(lambda: ops.cut_loss(z, None, label_bits=bits, loss_kind=kind, metric=metric, tau=0.85, grad=grad,
+                                                loss_per_list=lpl))
+                b = n * (8 * L + 4 * bits.shape[1] + 4)
+                print(f"K3 cut_loss_bits {kind:6s}/{metric:3s} L={L:4d}: {t*1e3:7.3f} ms  {n/t/1e6:8.1f} M lists/s  {b/t/1e9:7.0f} GB/s  "
+                      f"{b/t/1e9/peak:.2f} of copy peak (8 L + L/8 bytes per list)")
         del z, y, p
 
 
