@@ -331,6 +331,10 @@ int rlt_set_dcg_tables(const float* coef32_host, const double* term64_host, int 
  * number of relevant in the list, F1 and DCG as float64 with numpy's arithmetic. */
 int rlt_eval_cut(const float* probs, const float* labels, int n_lists, int seq_len, int mode, int32_t* k_out,
                  int32_t* count_out, int32_t* nrel_out, double* f1_out, double* dcg_out, rlt_stream_t stream);
+/* mode 0 with the labels as the bit masks of rlt_pack_labels ([n_lists, ceil(seq_len/32)] words): 4 L + L/8 bytes per
+ * list instead of 8 L.  Even seq_len, probs 8-byte aligned. */
+int rlt_eval_cut_bits(const float* probs, const uint32_t* label_bits, int n_lists, int seq_len, int32_t* k_out,
+                      int32_t* count_out, int32_t* nrel_out, double* f1_out, double* dcg_out, rlt_stream_t stream);
 
 /* Same metrics for caller-supplied cut positions (the Metric.f1 / Metric.dcg signature, utils/metrics.py:15,26).
  * pyint_in[b] = 1 marks a k that was a Python int in the reference (float32 precision, run.py:135). */

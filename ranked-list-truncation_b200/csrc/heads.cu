@@ -424,6 +424,174 @@ __global__ void __launch_bounds__(128) eval_cut_kernel(const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// K4, the arg-max path at even L (the inference sweep of BASELINE config 5), second version.  Same results bit for bit;
+// what changed against eval_cut_kernel above (576 warp instructions per 300-position list, 0.56 of the copy peak):
+//   * phase 1 reads the probabilities as 64-bit pairs (position 2 lane + 64 i), labels stay one position per lane so
+//     that a ballot IS the bit word of 32 consecutive positions; with kBits the words come from rlt_pack_labels
+//     (4 L + L/8 bytes per list instead of 8 L) and phase 1 is the arg-max alone;
+//   * phase 2 (numpy's pairwise float64 order, one list per lane) took 12.7 instructions per term: the 1/log2(j+2)
+//     table now sits in shared memory (one broadcast LDS.64 per term), every leaf of the pairwise tree starts at a
+//     multiple of 8, so the 8 label bits of an unrolled step are ONE byte of the mask and the sign is one shift + one
+//     LOP3 on the high word: 4 instructions per term.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double signed_term(double t, uint32_t nbits, int q) {
+  // nbits = ~label bits; bit q set -> the label is 0 -> the term is negative
+  const int hi = __double2hiint(t) ^ int((nbits << (31 - q)) & 0x80000000u);
+  return __hiloint2double(hi, __double2loint(t));
+}
+__device__ __noinline__ double np_leaf(const uint32_t* bits, const double* term, int a0, int n) {
+  auto one = [&](int j) -> double {
+    const double t = term[j];
+    return ((bits[j >> 5] >> (j & 31)) & 1u) ? t : -t;
+  };
+  if (n < 8) {
+    double s = one(a0);
+    for (int i = 1; i < n; ++i) s = __dadd_rn(s, one(a0 + i));
+    return s;
+  }
+  // a0 is a multiple of 8 (leaves start at 0 or at a split point rounded to 8): 8 consecutive labels = one byte
+  uint32_t nb = ~(bits[a0 >> 5] >> (a0 & 31));
+  double r0 = signed_term(term[a0], nb, 0), r1 = signed_term(term[a0 + 1], nb, 1), r2 = signed_term(term[a0 + 2], nb, 2),
+         r3 = signed_term(term[a0 + 3], nb, 3), r4 = signed_term(term[a0 + 4], nb, 4), r5 = signed_term(term[a0 + 5], nb, 5),
+         r6 = signed_term(term[a0 + 6], nb, 6), r7 = signed_term(term[a0 + 7], nb, 7);
+  int i = 8;
+  const int n8 = n - (n % 8);
+  for (; i < n8; i += 8) {
+    const int j = a0 + i;
+    nb = ~(bits[j >> 5] >> (j & 31));
+    r0 = __dadd_rn(r0, signed_term(term[j], nb, 0)); r1 = __dadd_rn(r1, signed_term(term[j + 1], nb, 1));
+    r2 = __dadd_rn(r2, signed_term(term[j + 2], nb, 2)); r3 = __dadd_rn(r3, signed_term(term[j + 3], nb, 3));
+    r4 = __dadd_rn(r4, signed_term(term[j + 4], nb, 4)); r5 = __dadd_rn(r5, signed_term(term[j + 5], nb, 5));
+    r6 = __dadd_rn(r6, signed_term(term[j + 6], nb, 6)); r7 = __dadd_rn(r7, signed_term(term[j + 7], nb, 7));
+  }
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)), __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+  for (; i < n; ++i) res = __dadd_rn(res, one(a0 + i));
+  return res;
+}
+// numpy's pairwise sum (pairwise_sum in numpy/core/src/umath/loops_utils.h.src): n <= 128 one leaf; else split at n/2
+// rounded down to a multiple of 8 and recurse.  The larger part has at most n/2 + 7.5 terms, so n <= 1024 needs at most
+// four splits (1023 -> 519 -> 263 -> 135 -> 71); the recursion is a template over the remaining depth, no local-memory
+// stack.
+template <int D>
+__device__ __forceinline__ double np_pairwise_fast(const uint32_t* bits, const double* term, int a, int m) {
+  if constexpr (D == 0) {
+    return np_leaf(bits, term, a, m);
+  } else {
+    if (m <= 128) return np_leaf(bits, term, a, m);
+    int h = m / 2;
+    h -= h % 8;
+    const double l = np_pairwise_fast<D - 1>(bits, term, a, h);
+    return __dadd_rn(l, np_pairwise_fast<D - 1>(bits, term, a + h, m - h));
+  }
+}
+
+template <int NP, bool kBits, bool kPrefetch>
+__global__ void __launch_bounds__(128) eval_cut_fast_kernel(const float* __restrict__ probs, const void* __restrict__ labels,
+                                                            int B, int L, int32_t* __restrict__ k_out,
+                                                            int32_t* __restrict__ count_out, int32_t* __restrict__ nrel_out,
+                                                            double* __restrict__ f1_out, double* __restrict__ dcg_out) {
+  constexpr int NI = 2 * NP;
+  __shared__ uint32_t s_bits[4][32][33];  // [warp][list in warp][word]; 33: phase 2 reads one ROW per lane, conflict-free
+  __shared__ int s_k[4][32];
+  __shared__ double s_term[64 * NP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwords = (L + 31) / 32, npair = L >> 1;
+  const long long base = (long long)(blockIdx.x * 4 + warp) * 32;
+  if (dcg_out != nullptr)
+    for (int j = threadIdx.x; j < L; j += 128) s_term[j] = g_dcg_term64[j];
+  // ---- phase 1: cooperative, one list at a time
+  float2 pv[NP];
+  float yv[kBits ? 1 : NI];
+  auto fetch = [&](long long b, float2 (&pd)[NP], float (&yd)[kBits ? 1 : NI]) {
+    const float2* pr = reinterpret_cast<const float2*>(probs + size_t(b) * L);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int pj = lane + 32 * i;
+      pd[i] = pj < npair ? __ldg(pr + pj) : make_float2(-INFINITY, -INFINITY);
+    }
+    if (!kBits) {
+      const float* yr = static_cast<const float*>(labels) + size_t(b) * L;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int j = lane + 32 * i;
+        yd[i] = j < L ? __ldg(yr + j) : 0.f;
+      }
+    }
+  };
+  if (kBits) {   // the warp's 32 x nwords label words: one coalesced copy into the rows phase 2 reads
+    const uint32_t* src = static_cast<const uint32_t*>(labels) + size_t(base) * nwords;
+    const long long left = (long long)(B - base) * nwords;
+    for (int idx = lane; idx < 32 * nwords && idx < left; idx += 32) s_bits[warp][idx / nwords][idx % nwords] = __ldg(src + idx);
+  }
+  if (base < B) fetch(base, pv, yv);
+  for (int t = 0; t < 32; ++t) {
+    const long long b = base + t;
+    if (b >= B) break;  // warp-uniform
+    float2 pn[NP];
+    float yn[kBits ? 1 : NI];
+    if (kPrefetch && t + 1 < 32 && b + 1 < B) fetch(b + 1, pn, yn);
+    float best = -INFINITY;
+    int best_j = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {          // strict >: the first maximum of this lane wins (positions ascend with i)
+      if (pv[i].x > best) { best = pv[i].x; best_j = 2 * lane + 64 * i; }
+      if (pv[i].y > best) { best = pv[i].y; best_j = 2 * lane + 64 * i + 1; }
+    }
+    // order-preserving key (negative floats: all bits flipped; others: sign bit set); 0 = "nothing above -inf / NaN"
+    const uint32_t u = __float_as_uint(best);
+    const uint32_t key = best_j == 0x7fffffff ? 0u : ((u & 0x80000000u) ? ~u : (u | 0x80000000u));
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+    const uint32_t cand = (key == kmax && best_j != 0x7fffffff) ? uint32_t(best_j) : 0x7fffffffu;
+    best_j = int(__reduce_min_sync(0xffffffffu, cand));          // the first position among the lanes that hold the maximum
+    if (best_j == 0x7fffffff) best_j = 0;  // all -inf / NaN row
+    if (lane == 0) s_k[warp][t] = best_j + 1;
+    if (!kBits) {
+      uint32_t mine = 0u;
+#pragma unroll
+      for (int w = 0; w < NI; ++w) {
+        const uint32_t m = __ballot_sync(0xffffffffu, yv[w] == 1.f);   // positions >= L hold 0
+        if (lane == w) mine = m;
+      }
+      if (lane < nwords) s_bits[warp][t][lane] = mine;
+    }
+    if (kPrefetch) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) pv[i] = pn[i];
+      if (!kBits) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) yv[i] = yn[i];
+      }
+    } else if (t + 1 < 32 && b + 1 < B) {
+      fetch(b + 1, pv, yv);
+    }
+  }
+  __syncthreads();      // s_term (all warps) and this warp's s_bits / s_k rows
+  // ---- phase 2: one list per lane
+  const long long b = base + lane;
+  if (b >= B) return;
+  const uint32_t* bits = s_bits[warp][lane];
+  const int k = s_k[warp][lane];
+  int count = 0, nrel = 0;
+  for (int w = 0; w < nwords; ++w) {
+    const uint32_t m = bits[w];
+    nrel += __popc(m);
+    const int lo = w * 32;
+    if (k >= lo + 32) count += __popc(m);
+    else if (k > lo) count += __popc(m & ((1u << (k - lo)) - 1u));
+  }
+  // F1 with numpy's promotion (k is an np.int64 here): p in float64, r in float32 (utils/metrics.py:15-24)
+  const float r32 = nrel != 0 ? __fdiv_rn(float(count), float(nrel)) : 0.f;
+  const double p64 = __ddiv_rn(double(count), double(k));
+  const double den = __dadd_rn(p64, double(r32));
+  const double f1 = den != 0.0 ? __ddiv_rn(__dmul_rn(__dmul_rn(2.0, p64), double(r32)), den) : 0.0;
+  if (k_out) k_out[b] = k;
+  if (count_out) count_out[b] = count;
+  if (nrel_out) nrel_out[b] = nrel;
+  if (f1_out) f1_out[b] = f1;
+  if (dcg_out) dcg_out[b] = np_pairwise_fast<4>(bits, s_term, 0, k);
+}
+
+// ------------------------------------------------------------------------------------------
 // d -> n_heads dot products per token (Linear(d, 1) heads): z[h, t] = x[t,:] . w[h,:] + b[h]
 // ------------------------------------------------------------------------------------------
 template <int D, int NH>
@@ -785,6 +953,18 @@ __global__ void pair_softmax_bwd_kernel(const float* __restrict__ o, const float
   RLT_K3(0, 0, 0) RLT_K3(0, 0, 1) RLT_K3(0, 1, 0) RLT_K3(0, 1, 1) RLT_K3(0, 2, 0) RLT_K3(0, 2, 1) RLT_K3(0, 3, 0) RLT_K3(0, 3, 1) \
   RLT_K3(1, 0, 0) RLT_K3(1, 0, 1) RLT_K3(1, 1, 0) RLT_K3(1, 1, 1) RLT_K3(1, 2, 0) RLT_K3(1, 2, 1) RLT_K3(1, 3, 0) RLT_K3(1, 3, 1)
 
+template <bool kBits>
+static void eval_cut_fast_launch(const float* probs, const void* labels, int n_lists, int L, int32_t* k_out, int32_t* count_out,
+                                 int32_t* nrel_out, double* f1_out, double* dcg_out, cudaStream_t stream) {
+  const int grid = (n_lists + 127) / 128;
+#define RLT_K4F(NP_, PF_) eval_cut_fast_kernel<NP_, kBits, PF_><<<grid, 128, 0, stream>>>(probs, labels, n_lists, L, k_out, count_out, nrel_out, f1_out, dcg_out)
+  if (L <= 64) RLT_K4F(1, true);
+  else if (L <= 320) RLT_K4F(5, true);
+  else if (L <= 512) RLT_K4F(8, true);
+  else RLT_K4F(16, false);       // 1024 positions: no second register set for the next list, occupancy hides the latency
+#undef RLT_K4F
+}
+
 template <typename F>
 static int dispatch_ni(int L, F&& f) {
   if (L <= 64) return f(std::integral_constant<int, 2>{});
@@ -919,11 +1099,28 @@ int rlt_eval_cut(const float* probs, const float* labels, int n_lists, int seq_l
   RLT_REQUIRE(mode == 0 || mode == 1, RLT_INVALID_ARG, "rlt_eval_cut: mode must be 0 (argmax cut) or 1 (BiCut rule)");
   const int grid = (n_lists + 127) / 128;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (mode == 0 && seq_len % 2 == 0 && ((reinterpret_cast<uintptr_t>(probs) | reinterpret_cast<uintptr_t>(labels)) & 7u) == 0) {
+    eval_cut_fast_launch<false>(probs, labels, n_lists, seq_len, k_out, count_out, nrel_out, f1_out, dcg_out, stream);
+    RLT_CHECK_LAUNCH();
+    return RLT_OK;
+  }
   RLT_TRY(dispatch_ni(seq_len, [&](auto ni) {
     eval_cut_kernel<decltype(ni)::value><<<grid, 128, 0, stream>>>(probs, labels, nullptr, nullptr, n_lists, seq_len, mode, k_out,
                                                                    count_out, nrel_out, f1_out, dcg_out);
     return RLT_OK;
   }));
+  RLT_CHECK_LAUNCH();
+  return RLT_OK;
+}
+
+int rlt_eval_cut_bits(const float* probs, const uint32_t* label_bits, int n_lists, int seq_len, int32_t* k_out,
+                      int32_t* count_out, int32_t* nrel_out, double* f1_out, double* dcg_out, rlt_stream_t stream_) {
+  RLT_REQUIRE(probs && label_bits && n_lists > 0 && seq_len > 0, RLT_INVALID_ARG, "rlt_eval_cut_bits: bad arguments");
+  RLT_REQUIRE(seq_len <= 1024, RLT_UNSUPPORTED_SHAPE, "rlt_eval_cut_bits: seq_len %d exceeds 1024", seq_len);
+  RLT_REQUIRE(seq_len % 2 == 0 && (reinterpret_cast<uintptr_t>(probs) & 7u) == 0, RLT_UNSUPPORTED_SHAPE,
+              "rlt_eval_cut_bits: seq_len %d must be even and probs 8-byte aligned", seq_len);
+  eval_cut_fast_launch<true>(probs, label_bits, n_lists, seq_len, k_out, count_out, nrel_out, f1_out, dcg_out,
+                             static_cast<cudaStream_t>(stream_));
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }

@@ -340,16 +340,23 @@ def reward_matrix(labels, rewards, metric="f1"):
                                   0 if metric == "f1" else 1, stream_ptr()), "rlt_reward_matrix")
 
 
-def eval_cut(probs, labels, mode=0):
-    """Returns (k int32[B], count int32[B], n_rel int32[B], f1 float64[B], dcg float64[B]) on the device."""
+def eval_cut(probs, labels, mode=0, label_bits=None):
+    """Returns (k int32[B], count int32[B], n_rel int32[B], f1 float64[B], dcg float64[B]) on the device.
+    labels: [B, L] float32 -- or None with label_bits = the words of pack_labels (mode 0, even L: rlt_eval_cut_bits)."""
     ensure_tables()
-    n_lists, seq_len = labels.shape
-    dev = labels.device
+    n_lists, seq_len = probs.shape[0], probs.shape[1]
+    dev = probs.device
     k = torch.empty(n_lists, dtype=torch.int32, device=dev)
     cnt = torch.empty_like(k)
     nrel = torch.empty_like(k)
     f1 = torch.empty(n_lists, dtype=torch.float64, device=dev)
     dcg = torch.empty_like(f1)
+    if label_bits is not None:
+        if mode != 0 or label_bits.shape != (n_lists, (seq_len + 31) // 32) or label_bits.element_size() != 4:
+            raise ValueError("label_bits: mode 0 and [n_lists, ceil(seq_len/32)] 32-bit words")
+        check(lib().rlt_eval_cut_bits(ptr(probs), ptr(label_bits), n_lists, seq_len, ptr(k), ptr(cnt), ptr(nrel), ptr(f1),
+                                      ptr(dcg), stream_ptr()), "rlt_eval_cut_bits")
+        return k, cnt, nrel, f1, dcg
     check(lib().rlt_eval_cut(ptr(probs), ptr(labels), n_lists, seq_len, mode, ptr(k), ptr(cnt), ptr(nrel), ptr(f1),
                              ptr(dcg), stream_ptr()), "rlt_eval_cut")
     return k, cnt, nrel, f1, dcg

@@ -145,6 +145,42 @@ def test_eval_cut_bit_exact_vs_reference_golden(L):
 
 
 @pytest.mark.parametrize("L", [300, 40])
+def test_eval_cut_from_label_bit_masks_is_bit_identical(L):
+    """rlt_eval_cut_bits (labels as rlt_pack_labels words) == rlt_eval_cut == the reference golden, every output."""
+    from rlt_b200 import ops
+    g = load_golden("metrics.npz")
+    y = torch.from_numpy(g[f"y_{L}"]).cuda()
+    p = torch.from_numpy(g[f"p_{L}"]).cuda()
+    a = ops.eval_cut(p, y, mode=0)
+    b = ops.eval_cut(p, None, mode=0, label_bits=ops.pack_labels(y))
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    assert np.array_equal(b[3].cpu().numpy()[2:], g[f"f1_{L}"][2:]) and np.array_equal(b[4].cpu().numpy()[2:], g[f"dcg_{L}"][2:])
+
+
+def test_eval_cut_every_cut_position_and_ragged_batches():
+    """Every k = 1..L (each leaf shape of numpy's pairwise tree: 1, 2, 3, 4 and 8 leaves, tails of 0..7 terms) at L = 300,
+    500 and 1000, odd L through the scalar kernel, and batch sizes that leave warps / CTAs partly empty."""
+    from rlt_b200 import ops
+    for L, B in ((300, 300), (500, 500), (1000, 1000), (301, 301), (300, 131), (40, 5)):
+        torch.manual_seed(L + B)
+        y = (torch.rand(B, L, device="cuda") < 0.2).float()
+        p = torch.rand(B, L, device="cuda") * 0.5
+        rows = torch.arange(B, device="cuda")
+        p[rows, rows % L] = 1.0                              # list b cuts at k = b % L + 1
+        k, cnt, nrel, f1, dcg = ops.eval_cut(p, y, mode=0)
+        kk = k.cpu().numpy().astype(np.int64)
+        assert np.array_equal(kk, np.arange(B) % L + 1)
+        yn = y.cpu().numpy()
+        assert np.array_equal(dcg.cpu().numpy(), np.array(O.dcg_per_list(yn, kk)))
+        assert np.array_equal(f1.cpu().numpy(), np.array(O.f1_per_list(yn, kk), dtype=np.float64))
+        assert np.array_equal(cnt.cpu().numpy(), np.array([int(yn[i, :kk[i]].sum()) for i in range(B)], dtype=np.int32))
+        if L % 2 == 0:
+            for u, v in zip((k, cnt, nrel, f1, dcg), ops.eval_cut(p, None, mode=0, label_bits=ops.pack_labels(y))):
+                assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("L", [300, 40])
 def test_metric_api_bit_exact(L):
     """Drop-in Metric.f1 / Metric.dcg (host numpy in, float out) equal the reference's numbers exactly."""
     from utils.metrics import Metric

@@ -34,6 +34,11 @@ def main():
         t = timeit(lambda: ops.eval_cut(p, y))
         b = n * (8 * L + 28)
         print(f"K4 eval_cut        L={L:4d} n={n}: {t*1e3:7.3f} ms  {n/t/1e6:8.1f} M lists/s  {b/t/1e9:7.0f} GB/s  {b/t/1e9/peak:.2f} of copy peak")
+        yb = ops.pack_labels(y)
+        t = timeit(lambda: ops.eval_cut(p, None, label_bits=yb))
+        b = n * (4 * L + 4 * yb.shape[1] + 28)
+        print(f"K4 eval_cut_bits   L={L:4d} n={n}: {t*1e3:7.3f} ms  {n/t/1e6:8.1f} M lists/s  {b/t/1e9:7.0f} GB/s  {b/t/1e9/peak:.2f} of copy peak (4 L + L/8 bytes per list)")
+        del yb
         if L <= 320:
             grad = torch.empty_like(z)
             lpl = torch.empty(n, device="cuda")
