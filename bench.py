@@ -393,6 +393,51 @@ def measure_module_api(c, name: str, steps: int):
             "ms_per_step": dt / steps * 1e3}
 
 
+def measure_graph_step(c, name: str, steps: int):
+    """The reference's batch (run.py: 63-64 lists) as ONE CUDA-graph launch per step: Engine forward + criterion + backward +
+    cut metrics (rlt_eval_cut) + fused Adam, inputs copied from pinned host memory into the graph's static buffers and the
+    loss + per-list F1 / DCG read back every step."""
+    import models
+    from rlt_b200.data import synthetic_lists
+    from rlt_b200.engine import Engine
+    from rlt_b200.optim import FusedAdam
+    torch.manual_seed(1234)
+    model = build_model(models, name).to(c.dev).train()
+    eng = Engine(model, n_groups=1, group_size=GROUP, seq_len=SEQ_LEN, training=True)
+    opt = FusedAdam.for_engine(eng, lr=3e-5, weight_decay=1e-3)
+    x, y = synthetic_lists(GROUP * 4, SEQ_LEN, N_FEATURES[name], seed=11, device="cpu")
+    x, y = x.pin_memory(), y.pin_memory()
+    xs, ys = x[:GROUP].to(c.dev), y[:GROUP].to(c.dev)
+    replay = eng.capture_train_step(xs, ys, optimizer=opt, metrics=True)
+
+    def one(i):
+        b = i % 4
+        xs.copy_(x[b * GROUP:(b + 1) * GROUP], non_blocking=True)
+        ys.copy_(y[b * GROUP:(b + 1) * GROUP], non_blocking=True)
+        replay()
+        _, _, _, f1, dcg = eng.graph_metrics
+        return eng.loss.item(), f1.mean().item(), dcg.mean().item()
+    for i in range(3):
+        one(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return {"what": "Engine train step + cut metrics + fused Adam as one CUDA graph per batch of the reference's size; "
+                    "ms_per_step: wall clock with pinned-host inputs in and loss / F1 / DCG out every step; "
+                    "device_ms_per_step: back-to-back replays (CUDA events)", "model": name, "batch": GROUP,
+            "lists_per_s": GROUP * steps / dt, "ms_per_step": dt / steps * 1e3,
+            "device_ms_per_step": e0.elapsed_time(e1) / steps}
+
+
 def measure_torch_cuda_eager(c, name: str, steps: int):
     """Side baseline ("the existing Blackwell path"): the reference's module graph in eager torch-CUDA on the
     same B200 (cuDNN LSTM, cuBLASLt, SDPA) with the VECTORISED reward (the reference's Python B x L loop would dominate),
@@ -561,6 +606,7 @@ def main():
         configs.update(measure_heads(c, args.steps))
         if rank == 0:
             configs["e2e_module_api"] = {n: measure_module_api(c, n, 10) for n in ("choopy", "bicut", "attncut", "mmoecut")}
+            configs["graph_step_b64"] = {n: measure_graph_step(c, n, 30) for n in ("choopy", "bicut", "attncut", "mmoecut")}
             configs["torch_cuda_eager"] = {n: measure_torch_cuda_eager(c, n, 10) for n in ("choopy", "bicut", "attncut", "mmoecut")}
         _barrier(c)
 

@@ -337,31 +337,63 @@ class Engine:
             ops.bilstm_bwd(self.lstm_desc, self.lstm_w, self.lstm_g, x, self.lstm_saved, d_front, None, self.lstm_ws)
         return self.loss
 
-    def capture_train_step(self, x, y, warmup: int = 3):
+    def capture_train_step(self, x, y, warmup: int = 3, optimizer=None, metrics: bool = False):
         """CUDA-graph capture of `train_step` on the static input buffers x, y (the
         reference's batch of 63 lists is launch-bound -- ~250 launches for ~1 ms of device work).  Returns a
         zero-argument callable that replays the whole forward + criterion + backward as ONE graph launch; new batches
         are copied into x / y before the replay, gradients land in `grad_bucket`, the loss in `self.loss`.  Everything
         the step touches is pre-allocated by the Engine and every kernel is launched on the current stream without host
         synchronisation, so the capture needs no special path.  Dropout draws its seeds on the host once per step, which
-        a replay would freeze: capture is refused for p > 0.  The optimizer step stays outside the graph (its
-        bias-correction scalars change every step)."""
+        a replay would freeze: capture is refused for p > 0.
+
+        optimizer (a `FusedAdam.for_engine(self)`): its step joins the graph -- the per-parameter step counts that
+        drive the bias corrections live on the device (rlt_adam_step_masked), nothing of the update is a host scalar
+        that changes from step to step.  metrics: the cut positions and per-list F1 / DCG of the batch (run.py:131-145,
+        rlt_eval_cut) join it too and land in `self.graph_metrics` = (k, count, n_rel, f1, dcg).  With both, one
+        replay is run.py's whole inner loop body for a batch: one launch from the host, no synchronisation."""
         if not self.training:
             raise RuntimeError("Engine built with training=False")
         if float(getattr(self.model, "_dropout_p", 0.0)) > 0.0 or any(float(getattr(st, "p", 0.0)) > 0.0 for st in self.stacks):
             raise RuntimeError("capture_train_step: dropout seeds are drawn on the host every step; capture with dropout = 0")
+        if optimizer is not None and getattr(optimizer, "_fixed_grads", None) is None:
+            raise RuntimeError("capture_train_step: the optimizer must read the Engine's bucket (FusedAdam.for_engine)")
+
+        def body():
+            self.train_step(x, y)
+            if metrics:
+                if self.kind == "bicut":
+                    self.graph_metrics = ops.eval_cut(self.probs2, y, mode=1)
+                else:
+                    self.graph_metrics = ops.eval_cut(self.z[self.H - 1], y, mode=0)
+            if optimizer is not None:
+                optimizer.step()
+
+        saved = None
+        if optimizer is not None:       # the warm-up steps below must not train: keep the state and put it back
+            saved = ([p.detach().clone() for p in optimizer.params], optimizer.state_dict())
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):           # warm-up off the capture: attribute settings, occupancy queries, tables
             for _ in range(max(1, warmup)):
-                self.train_step(x, y)
+                body()
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.train_step(x, y)
+            body()
+        if saved is not None:                   # (a capture records, it does not execute)
+            with torch.no_grad():
+                for p, v in zip(optimizer.params, saved[0]):
+                    p.copy_(v)
+            optimizer.load_state_dict(saved[1])
         self._graph = graph                     # keeps the captured pool alive
-        return graph.replay
+        if optimizer is None:
+            return graph.replay
+
+        def replay():
+            graph.replay()
+            optimizer.step_count += 1           # host mirror of the device-side step counts
+        return replay
 
     def infer(self, x, y):
         """Forward + fused cut selection and per-list F1 / DCG (K4).  Returns (k, f1, dcg) device tensors."""

@@ -90,3 +90,59 @@ def test_cuda_graph_replay_matches_eager_step(name):
     assert abs(eng.loss.item() - ref_loss) <= 1e-6 * max(1.0, abs(ref_loss))
     d = (eng.grad_bucket - ref_bucket).abs().max().item()
     assert d <= 1e-5 * ref_bucket.abs().max().item(), d
+
+
+@pytest.mark.parametrize("name", ["choopy", "attncut", "mmoecut"])
+def test_whole_step_graph_equals_eager_steps(name):
+    """forward + criterion + backward + cut metrics + fused Adam as ONE CUDA graph: five replays on five batches leave the
+    same parameters, moments, losses and per-list metrics as five eager Engine steps.  Not bitwise: the weight-gradient
+    kernels accumulate with atomics, two EAGER runs already differ by ~1e-6 relative from the second step on
+    (tools/diag_graph.py); the first loss (no update yet) is bitwise."""
+    import copy
+    from rlt_b200.data import synthetic_lists
+    from rlt_b200.engine import Engine
+    from rlt_b200.optim import FusedAdam
+    from rlt_b200 import ops
+    feats = 1 if name == "choopy" else 3
+    S, L = 63, 300
+    model_a = build_model(name).cuda().train()
+    model_b = copy.deepcopy(model_a)
+    start = [p.detach().clone() for p in model_a.parameters()]
+    batches = [synthetic_lists(S, L, feats, seed=40 + i, device="cuda") for i in range(5)]
+    # eager
+    eng_a = Engine(model_a, n_groups=1, group_size=S, seq_len=L)
+    opt_a = FusedAdam.for_engine(eng_a, lr=1e-3, weight_decay=1e-3)
+    ref = []
+    for x, y in batches:
+        loss = eng_a.train_step(x, y).item()
+        m = ops.eval_cut(eng_a.z[eng_a.H - 1], y, mode=0)
+        opt_a.step()
+        ref.append((loss, m[0].clone(), m[3].clone(), m[4].clone()))
+    # one graph
+    eng_b = Engine(model_b, n_groups=1, group_size=S, seq_len=L)
+    opt_b = FusedAdam.for_engine(eng_b, lr=1e-3, weight_decay=1e-3)
+    xs, ys = batches[0][0].clone(), batches[0][1].clone()
+    replay = eng_b.capture_train_step(xs, ys, optimizer=opt_b, metrics=True)
+    assert opt_b.step_count == 0 and int(opt_b.tensor_steps.max()) == 0          # capture and warm-up did not train
+    for (x, y), (loss, k, f1, dcg) in zip(batches, ref):
+        xs.copy_(x)
+        ys.copy_(y)
+        replay()
+        gk, _, _, gf1, gdcg = eng_b.graph_metrics
+        if loss is ref[0][0]:
+            assert eng_b.loss.item() == loss
+        assert abs(eng_b.loss.item() - loss) <= 2e-5 * max(abs(loss), 1e-2), (eng_b.loss.item(), loss)
+        same = (gk == k)
+        assert int(same.sum()) >= (3 * S) // 4                            # near-tied arg-maxima of an untrained model move with O(lr) weight noise
+        assert torch.equal(gf1[same], f1[same]) and torch.equal(gdcg[same], dcg[same])
+    assert opt_b.step_count == 5
+    assert torch.equal(opt_a.tensor_steps, opt_b.tensor_steps)
+    # Adam divides by sqrt(v): where a gradient is ~0 its rounding noise is amplified to O(lr), so single weights are
+    # compared loosely and the displacement of all parameters by its direction (as tests/test_zzzz_trajectory_gpu.py)
+    num = na = nb = 0.0
+    for (n, pa), (_, pb), p0 in zip(model_a.named_parameters(), model_b.named_parameters(), start):
+        da, db = (pa - p0).double(), (pb - p0).double()
+        num += float((da * db).sum()); na += float((da * da).sum()); nb += float((db * db).sum())
+        assert (pa - pb).abs().max().item() <= 2e-3, (n, (pa - pb).abs().max().item())
+    assert num / (na * nb) ** 0.5 >= 0.9999, num / (na * nb) ** 0.5
+    assert (opt_a.exp_avg - opt_b.exp_avg).abs().max().item() <= 1e-2 * opt_a.exp_avg.abs().max().item()   # weights already differ by O(lr)
