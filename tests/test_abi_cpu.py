@@ -17,6 +17,27 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.rlt_version()
 
 
+def test_every_export_is_bound_with_the_header_prototype():
+    """ctypes argtypes / restype of every function come from include/rlt_b200.h (rlt_b200/_lib.py: prototypes()): a call
+    whose arguments do not convert to the declared C types raises ArgumentError on the host."""
+    lib = _lib.load()
+    protos = _lib.prototypes()
+    assert set(protos) == set(_lib.declared_symbols())
+    for name, (restype, argtypes) in protos.items():
+        fn = getattr(lib, name)
+        assert fn.restype is restype and list(fn.argtypes) == argtypes, name
+    assert protos["rlt_version"] == (ctypes.c_char_p, [])
+    assert protos["rlt_encoder_layer_saved_bytes"] == (ctypes.c_size_t, [ctypes.c_void_p])
+    assert protos["rlt_adam_step_masked"][1][12:18] == [ctypes.c_double] * 6
+    assert protos["rlt_pair_softmax_fwd"][1].count(ctypes.c_float) == 1
+    with pytest.raises(ctypes.ArgumentError):
+        lib.rlt_set_option(b"gemm_backend", 1.5)                 # a float where the header says int
+    with pytest.raises(ctypes.ArgumentError):
+        lib.rlt_round_tf32(None, None, "4", None)                # a str where the header says size_t
+    with pytest.raises(TypeError):
+        lib.rlt_set_option(b"gemm_backend")                      # too few arguments
+
+
 def test_status_codes_and_last_error_without_gpu():
     lib = _lib.load()
     assert lib.rlt_set_option(b"no_such_option", 1) == -1
@@ -75,7 +96,7 @@ def test_probe_modules_match_reference_layout():
 
 
 def test_python_call_sites_match_header_arity():
-    """The ctypes calls carry no argtypes, so a drifted argument list would only show up as garbage on the GPU: every
+    """Static twin of the run-time argtypes check (which only fires when a call site executes): every
     `<lib>.rlt_*(...)` call in the host package must pass exactly as many arguments as include/rlt_b200.h declares."""
     import ast
     import re
