@@ -101,7 +101,8 @@ struct FfnFwdParams {
 template <int D>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FfnFwdCfg<D>::THREADS, 1)
 ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1,
-               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmH, const FfnFwdParams p) {
+               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmH,
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmU2, const FfnFwdParams p) {
   using Cfg = FfnFwdCfg<D>;
   constexpr int CH = Cfg::CH, NS1 = Cfg::NS1, NS2 = Cfg::NS2, YB = Cfg::YB;
   constexpr int SC = CH / 4;       // S columns per epilogue thread
@@ -365,12 +366,8 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
             for (int q4 = 0; q4 < 2; ++q4)
               *reinterpret_cast<uint4*>(st_out + lane * 32 + (q4 << 4)) = make_uint4(hp[4 * q4], hp[4 * q4 + 1], hp[4 * q4 + 2], hp[4 * q4 + 3]);
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmH, st_out, j * CH + cq * SC, tile * 2 * Cfg::BM + int(rank) * Cfg::BM + quarter * 32);
-            tma_store_commit();
-          }
+          // (the proxy fence and the TMA store are issued AFTER the H hand-over below: by then the staging writes have
+          // landed and the fence costs nothing on the path MMA2 waits for)
         }
         if (dbg) p.dbg[g * 16 + 11] = clock64();
         mbar_wait(&h_empty[buf], u ^ 1);        // MMA2 of chunk g - 2 has consumed this H buffer
@@ -387,6 +384,14 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(h_full_r[buf]);
+        if (p.h_out != nullptr) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmH, st_out, j * CH + cq * SC, tile * 2 * Cfg::BM + int(rank) * Cfg::BM + quarter * 32);
+            tma_store_commit();
+          }
+        }
         if (dbg) p.dbg[g * 16 + 13] = clock64();
       }
       // ---------------- Z epilogue: + b2 + residual -> LayerNorm -> out ----------------
@@ -418,27 +423,32 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
           }
       };
-      // a [32 x 32] block of this warp from registers (thread = row) to global memory through the staging tile
-      auto store_block = [&](float* gbase, const float (&val)[32], int zb) {
+      // a [32 x 32] block of this warp from registers (thread = row) to global memory: two [32 rows x 16 columns] boxes
+      // through the staging tile, written by the copy engine (TMA store, SWIZZLE_64B).  Per-thread stores -- even the
+      // coalesced 8 rows x 64 bytes per instruction of the first version -- held the warp for 2 300 cycles per 64 KB
+      // tile and tensor (tools/bench_ffn.py --timeline); rows beyond T are clipped by the tensor map.
+      auto store_block = [&](const CUtensorMap* tm, const float (&val)[32], int zb) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+          if (lane == 0) tma_store_wait_read<0>();               // the previous box has left the staging tile
+          __syncwarp();
 #pragma unroll
           for (int u4 = 0; u4 < 4; ++u4)
             *reinterpret_cast<float4*>(st_out + lane * 64 + ((u4 ^ sw) << 4)) =
                 make_float4(val[16 * h + 4 * u4], val[16 * h + 4 * u4 + 1], val[16 * h + 4 * u4 + 2], val[16 * h + 4 * u4 + 3]);
+          fence_proxy_async_smem();
           __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const long long rg = row_base + 8 * i + crow;
-            const float4 t4 = *reinterpret_cast<const float4*>(st_out + c_off[i]);
-            if (rg < p.T) *reinterpret_cast<float4*>(gbase + size_t(rg) * D + cq * ZC + 32 * zb + 16 * h + 4 * cu) = t4;
+          if (lane == 0) {
+            tma_store_2d(tm, st_out, cq * ZC + 32 * zb + 16 * h, int(row_base));
+            tma_store_commit();
           }
-          __syncwarp();
         }
       };
       load_residual(0);                                            // issued before waiting for the last MMA2
+      const bool zdbg = p.dbg != nullptr && pair == 0 && leader && ew == 0 && lane == 0 && g - 1 < 64;
       mbar_wait(z_full, tt & 1);
       tc_fence_after();
+      if (zdbg) p.dbg[(g - 1) * 16 + 3] = clock64();
       float uv[32];
       float s = 0.f;
 #pragma unroll
@@ -451,9 +461,9 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(z_empty_r);         // Z is in registers: the next tile may accumulate
           }
-          if (lane == 0) tma_store_wait_read<0>();                 // (training) the last hidden store has left the staging tile
-          __syncwarp();
         }
+        if (lane == 0) tma_store_wait_read<0>();                   // the last store (hidden / previous block) has left the staging tile
+        __syncwarp();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -469,9 +479,11 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
           }
           __syncwarp();
         }
-        if (p.u2 != nullptr) store_block(p.u2, uv, zb);
+        if (zdbg) p.dbg[(g - 1) * 16 + 7] = clock64();
+        if (p.u2 != nullptr) store_block(&tmU2, uv, zb);
         if constexpr (NB > 1) tmem_st32f(lane_tmem + Cfg::COL_Z + cq * ZC + 32 * zb, uv);
       }
+      if (zdbg) p.dbg[(g - 1) * 16 + 14] = clock64();
       if constexpr (NB > 1) tmem_st_wait();
       // row statistics across the four column quarters (warps quarter, quarter + 4, ...): two-pass like torch
       red0[cq * 32 + lane] = s;
@@ -490,6 +502,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       red1[cq * 32 + lane] = q;
       asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
       const float rstd = rsqrtf((red1[lane] + red1[32 + lane] + red1[64 + lane] + red1[96 + lane]) * (1.f / D) + p.eps);
+      if (zdbg) p.dbg[(g - 1) * 16 + 15] = clock64();
 #pragma unroll
       for (int zb = 0; zb < NB; ++zb) {
         if constexpr (NB > 1) tmem_ld32(lane_tmem + Cfg::COL_Z + cq * ZC + 32 * zb, uv);
@@ -504,7 +517,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
             if (lane == 0) mbar_arrive_cluster(z_empty_r);
           }
         }
-        store_block(p.out, uv, zb);
+        store_block(&tmOut, uv, zb);
       }
       if (p.stats != nullptr && cq == 0 && live) {
         p.stats[2 * size_t(row)] = mu;

@@ -499,8 +499,13 @@ static int ffn_fwd_fused_launch(const __half* y16, const float* y, const __half*
                                 const float* b2, const float* gamma, const float* beta, float* out, float* u2, float* stats,
                                 __half* h_out, int T, int f, float eps, cudaStream_t stream, int tag) {
   using Cfg = FfnFwdCfg<D>;
-  CUtensorMap tmY, tmW1, tmW2, tmH;
+  CUtensorMap tmY, tmW1, tmW2, tmH, tmOut, tmU2;
   RLT_TRY(make_tmap_h(&tmY, y16, T, D, D, Cfg::BM));
+  // out / pre-norm sums: per-warp [32 rows x 16 columns] fp32 boxes (64-byte rows, SWIZZLE_64B) stored by the copy engine
+  RLT_TRY(make_tmap_any(&tmOut, out, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, T, D, D, 32, false, 16, CU_TENSOR_MAP_SWIZZLE_64B));
+  tmU2 = tmOut;
+  if (u2 != nullptr)
+    RLT_TRY(make_tmap_any(&tmU2, u2, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, T, D, D, 32, false, 16, CU_TENSOR_MAP_SWIZZLE_64B));
   RLT_TRY(make_tmap_h(&tmW1, w1h, f, D, D, Cfg::CH / 2));
   RLT_TRY(make_tmap_h(&tmW2, w2h, D, f, f, D / 2));
   tmH = tmY;       // placeholder when the hidden is not saved (never dereferenced then)
@@ -535,7 +540,7 @@ static int ffn_fwd_fused_launch(const __half* y16, const float* y, const __half*
   prm.h_out = h_out; prm.T = T; prm.F = f; prm.eps = eps;
   prm.dbg = g_ffn_dbg;
   TimeScope scope(tag, stream);
-  ffn_fwd_kernel<D><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmY, tmW1, tmW2, tmH, prm);
+  ffn_fwd_kernel<D><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmY, tmW1, tmW2, tmH, tmOut, tmU2, prm);
   RLT_CHECK_LAUNCH();
   return RLT_OK;
 }

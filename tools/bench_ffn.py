@@ -59,7 +59,7 @@ if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "--timel
     main()
 
 
-def timeline():
+def timeline(train=False):
     """Per-chunk clock64 stamps of pair 0 (leader CTA): where the MMA thread and the first epilogue warp spend a chunk."""
     import ctypes as C
     T, d, f = 256 * 74 * 4, 128, 2048
@@ -72,20 +72,22 @@ def timeline():
     out = torch.empty_like(y)
     buf = torch.zeros(64 * 16, dtype=torch.int64, device="cuda")
     lib = ops.lib()
+    kw = dict(u2=torch.empty_like(y), stats=torch.empty(T, 2, device="cuda"),
+              h_out=torch.empty(T, f, device="cuda", dtype=torch.float16)) if train else {}
     for _ in range(2):
-        ops.ffn_fused_fwd(y.half(), y, w1h, z, w2h, zd, zd + 1, zd, out)
+        ops.ffn_fused_fwd(y.half(), y, w1h, z, w2h, zd, zd + 1, zd, out, **kw)
     lib.rlt_ffn_fused_set_timeline(C.c_void_p(buf.data_ptr()))
-    ops.ffn_fused_fwd(y.half(), y, w1h, z, w2h, zd, zd + 1, zd, out)
+    ops.ffn_fused_fwd(y.half(), y, w1h, z, w2h, zd, zd + 1, zd, out, **kw)
     torch.cuda.synchronize()
     lib.rlt_ffn_fused_set_timeline(C.c_void_p(0))
     t = buf.view(64, 16).cpu().numpy()
     t0 = t[0, 0]
-    names = ["mma1:top", "waits", "issued", "-", "mma2:top", "waits", "issued", "-", "epi:top", "s_full",
-             "S in regs", "math done", "h_empty", "H written"]
+    names = ["mma1:top", "waits", "issued", "Z:full", "mma2:top", "waits", "issued", "Z:u done", "epi:top", "s_full",
+             "S in regs", "math done", "h_empty", "H written", "Z:u2 out", "Z:stats"]
     print("chunk " + " ".join(f"{n:>11s}" for n in names))
     for gidx in range(40):
-        print(f"{gidx:5d} " + " ".join(f"{int(t[gidx, k] - t0) if t[gidx, k] else 0:11d}" for k in range(14)))
+        print(f"{gidx:5d} " + " ".join(f"{int(t[gidx, k] - t0) if t[gidx, k] else 0:11d}" for k in range(16)))
 
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "--timeline":
-    timeline()
+    timeline(train=len(sys.argv) > 2 and sys.argv[2] == "train")
