@@ -190,17 +190,24 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       };
       uint32_t st1 = 0, ph1 = 0, yb = 0, yph = 0;
       int j = 0, tile = pair;
+      // The y tile of the NEXT tile is requested in the middle of the current one (two buffers): it is the only operand
+      // that comes from HBM, and at the tile boundary its latency under the hidden-store write stream held up the W1 / W2
+      // loads queued behind it by ~2 500 cycles (tools/bench_ffn.py --timeline train).  With one buffer (d = 256) it can
+      // only be requested at the boundary.
+      auto load_y = [&]() {
+        const int row0 = tile * 2 * Cfg::BM + int(rank) * Cfg::BM;
+        mbar_wait(&y_empty[yb], yph ^ 1);
+        if (leader) mbar_expect_tx(&y_full[yb], 2 * Cfg::Y_BYTES);
+        const uint32_t bar = mapa_u32(smem_u32(&y_full[yb]), 0);
+        for (int kb = 0; kb < D / 64; ++kb)
+          tma_load_2d_pair(sY + yb * Cfg::Y_BYTES + kb * Cfg::Y_BOX_BYTES, &tmY, bar, kb * 64, row0);
+        if (++yb == YB) { yb = 0; yph ^= 1; }
+        tile += n_pairs;
+      };
+      constexpr bool kEarlyY = YB > 1;
+      if (kEarlyY && total > 0) load_y();
       for (uint32_t g = 0; g < total; ++g) {
-        if (j == 0) {
-          const int row0 = tile * 2 * Cfg::BM + int(rank) * Cfg::BM;
-          mbar_wait(&y_empty[yb], yph ^ 1);
-          if (leader) mbar_expect_tx(&y_full[yb], 2 * Cfg::Y_BYTES);
-          const uint32_t bar = mapa_u32(smem_u32(&y_full[yb]), 0);
-          for (int kb = 0; kb < D / 64; ++kb)
-            tma_load_2d_pair(sY + yb * Cfg::Y_BYTES + kb * Cfg::Y_BOX_BYTES, &tmY, bar, kb * 64, row0);
-          if (++yb == YB) { yb = 0; yph ^= 1; }
-          tile += n_pairs;
-        }
+        if (kEarlyY ? (j == n_chunks / 2 && g + n_chunks / 2 < total) : (j == 0)) load_y();
         {
           mbar_wait(&w1_empty[st1], ph1 ^ 1);
           if (leader) mbar_expect_tx(&w1_full[st1], 2 * Cfg::W1_BYTES);
@@ -234,11 +241,12 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       for (uint32_t g = 0; g < total; ++g) {
         const uint32_t buf1 = g & 1, u1 = (g >> 1) & 1;            // S buffer of chunk g
         const bool dbg = p.dbg != nullptr && pair == 0 && g < 64;
-        if (dbg) p.dbg[g * 16 + 0] = clock64();
+        if (dbg) p.dbg[g * 24 + 0] = clock64();
         if (j == 0) mbar_wait_cluster(&y_full[yb], yph);
         mbar_wait_cluster(&w1_full[st1], ph1);
+        if (dbg) p.dbg[g * 24 + 18] = clock64();
         mbar_wait_cluster(&s_empty[buf1], u1 ^ 1);
-        if (dbg) p.dbg[g * 16 + 1] = clock64();
+        if (dbg) p.dbg[g * 24 + 1] = clock64();
         tc_fence_after();
         const uint32_t a1 = y_addr + yb * Cfg::Y_BYTES, b1a = w1_addr + st1 * Cfg::W1_BYTES;
 #pragma unroll
@@ -259,7 +267,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
           ++j;
         }
         if (++st1 == NS1) { st1 = 0; ph1 ^= 1; }
-        if (dbg) p.dbg[g * 16 + 2] = clock64();
+        if (dbg) p.dbg[g * 24 + 2] = clock64();
       }
     }
     __syncwarp();
@@ -275,11 +283,13 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       for (uint32_t c = 0; c < total; ++c) {
         const uint32_t buf2 = c & 1, u2 = (c >> 1) & 1;            // H buffer of chunk c
         const bool dbg = p.dbg != nullptr && pair == 0 && c < 64;
-        if (dbg) p.dbg[c * 16 + 4] = clock64();
+        if (dbg) p.dbg[c * 24 + 4] = clock64();
         mbar_wait_cluster(&w2_full[st2], ph2);
+        if (dbg) p.dbg[c * 24 + 16] = clock64();
         mbar_wait_cluster(&h_full[buf2], u2);
+        if (dbg) p.dbg[c * 24 + 17] = clock64();
         if (cj == 0) mbar_wait_cluster(z_empty, (ztile & 1) ^ 1);
-        if (dbg) p.dbg[c * 16 + 5] = clock64();
+        if (dbg) p.dbg[c * 24 + 5] = clock64();
         tc_fence_after();
         const uint32_t b2a = w2_addr + st2 * Cfg::W2_BYTES;
         const uint32_t a_t = tmem_base + Cfg::COL_H + buf2 * (CH / 2);
@@ -300,7 +310,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
           ++cj;
         }
         if (++st2 == NS2) { st2 = 0; ph2 ^= 1; }
-        if (dbg) p.dbg[c * 16 + 6] = clock64();
+        if (dbg) p.dbg[c * 24 + 6] = clock64();
       }
     }
     __syncwarp();
@@ -325,9 +335,9 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       for (int j = 0; j < n_chunks; ++j, ++g) {
         const uint32_t buf = g & 1, u = (g >> 1) & 1;
         const bool dbg = p.dbg != nullptr && pair == 0 && leader && ew == 0 && lane == 0 && g < 64;
-        if (dbg) p.dbg[g * 16 + 8] = clock64();
+        if (dbg) p.dbg[g * 24 + 8] = clock64();
         mbar_wait(&s_full[buf], u);
-        if (dbg) p.dbg[g * 16 + 9] = clock64();
+        if (dbg) p.dbg[g * 24 + 9] = clock64();
         tc_fence_after();
         float v[SC];
         if constexpr (SC == 32) tmem_ld32(lane_tmem + Cfg::COL_S + buf * CH + cq * SC, v);
@@ -335,7 +345,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(s_empty_r[buf]);          // S_j is in registers
-        if (dbg) p.dbg[g * 16 + 10] = clock64();
+        if (dbg) p.dbg[g * 24 + 10] = clock64();
         // ---- bias + relu + fp16 pack (two hidden units per 32-bit word = the TMEM A-operand layout): packed fp32x2
         // adds, one pack per pair, relu on the packed halves (max commutes with the rounding)
         const float4* bias = reinterpret_cast<const float4*>(sB1 + j * CH + cq * SC);
@@ -369,9 +379,9 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
           // (the proxy fence and the TMA store are issued AFTER the H hand-over below: by then the staging writes have
           // landed and the fence costs nothing on the path MMA2 waits for)
         }
-        if (dbg) p.dbg[g * 16 + 11] = clock64();
+        if (dbg) p.dbg[g * 24 + 11] = clock64();
         mbar_wait(&h_empty[buf], u ^ 1);        // MMA2 of chunk g - 2 has consumed this H buffer
-        if (dbg) p.dbg[g * 16 + 12] = clock64();
+        if (dbg) p.dbg[g * 24 + 12] = clock64();
         tc_fence_after();
         if constexpr (SC == 32) {
           const uint32_t(&h16)[16] = hp;
@@ -392,7 +402,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
             tma_store_commit();
           }
         }
-        if (dbg) p.dbg[g * 16 + 13] = clock64();
+        if (dbg) p.dbg[g * 24 + 13] = clock64();
       }
       // ---------------- Z epilogue: + b2 + residual -> LayerNorm -> out ----------------
       // This warp owns a [32 rows x 32 columns] fp32 block of the tile (thread = row in tensor memory).  Row-per-thread
@@ -448,7 +458,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       const bool zdbg = p.dbg != nullptr && pair == 0 && leader && ew == 0 && lane == 0 && g - 1 < 64;
       mbar_wait(z_full, tt & 1);
       tc_fence_after();
-      if (zdbg) p.dbg[(g - 1) * 16 + 3] = clock64();
+      if (zdbg) p.dbg[(g - 1) * 24 + 3] = clock64();
       float uv[32];
       float s = 0.f;
 #pragma unroll
@@ -479,11 +489,11 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
           }
           __syncwarp();
         }
-        if (zdbg) p.dbg[(g - 1) * 16 + 7] = clock64();
+        if (zdbg) p.dbg[(g - 1) * 24 + 7] = clock64();
         if (p.u2 != nullptr) store_block(&tmU2, uv, zb);
         if constexpr (NB > 1) tmem_st32f(lane_tmem + Cfg::COL_Z + cq * ZC + 32 * zb, uv);
       }
-      if (zdbg) p.dbg[(g - 1) * 16 + 14] = clock64();
+      if (zdbg) p.dbg[(g - 1) * 24 + 14] = clock64();
       if constexpr (NB > 1) tmem_st_wait();
       // row statistics across the four column quarters (warps quarter, quarter + 4, ...): two-pass like torch
       red0[cq * 32 + lane] = s;
@@ -502,7 +512,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       red1[cq * 32 + lane] = q;
       asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
       const float rstd = rsqrtf((red1[lane] + red1[32 + lane] + red1[64 + lane] + red1[96 + lane]) * (1.f / D) + p.eps);
-      if (zdbg) p.dbg[(g - 1) * 16 + 15] = clock64();
+      if (zdbg) p.dbg[(g - 1) * 24 + 15] = clock64();
 #pragma unroll
       for (int zb = 0; zb < NB; ++zb) {
         if constexpr (NB > 1) tmem_ld32(lane_tmem + Cfg::COL_Z + cq * ZC + 32 * zb, uv);

@@ -70,7 +70,7 @@ def timeline(train=False):
     z = torch.zeros(f, device="cuda")
     zd = torch.zeros(d, device="cuda")
     out = torch.empty_like(y)
-    buf = torch.zeros(64 * 16, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(64 * 24, dtype=torch.int64, device="cuda")
     lib = ops.lib()
     kw = dict(u2=torch.empty_like(y), stats=torch.empty(T, 2, device="cuda"),
               h_out=torch.empty(T, f, device="cuda", dtype=torch.float16)) if train else {}
@@ -80,13 +80,13 @@ def timeline(train=False):
     ops.ffn_fused_fwd(y.half(), y, w1h, z, w2h, zd, zd + 1, zd, out, **kw)
     torch.cuda.synchronize()
     lib.rlt_ffn_fused_set_timeline(C.c_void_p(0))
-    t = buf.view(64, 16).cpu().numpy()
+    t = buf.view(64, 24).cpu().numpy()
     t0 = t[0, 0]
     names = ["mma1:top", "waits", "issued", "Z:full", "mma2:top", "waits", "issued", "Z:u done", "epi:top", "s_full",
-             "S in regs", "math done", "h_empty", "H written", "Z:u2 out", "Z:stats"]
+             "S in regs", "math done", "h_empty", "H written", "Z:u2 out", "Z:stats", "m2:w2_full", "m2:h_full", "m1:w1_full"]
     print("chunk " + " ".join(f"{n:>11s}" for n in names))
     for gidx in range(40):
-        print(f"{gidx:5d} " + " ".join(f"{int(t[gidx, k] - t0) if t[gidx, k] else 0:11d}" for k in range(16)))
+        print(f"{gidx:5d} " + " ".join(f"{int(t[gidx, k] - t0) if t[gidx, k] else 0:11d}" for k in range(19)))
 
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "--timeline":
