@@ -11,8 +11,21 @@ namespace rlt {
 
 constexpr int kGatherThreads = 256;
 
-// One CTA per output list (grid-stride): the X row (L*F floats) and the label row (L floats or ceil(L/32) words)
-// of list index[o] are copied with 128-bit accesses when the row length allows it.
+// One WARP per output list (grid-stride over warps): the X row (L*F floats) and the label row (L floats or
+// ceil(L/32) words) of list index[o] are copied with 128-bit accesses when the row length allows it, four loads in
+// flight per lane before the first store.  (The first version gave a list to a whole CTA: at L = 300, F = 1 a row is 75
+// float4, so 181 of 256 threads idled behind one dependent load each -- 0.21-0.47 of the copy peak,
+// profiles/r02_bench_data.txt.)
+template <typename T>
+__device__ __forceinline__ void warp_copy(const T* __restrict__ src, T* __restrict__ dst, int n, int lane) {
+  int i = lane;
+  for (; i + 96 < n; i += 128) {
+    const T a = __ldg(src + i), b = __ldg(src + i + 32), c = __ldg(src + i + 64), d = __ldg(src + i + 96);
+    dst[i] = a; dst[i + 32] = b; dst[i + 64] = c; dst[i + 96] = d;
+  }
+  for (; i < n; i += 32) dst[i] = __ldg(src + i);
+}
+
 template <bool kVec4>
 __global__ void __launch_bounds__(kGatherThreads) gather_lists_kernel(const float* __restrict__ x,
                                                                       const float* __restrict__ y,
@@ -22,35 +35,31 @@ __global__ void __launch_bounds__(kGatherThreads) gather_lists_kernel(const floa
                                                                       float* __restrict__ y_out, int32_t* __restrict__ status) {
   const int row_x = seq_len * n_features;
   const int words = (seq_len + 31) >> 5;
-  for (int o = blockIdx.x; o < n_out; o += gridDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * kGatherThreads) >> 5;
+  for (int o = (blockIdx.x * kGatherThreads + threadIdx.x) >> 5; o < n_out; o += warps) {
     const int64_t src = index != nullptr ? index[o] : int64_t(o);
     if (src < 0 || src >= n_src) {                       // IndexError on the host side
-      if (threadIdx.x == 0) atomicOr(status, 1);
+      if (lane == 0) atomicOr(status, 1);
       continue;
     }
     const float* xs = x + size_t(src) * row_x;
     float* xd = x_out + size_t(o) * row_x;
-    if (kVec4) {
-      const float4* s4 = reinterpret_cast<const float4*>(xs);
-      float4* d4 = reinterpret_cast<float4*>(xd);
-      for (int i = threadIdx.x; i < (row_x >> 2); i += kGatherThreads) d4[i] = __ldg(s4 + i);
-    } else {
-      for (int i = threadIdx.x; i < row_x; i += kGatherThreads) xd[i] = __ldg(xs + i);
-    }
+    if (kVec4) warp_copy(reinterpret_cast<const float4*>(xs), reinterpret_cast<float4*>(xd), row_x >> 2, lane);
+    else warp_copy(xs, xd, row_x, lane);
     if (y_out == nullptr) continue;
     float* yd = y_out + size_t(o) * seq_len;
     if (y_bits != nullptr) {
       const uint32_t* ws = y_bits + size_t(src) * words;
-      for (int i = threadIdx.x; i < seq_len; i += kGatherThreads) yd[i] = float((__ldg(ws + (i >> 5)) >> (i & 31)) & 1u);
+      for (int w = 0; w < words; ++w) {                  // one word serves the 32 lanes (broadcast load)
+        const int i = w * 32 + lane;
+        const uint32_t m = __ldg(ws + w);
+        if (i < seq_len) yd[i] = float((m >> lane) & 1u);
+      }
     } else {
       const float* ys = y + size_t(src) * seq_len;
-      if (kVec4) {
-        const float4* s4 = reinterpret_cast<const float4*>(ys);
-        float4* d4 = reinterpret_cast<float4*>(yd);
-        for (int i = threadIdx.x; i < (seq_len >> 2); i += kGatherThreads) d4[i] = __ldg(s4 + i);
-      } else {
-        for (int i = threadIdx.x; i < seq_len; i += kGatherThreads) yd[i] = __ldg(ys + i);
-      }
+      if (kVec4) warp_copy(reinterpret_cast<const float4*>(ys), reinterpret_cast<float4*>(yd), seq_len >> 2, lane);
+      else warp_copy(ys, yd, seq_len, lane);
     }
   }
 }
@@ -93,8 +102,8 @@ int rlt_gather_lists(const float* x, const float* labels, const uint32_t* label_
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_out) | reinterpret_cast<uintptr_t>(labels) |
                          reinterpret_cast<uintptr_t>(labels_out)) & 15u) == 0;
   const bool vec4 = aligned && row_x % 4 == 0 && seq_len % 4 == 0;
-  int grid = num_sms() * 8;
-  if (grid > n_out) grid = n_out;
+  int grid = num_sms() * 8;                              // 8 CTAs x 8 warps per SM, one list per warp and pass
+  if (grid > (n_out + 7) / 8) grid = (n_out + 7) / 8;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (vec4)
     gather_lists_kernel<true><<<grid, kGatherThreads, 0, stream>>>(x, labels, label_bits, index, n_src, n_out, seq_len, n_features,
