@@ -16,7 +16,9 @@
 //            3xTF32 products of the mma.sync kernels)                                   -> tensor memory, 128 columns
 //   softmax  (4 warps, thread = query row): its 64 valid columns -> max, exp2, sum -> P as fp16 pairs written back to
 //            TENSOR MEMORY (the invalid half of the row as zeros)
-//   MMA      O = P . V with P as the TMEM A operand, eight K = 16 steps, N = dh         -> tensor memory, dh columns
+//   MMA      O' = P' . [V_pos0 | V_pos1] with P' as the TMEM A operand: a row keeps only the 64 probabilities of its own
+//            position (K = 64: four K = 16 steps instead of eight over a zero-padded 128-key row) against BOTH positions'
+//            values side by side (N = 2 dh); rows of position p read columns [p dh, p dh + dh)   -> tensor memory, 2 dh columns
 //   epilogue the softmax warps scale O by 1 / sum and store it through a staging transposition (8 rows x 64 B per store
 //            instruction); the log-sum-exp of the pair's heads goes to lse[token, :] for the backward.
 // Warps: 0 TMA, 1 MMA issuer (scores), 2-5 convert, 6-9 softmax, 10-13 epilogue (softmax statistics handed over in shared
@@ -52,8 +54,10 @@ struct AttnTcCfg {
   static constexpr size_t SMEM_BYTES = 1024 + OFF_BARS + N_BARS * 8 + 16;
   static constexpr int THREADS = 32 * 15;                            // TMA | MMA(S) | 4 convert | 4 softmax | 4 epilogue | MMA(PV)
   // tensor memory columns: NS x 128 for S, with P (64 packed columns) written IN PLACE over the first half of the stage's
-  // score columns (a lane only ever touches its own row: it has its scores in registers before it writes P) | NS x DH for O
+  // score columns (a lane only ever touches its own row: it has its scores in registers before it writes P) | NS x 2 DH
+  // for O' (both positions' value columns; a row uses its own position's half)
   static constexpr uint32_t COL_S = 0, COL_P = 0, COL_O = NS * 128;
+  static_assert(NS * 128 + NS * 2 * DH <= 512, "tensor memory budget");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
@@ -186,7 +190,7 @@ attn_lists_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
   } else if (warp == 14) {
     // ------------------------------ MMA issuer 2: O = P . V ------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc_o = make_idesc(kFmtF16, 128, DH, false, false);
+      constexpr uint32_t idesc_o = make_idesc(kFmtF16, 128, 2 * DH, false, false);
       const uint32_t op_addr = smem_u32(sOp);
       long long my_super = 0;
       for (long long sp = blockIdx.x; sp < n_super; sp += gridDim.x) ++my_super;
@@ -198,15 +202,14 @@ attn_lists_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
         mbar_wait(&p_full[st], ph);
         if (d_) dbg[i * 16 + 4] = clock64();
         tc_fence_after();
-        const uint32_t vt = op_addr + st * OP_STRIDE + 2 * Cfg::QQ_BYTES;
+        // B = the two positions' V^T blocks as ONE [2 DH rows x 64 keys] K-major tile (they are adjacent 8-row-swizzled
+        // blocks of the stage); A = P' (32 packed columns); a tcgen05.mma costs its issuer the same ~100+ cycles at N = 16
+        // and N = 32, so halving the number of K steps halves this thread's time per item
+        const uint64_t db = make_smem_desc_sw128(op_addr + st * OP_STRIDE + 2 * Cfg::QQ_BYTES, 16, 1024);
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t db = make_smem_desc_sw128(vt + kb * (DH * 128), 16, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ts(tmem_base + Cfg::COL_O + st * DH, tmem_base + Cfg::COL_P + st * 128 + uint32_t(kb * 32 + k * 8),
-                        db + uint64_t(2 * k), idesc_o, (kb | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ts(tmem_base + Cfg::COL_O + st * (2 * DH), tmem_base + Cfg::COL_P + st * 128 + uint32_t(k * 8),
+                      db + uint64_t(2 * k), idesc_o, k != 0 ? 1u : 0u);
         umma_commit(&o_full[st]);
         umma_commit(&op_empty[st]);
         if (d_) dbg[i * 16 + 5] = clock64();
@@ -333,22 +336,16 @@ attn_lists_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
         // the score product of this item waited for)
         s_stat[st * Cfg::ROWS + r] = make_float2(m, sum);
         mbar_arrive(&stat_full[st]);
-        // P row: 128 keys = 64 packed columns; this row's position block holds pk, the other block zeros
+        // P' row: the 64 keys of this row's own position = 32 packed columns at the start of the stage's score columns
         {
-          uint32_t z16[16];
-#pragma unroll
-          for (int c = 0; c < 16; ++c) z16[c] = 0u;
           const uint32_t pbase = lane_tmem + Cfg::COL_P + st * 128;
-          const uint32_t mine = pbase + pos * 32, other = pbase + (pos ^ 1) * 32;
           uint32_t a16[16];
 #pragma unroll
           for (int c = 0; c < 16; ++c) a16[c] = pk[c];
-          tmem_st16(mine, a16);
+          tmem_st16(pbase, a16);
 #pragma unroll
           for (int c = 0; c < 16; ++c) a16[c] = pk[16 + c];
-          tmem_st16(mine + 16, a16);
-          tmem_st16(other, z16);
-          tmem_st16(other + 16, z16);
+          tmem_st16(pbase + 16, a16);
           tmem_st_wait();
         }
         tc_fence_before();
@@ -384,7 +381,7 @@ attn_lists_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
         mbar_wait(&o_full[st], ph);
         tc_fence_after();
         float ov[DH];
-        tmem_ld16(lane_tmem + Cfg::COL_O + st * DH, ov);
+        tmem_ld16(lane_tmem + Cfg::COL_O + st * (2 * DH) + pos * DH, ov);     // this row's position: its half of O'
         tc_fence_before();
         mbar_arrive(&t_empty[st]);                                   // S / P / O (and the statistics slot) of this stage are free
         if (d_) dbg[it * 16 + 15] = clock64();
