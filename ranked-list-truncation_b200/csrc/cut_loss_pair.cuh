@@ -15,40 +15,13 @@
 #pragma once
 #include <stdint.h>
 
+#include "f32x2.cuh"
+
 namespace rlt {
 
 // float32(1) / float32(log2(j + 2)): this translation unit's copy of heads.cu's table (uploaded by rlt_set_dcg_tables)
 __device__ __align__(16) float g_pair_rcoef32[1024];
 
-__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
-  unsigned long long x, y, z, r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(z) : "f"(c.x), "f"(c.y));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(y), "l"(z));
-  float2 o;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
-  return o;
-}
-__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
-  unsigned long long x, y, r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
-  float2 o;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
-  return o;
-}
-__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
-  unsigned long long x, y, r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
-  float2 o;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
-  return o;
-}
-__device__ __forceinline__ float2 f2_dup(float v) { return make_float2(v, v); }
 __device__ __forceinline__ float ex2_fast(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
