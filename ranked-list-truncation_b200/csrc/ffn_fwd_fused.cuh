@@ -21,8 +21,8 @@
 // measured L2 throughput at full tensor rate) and B-operand shared-memory reads are halved.  Putting H in tensor memory
 // takes the whole A operand of MMA2 (4 KB per MMA) off the shared-memory pipe.
 //
-// Tensor memory (512 columns per CTA): S double buffer 2 x CH | Z d | H double buffer 2 x CH/2  (d 128: CH 128 -> 512;
-// d 256: CH 64 -> 448).
+// Tensor memory (512 columns per CTA): d 256: S double buffer 2 x 64 | Z 256 | H double buffer 2 x 32 (448);
+// d 128: S TRIPLE buffer 3 x 128 with H_g written in place over the score columns its warp has read | Z 128 (512).
 // Shared memory: y16 tile(s) 128 x d fp16 | W1 ring 3 x 16 KB (half-chunks) | W2 ring 4 x 16 KB | b1 | b2, gamma, beta |
 // LayerNorm partials | 16 x 2 KB staging tiles of the saved hidden (TMA store) | barriers.
 // Warp roles per CTA: 0 TMA producer (both CTAs load their own halves; the bytes are counted on the LEADER's barriers),
@@ -73,14 +73,20 @@ struct FfnFwdCfg {
   static constexpr int OFF_RED = OFF_VEC + 3 * D * 4;            // [2][4 quarters][4 column quarters][32 lanes]
   static constexpr int OFF_STAGE = ((OFF_RED + 2 * 4 * 4 * 32 * 4 + 1023) / 1024) * 1024;   // per-warp [32 x 32] fp16 tiles of the saved hidden
   static constexpr int OFF_BARS = OFF_STAGE + EPI_WARPS * 2048;
-  static constexpr int N_BARS = 2 * NS1 + 2 * NS2 + 2 * YB + 4 + 4 + 2;
+  // d_model 128: H_g is written IN PLACE over the S_g columns its own warp has just read (the attention kernel does the
+  // same with P), which frees 128 tensor-memory columns for a THIRD S / H buffer: the per-buffer dependency loop
+  // MMA1_g -> bias / ReLU / pack -> MMA2_g -> MMA1_{g+NSB} (~2 900 cycles, measured with two buffers: 1 450 per chunk) is
+  // then shared by three chunks in flight instead of two.
+  static constexpr bool ALIAS_H = D == 128;
+  static constexpr int NSB = ALIAS_H ? 3 : 2;          // S (and H) buffers
+  static constexpr int N_BARS = 2 * NS1 + 2 * NS2 + 2 * YB + 4 * NSB + 2;
   static constexpr size_t SMEM_BYTES = 1024 + OFF_BARS + N_BARS * 8 + 16;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   // tensor memory columns
-  static constexpr uint32_t COL_S = 0;                 // 2 x CH
-  static constexpr uint32_t COL_Z = 2 * CH;            // D
-  static constexpr uint32_t COL_H = 2 * CH + D;        // 2 x CH/2
-  static_assert(COL_H + CH <= 512, "tensor memory budget");
+  static constexpr uint32_t COL_S = 0;                 // NSB x CH
+  static constexpr uint32_t COL_Z = NSB * CH;          // D
+  static constexpr uint32_t COL_H = 2 * CH + D;        // 2 x CH/2 (not ALIAS_H)
+  static_assert(ALIAS_H ? (COL_Z + D <= 512) : (COL_H + CH <= 512), "tensor memory budget");
 };
 
 struct FfnFwdParams {
@@ -122,11 +128,12 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
   uint64_t* w2_empty = w2_full + NS2;      // [NS2]  local: MMA2 of the chunk retired
   uint64_t* y_full = w2_empty + NS2;       // [YB]   leader
   uint64_t* y_empty = y_full + YB;         // [YB]   local: last MMA1 of the tile retired
-  uint64_t* s_full = y_empty + YB;         // [2]    local: S_j ready
-  uint64_t* s_empty = s_full + 2;          // [2]    leader: both CTAs' epilogues have S_j in registers (count 32)
-  uint64_t* h_full = s_empty + 2;          // [2]    leader: both CTAs' epilogues wrote H_j (count 32)
-  uint64_t* h_empty = h_full + 2;          // [2]    local: MMA2_j retired
-  uint64_t* z_full = h_empty + 2;          // local
+  constexpr int NSB = Cfg::NSB;
+  uint64_t* s_full = y_empty + YB;         // [NSB]  local: S_j ready
+  uint64_t* s_empty = s_full + NSB;        // [NSB]  leader: both CTAs' epilogues have S_j in registers (count 32; unused with ALIAS_H)
+  uint64_t* h_full = s_empty + NSB;        // [NSB]  leader: both CTAs' epilogues wrote H_j (count 32)
+  uint64_t* h_empty = h_full + NSB;        // [NSB]  local: MMA2_j retired (ALIAS_H: the S buffer may be rewritten)
+  uint64_t* z_full = h_empty + NSB;        // local
   uint64_t* z_empty = z_full + 1;          // leader (count 32)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::N_BARS);
 
@@ -145,7 +152,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       for (int s = 0; s < NS1; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 1); }
       for (int s = 0; s < NS2; ++s) { mbar_init(&w2_full[s], 1); mbar_init(&w2_empty[s], 1); }
       for (int s = 0; s < YB; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < NSB; ++s) {
         mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 2 * Cfg::EPI_WARPS);
         mbar_init(&h_full[s], 2 * Cfg::EPI_WARPS); mbar_init(&h_empty[s], 1);
       }
@@ -236,16 +243,17 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       const uint32_t y_addr = smem_u32(sY), w1_addr = smem_u32(sW1);
       const int my_tiles = pair < n_tiles ? (n_tiles - pair + n_pairs - 1) / n_pairs : 0;
       const uint32_t total = uint32_t(my_tiles) * uint32_t(n_chunks);
-      uint32_t st1 = 0, ph1 = 0, yb = 0, yph = 0;
+      uint32_t st1 = 0, ph1 = 0, yb = 0, yph = 0, sb1 = 0, sp1 = 0;
       int j = 0;
       for (uint32_t g = 0; g < total; ++g) {
-        const uint32_t buf1 = g & 1, u1 = (g >> 1) & 1;            // S buffer of chunk g
+        const uint32_t buf1 = sb1, u1 = sp1;                       // S buffer of chunk g (g % NSB, parity of g / NSB)
         const bool dbg = p.dbg != nullptr && pair == 0 && g < 64;
         if (dbg) p.dbg[g * 24 + 0] = clock64();
         if (j == 0) mbar_wait_cluster(&y_full[yb], yph);
         mbar_wait_cluster(&w1_full[st1], ph1);
         if (dbg) p.dbg[g * 24 + 18] = clock64();
-        mbar_wait_cluster(&s_empty[buf1], u1 ^ 1);
+        if constexpr (Cfg::ALIAS_H) mbar_wait_cluster(&h_empty[buf1], u1 ^ 1);   // H_{g-NSB} (inside this buffer) consumed by MMA2
+        else mbar_wait_cluster(&s_empty[buf1], u1 ^ 1);
         if (dbg) p.dbg[g * 24 + 1] = clock64();
         tc_fence_after();
         const uint32_t a1 = y_addr + yb * Cfg::Y_BYTES, b1a = w1_addr + st1 * Cfg::W1_BYTES;
@@ -259,6 +267,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
         }
         umma_commit_pair(&s_full[buf1]);
         umma_commit_pair(&w1_empty[st1]);
+        if (++sb1 == uint32_t(NSB)) { sb1 = 0; sp1 ^= 1; }
         if (j == n_chunks - 1) {
           umma_commit_pair(&y_empty[yb]);
           if (++yb == YB) { yb = 0; yph ^= 1; }
@@ -278,10 +287,10 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       const uint32_t w2_addr = smem_u32(sW2);
       const int my_tiles = pair < n_tiles ? (n_tiles - pair + n_pairs - 1) / n_pairs : 0;
       const uint32_t total = uint32_t(my_tiles) * uint32_t(n_chunks);
-      uint32_t st2 = 0, ph2 = 0, ztile = 0;
+      uint32_t st2 = 0, ph2 = 0, ztile = 0, sb2 = 0, sp2 = 0;
       int cj = 0;
       for (uint32_t c = 0; c < total; ++c) {
-        const uint32_t buf2 = c & 1, u2 = (c >> 1) & 1;            // H buffer of chunk c
+        const uint32_t buf2 = sb2, u2 = sp2;                       // H buffer of chunk c
         const bool dbg = p.dbg != nullptr && pair == 0 && c < 64;
         if (dbg) p.dbg[c * 24 + 4] = clock64();
         mbar_wait_cluster(&w2_full[st2], ph2);
@@ -292,16 +301,22 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
         if (dbg) p.dbg[c * 24 + 5] = clock64();
         tc_fence_after();
         const uint32_t b2a = w2_addr + st2 * Cfg::W2_BYTES;
-        const uint32_t a_t = tmem_base + Cfg::COL_H + buf2 * (CH / 2);
+        // A operand in tensor memory: H_c contiguous behind Z, or (ALIAS_H) the 16 packed columns at the start of every
+        // 32-column quarter of the S buffer -- K step ks = hidden units [16 ks, 16 ks + 16) = quarter ks / 2, half ks % 2
+        const uint32_t a_t = Cfg::ALIAS_H ? tmem_base + Cfg::COL_S + buf2 * CH : tmem_base + Cfg::COL_H + buf2 * (CH / 2);
 #pragma unroll
         for (int kb = 0; kb < CH / 64; ++kb) {
           const uint64_t db = make_smem_desc_sw128(b2a + kb * Cfg::W2_BOX_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ts_pair(tmem_base + Cfg::COL_Z, a_t + uint32_t(kb * 32 + k * 8), db + uint64_t(2 * k), idesc2, (cj | kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            const int ks = kb * 4 + k;
+            const uint32_t a_k = Cfg::ALIAS_H ? a_t + uint32_t((ks >> 1) * 32 + (ks & 1) * 8) : a_t + uint32_t(kb * 32 + k * 8);
+            umma_f16_ts_pair(tmem_base + Cfg::COL_Z, a_k, db + uint64_t(2 * k), idesc2, (cj | kb | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit_pair(&h_empty[buf2]);
         umma_commit_pair(&w2_empty[st2]);
+        if (++sb2 == uint32_t(NSB)) { sb2 = 0; sp2 ^= 1; }
         if (cj == n_chunks - 1) {
           umma_commit_pair(z_full);
           cj = 0;
@@ -321,19 +336,24 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
     const int cq = ew >> 2;                // column quarter
     const int r = quarter * 32 + lane;     // row inside this CTA's 128-row tile
     const uint32_t lane_tmem = tmem_base + (uint32_t(quarter * 32) << 16);
-    const uint32_t s_empty_r[2] = {mapa_u32(smem_u32(&s_empty[0]), 0), mapa_u32(smem_u32(&s_empty[1]), 0)};
-    const uint32_t h_full_r[2] = {mapa_u32(smem_u32(&h_full[0]), 0), mapa_u32(smem_u32(&h_full[1]), 0)};
+    uint32_t s_empty_r[NSB], h_full_r[NSB];
+#pragma unroll
+    for (int b = 0; b < NSB; ++b) {
+      s_empty_r[b] = mapa_u32(smem_u32(&s_empty[b]), 0);
+      h_full_r[b] = mapa_u32(smem_u32(&h_full[b]), 0);
+    }
     const uint32_t z_empty_r = mapa_u32(smem_u32(z_empty), 0);
     uint8_t* st_out = smem + Cfg::OFF_STAGE + ew * 2048;     // this warp's [32 rows x 32 columns] fp16 staging tile (SWIZZLE_64B)
     const int sw = (lane >> 1) & 3;                          // SWIZZLE_64B: 16-byte unit index ^= (row >> 1) & 3
     float* red0 = sRed + (quarter * 4) * 32;                 // [cq][lane] partial sums of this lane quarter
     float* red1 = sRed + 4 * 4 * 32 + (quarter * 4) * 32;
-    uint32_t g = 0, tt = 0;
+    uint32_t g = 0, tt = 0, sbe = 0, spe = 0;
     for (int tile = pair; tile < n_tiles; tile += n_pairs, ++tt) {
       const long long row = (long long)tile * 2 * Cfg::BM + (long long)rank * Cfg::BM + r;
       const bool live = row < p.T;
       for (int j = 0; j < n_chunks; ++j, ++g) {
-        const uint32_t buf = g & 1, u = (g >> 1) & 1;
+        const uint32_t buf = sbe, u = spe;
+        if (++sbe == uint32_t(NSB)) { sbe = 0; spe ^= 1; }
         const bool dbg = p.dbg != nullptr && pair == 0 && leader && ew == 0 && lane == 0 && g < 64;
         if (dbg) p.dbg[g * 24 + 8] = clock64();
         mbar_wait(&s_full[buf], u);
@@ -344,7 +364,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
         else tmem_ld16(lane_tmem + Cfg::COL_S + buf * CH + cq * SC, v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(s_empty_r[buf]);          // S_j is in registers
+        if (!Cfg::ALIAS_H && lane == 0) mbar_arrive_cluster(s_empty_r[buf]);          // S_j is in registers
         if (dbg) p.dbg[g * 24 + 10] = clock64();
         // ---- bias + relu + fp16 pack (two hidden units per 32-bit word = the TMEM A-operand layout): packed fp32x2
         // adds, one pack per pair, relu on the packed halves (max commutes with the rounding)
@@ -380,12 +400,15 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
           // landed and the fence costs nothing on the path MMA2 waits for)
         }
         if (dbg) p.dbg[g * 24 + 11] = clock64();
-        mbar_wait(&h_empty[buf], u ^ 1);        // MMA2 of chunk g - 2 has consumed this H buffer
+        // separate H buffers: MMA2 of chunk g - 2 has consumed this one.  ALIAS_H: H_g goes into the 16 packed columns at
+        // the start of this warp's own 32 score columns (it has them in registers; MMA1 rewrites the buffer only after
+        // MMA2_g has retired, which s_full of this chunk already implies for chunk g - NSB)
+        if constexpr (!Cfg::ALIAS_H) mbar_wait(&h_empty[buf], u ^ 1);
         if (dbg) p.dbg[g * 24 + 12] = clock64();
         tc_fence_after();
         if constexpr (SC == 32) {
           const uint32_t(&h16)[16] = hp;
-          tmem_st16(lane_tmem + Cfg::COL_H + buf * (CH / 2) + cq * (SC / 2), h16);
+          tmem_st16(Cfg::ALIAS_H ? lane_tmem + Cfg::COL_S + buf * CH + cq * SC : lane_tmem + Cfg::COL_H + buf * (CH / 2) + cq * (SC / 2), h16);
         } else {
           const uint32_t(&h8)[8] = hp;
           tmem_st8(lane_tmem + Cfg::COL_H + buf * (CH / 2) + cq * (SC / 2), h8);
