@@ -181,10 +181,11 @@ __global__ void __launch_bounds__(128) cut_loss_pair_kernel(const float* __restr
     }
   } else {
     // q = softmax(r / tau) over the L positions (losses.py:90-92, 226-228)
-    if (64 * NP > L) {
-      const int pj = lane + 32 * (NP - 1);
-      if (pj >= npair) r[NP - 1] = f2_dup(kNeg);
-    }
+    // positions >= L must not take part in q: L may be far below 64 NP (every L in (64, 320] runs NP = 5), so any slot
+    // from npair / 32 on can hold them -- a warp-uniform test per slot
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+      if (32 * (i + 1) > npair && lane + 32 * i >= npair) r[i] = f2_dup(kNeg);
     float rm = kNeg;
 #pragma unroll
     for (int i = 0; i < NP; ++i) rm = fmaxf(rm, fmaxf(r[i].x, r[i].y));

@@ -92,8 +92,18 @@ def test_cut_loss_odd_length_and_probability_input_keep_the_scalar_kernel():
             ref = (O.choopy_loss(p64, y64, metric) if lk == "choopy" else
                    O.attncut_loss(p64, y64, metric, tau) if lk == "raml" else O.div_loss(p64, y64, metric, tau, lk))
             assert abs(loss.item() - float(ref)) <= 2e-5 * max(1.0, abs(float(ref))), (kind, metric, loss.item(), float(ref))
-    # ... and an even length of another size class (NP = 8) through the packed kernel, floats and bit masks
-    L2 = 500
+    # ... and even lengths of every other size class of the packed kernel (NP = 8, 16, 1, the 64 / 66 boundary, and lengths that leave whole slots of NP = 5 empty),
+    # floats and bit masks
+    for L2 in (500, 1000, 64, 66, 100, 200, 258):
+        _packed_lengths(B, L2)
+    with pytest.raises(RuntimeError):
+        ops.cut_loss(z, None, label_bits=ops.pack_labels(y), loss_kind="js", metric="f1", tau=0.85,
+                     loss_per_list=torch.empty(B, device="cuda"))
+
+
+def _packed_lengths(B, L2):
+    from rlt_b200 import ops
+    torch.manual_seed(L2)
     z2 = torch.randn(B, L2, device="cuda")
     y2 = (torch.rand(B, L2, device="cuda") < 0.1).float()
     p2 = torch.softmax(z2.double().cpu(), dim=1)
@@ -107,9 +117,6 @@ def test_cut_loss_odd_length_and_probability_input_keep_the_scalar_kernel():
                 ops.cut_loss(z2, y2 if bits is None else None, label_bits=bits, loss_kind=lk, metric=metric, tau=tau,
                              loss_per_list=per, loss_out=loss, loss_scale=1.0 / B)
                 assert abs(loss.item() - float(ref)) <= 2e-5 * max(1.0, abs(float(ref))), (kind, metric, loss.item(), float(ref))
-    with pytest.raises(RuntimeError):
-        ops.cut_loss(z, None, label_bits=ops.pack_labels(y), loss_kind="js", metric="f1", tau=0.85,
-                     loss_per_list=torch.empty(B, device="cuda"))
 
 
 @pytest.mark.parametrize("L", [300, 40])
