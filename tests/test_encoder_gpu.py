@@ -220,3 +220,43 @@ def test_tcgen05_attention_forward_matches_the_mma_sync_path(S, L, G):
         # linear1.*); the 1e-3 contract is asserted on the model goldens
         scale = a.abs().max().item() + 1e-30 if n in ("out", "dx") else gmax
         assert e <= (3e-4 if n == "out" else 4e-2) * scale, (n, e, scale)
+
+
+@pytest.mark.parametrize("d", [128, 256])
+@pytest.mark.parametrize("f", [128, 256, 384, 640, 2048])
+@pytest.mark.parametrize("T", [1, 300, 5000, 70001])
+def test_fused_ffn_forward_hidden_widths_and_token_counts(d, f, T):
+    """rlt_ffn_fused_fwd on its own against a float64 evaluation with the same fp16-rounded operands, for hidden widths
+    of 1, 2, 3, 5 and 16 (d 128) / 2 ... 32 (d 256) chunks -- fewer chunks than S buffers, ring wrap-arounds at every
+    phase -- and token counts from one row to several tiles per CTA pair with a ragged last tile.  Both variants: forward
+    only, and with the hidden / pre-norm sums / statistics saved."""
+    from rlt_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(d + f + T)
+    y = torch.randn(T, d, device="cuda", generator=g)
+    w1 = torch.randn(f, d, device="cuda", generator=g) * d ** -0.5
+    w2 = torch.randn(d, f, device="cuda", generator=g) * f ** -0.5
+    b1 = torch.randn(f, device="cuda", generator=g) * 0.1
+    b2 = torch.randn(d, device="cuda", generator=g) * 0.1
+    gamma = 1 + 0.1 * torch.randn(d, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(d, device="cuda", generator=g)
+    y16, w1h, w2h = y.half(), w1.half().contiguous(), w2.half().contiguous()
+    n = min(T, 2048)
+    rows = torch.cat([torch.arange(n // 2), torch.arange(T - (n - n // 2), T)]).unique().cuda()      # first and last rows
+    hd = torch.relu(y16[rows].double() @ w1h.double().t() + b1.double()).half().double()
+    u = y[rows].double() + hd @ w2h.double().t() + b2.double()
+    ref = torch.nn.functional.layer_norm(u, (d,), gamma.double(), beta.double(), 1e-5)
+    out = torch.full((T, d), float("nan"), device="cuda")
+    ops.ffn_fused_fwd(y16, y, w1h, b1, w2h, b2, gamma, beta, out)
+    assert (out[rows].double() - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+    assert torch.isfinite(out).all()
+    out2 = torch.full((T, d), float("nan"), device="cuda")
+    u2 = torch.empty_like(y)
+    st = torch.empty(T, 2, device="cuda")
+    h = torch.empty(T, f, device="cuda", dtype=torch.float16)
+    ops.ffn_fused_fwd(y16, y, w1h, b1, w2h, b2, gamma, beta, out2, u2=u2, stats=st, h_out=h)
+    assert torch.equal(out, out2)                                             # the two variants run the same arithmetic
+    assert (h[rows].double() - hd).abs().max().item() <= 2e-3 * max(hd.abs().max().item(), 1.0)
+    assert (u2[rows].double() - u).abs().max().item() <= 2e-4 * u.abs().max().item()
+    mu, var = u.mean(1), u.var(1, unbiased=False)
+    assert (st[rows, 0].double() - mu).abs().max().item() <= 1e-4 * max(mu.abs().max().item(), 1.0)
+    assert (st[rows, 1].double() - (var + 1e-5).rsqrt()).abs().max().item() <= 1e-3 * (var + 1e-5).rsqrt().max().item()

@@ -169,7 +169,8 @@ def test_eval_cut_every_cut_position_and_ragged_batches():
     """Every k = 1..L (each leaf shape of numpy's pairwise tree: 1, 2, 3, 4 and 8 leaves, tails of 0..7 terms) at L = 300,
     500 and 1000, odd L through the scalar kernel, and batch sizes that leave warps / CTAs partly empty."""
     from rlt_b200 import ops
-    for L, B in ((300, 300), (500, 500), (1000, 1000), (301, 301), (300, 131), (40, 5)):
+    for L, B in ((300, 300), (500, 500), (1000, 1000), (301, 301), (300, 131), (40, 5), (66, 66), (100, 100), (258, 131),
+                 (600, 200)):     # ... and lengths that leave whole slots of a size class empty
         torch.manual_seed(L + B)
         y = (torch.rand(B, L, device="cuda") < 0.2).float()
         p = torch.rand(B, L, device="cuda") * 0.5
