@@ -102,21 +102,29 @@ def test_cut_loss_odd_length_and_probability_input_keep_the_scalar_kernel():
 
 
 def _packed_lengths(B, L2):
+    """Loss AND gradient of the packed kernel against float64 autograd through the oracle's criterion."""
     from rlt_b200 import ops
     torch.manual_seed(L2)
     z2 = torch.randn(B, L2, device="cuda")
     y2 = (torch.rand(B, L2, device="cuda") < 0.1).float()
-    p2 = torch.softmax(z2.double().cpu(), dim=1)
+    y64 = y2.cpu().double()
     for kind, (lk, tau) in KINDS.items():
         for metric in ("f1", "dcg"):
-            ref = (O.choopy_loss(p2, y2.cpu().double(), metric) if lk == "choopy" else
-                   O.attncut_loss(p2, y2.cpu().double(), metric, tau) if lk == "raml" else
-                   O.div_loss(p2, y2.cpu().double(), metric, tau, lk))
+            z64 = z2.double().cpu().requires_grad_(True)
+            p2 = torch.softmax(z64, dim=1)
+            ref = (O.choopy_loss(p2, y64, metric) if lk == "choopy" else
+                   O.attncut_loss(p2, y64, metric, tau) if lk == "raml" else O.div_loss(p2, y64, metric, tau, lk))
+            ref.backward()
+            gref = z64.grad
             for bits in (None, ops.pack_labels(y2)):
                 per, loss = torch.empty(B, device="cuda"), torch.empty((), device="cuda")
+                grad, probs = torch.empty_like(z2), torch.empty_like(z2)
                 ops.cut_loss(z2, y2 if bits is None else None, label_bits=bits, loss_kind=lk, metric=metric, tau=tau,
-                             loss_per_list=per, loss_out=loss, loss_scale=1.0 / B)
-                assert abs(loss.item() - float(ref)) <= 2e-5 * max(1.0, abs(float(ref))), (kind, metric, loss.item(), float(ref))
+                             probs_out=probs, grad=grad, loss_per_list=per, loss_out=loss, loss_scale=1.0 / B, grad_scale=1.0 / B)
+                assert abs(loss.item() - float(ref)) <= 2e-5 * max(1.0, abs(float(ref))), (kind, metric, L2, loss.item(), float(ref))
+                err = (grad.double().cpu() - gref).abs().max().item()
+                assert err <= 2e-4 * max(gref.abs().max().item(), 1e-6), (kind, metric, L2, err, gref.abs().max().item())
+                assert torch.allclose(probs.double().cpu(), p2.detach(), rtol=1e-5, atol=1e-9)
 
 
 @pytest.mark.parametrize("L", [300, 40])
